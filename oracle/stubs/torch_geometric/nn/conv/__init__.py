@@ -1,0 +1,1 @@
+from oracle.pyg import ChebConv, GCNConv, MessagePassing  # noqa: F401

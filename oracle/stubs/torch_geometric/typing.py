@@ -1,0 +1,3 @@
+from typing import Optional
+from torch import Tensor
+OptTensor = Optional[Tensor]
