@@ -1,0 +1,165 @@
+/*
+ * stmp.h -- C ABI of libstmp.so, the sm_100a spatiotemporal message-passing engine.
+ *
+ * The reference (benedekrozemberczki/pytorch_geometric_temporal @ adefe44) is pure Python and has no
+ * FFI layer: its hot path is `torch.nn.Module.forward` -> torch_geometric `MessagePassing.propagate`
+ * (index_select + scatter_add_) + ATen matmul/pointwise.  This header is therefore the boundary a
+ * maintainer would bind with ctypes from those modules (INTEGRATION.md shows the stub).  Each entry
+ * point cites the reference code it replaces, relative to /root/reference/torch_geometric_temporal/.
+ *
+ * Conventions
+ *  - plain C types only; all data pointers are DEVICE pointers unless a name ends in `_host`;
+ *  - tensors are fp32, row-major, indices int64 on input (torch LongTensor) and int32 inside a plan;
+ *  - every call enqueues on the caller's `stream` (a cudaStream_t passed as void*), never
+ *    synchronises the device and never allocates, except stmp_plan_create/destroy/export (setup path);
+ *  - return value: 0 = STMP_OK, otherwise an stmp_status code; the message is available from
+ *    stmp_last_error() (thread-local);
+ *  - entry points are re-entrant (autograd / DDP call backward from worker threads); a plan is
+ *    immutable after creation.
+ */
+#ifndef STMP_H_
+#define STMP_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct stmp_plan stmp_plan;
+
+enum stmp_status {
+  STMP_OK = 0,
+  STMP_EINVAL = 1,       /* bad argument (null pointer, negative size, unknown enum)  -> ValueError   */
+  STMP_ESHAPE = 2,       /* shape/stride/alignment the kernels cannot take            -> RuntimeError */
+  STMP_EGRAPH = 3,       /* edge_index out of range / duplicate edges where the reference would fail */
+  STMP_ECUDA = 4,        /* CUDA runtime error (message carries cudaGetErrorString)                   */
+  STMP_EUNSUPPORTED = 5, /* configuration does not fit the fused kernel; caller must use the tiled path */
+  STMP_ENOMEM = 6
+};
+
+/* Which normalised operator(s) a plan holds. */
+enum stmp_flavor {
+  /* DConv / BatchedDConv (nn/recurrent/dcrnn.py:59-77, :277-290): two operators,
+   *   op 0 "out": dst=col[e], src=row[e], val = 1/deg_out[row[e]]
+   *   op 1 "in" : p-th entry of the (col,row)-sorted reverse list: dst=row[q_p], src=col[q_p],
+   *               val = 1/deg_in[row[p]]   (positional pairing, quirk preserved)
+   * degrees are weighted sums; messages never multiply by edge_weight. */
+  STMP_FLAVOR_DCONV = 0,
+  /* PyG ChebConv.__norm__ (used by gconv_gru.py:57-107, gconv_lstm.py:62-138): scaled Laplacian
+   *   2L/lambda_max - I, self-loop entries appended after the non-loop edges. */
+  STMP_FLAVOR_CHEB = 1,
+  /* PyG gcn_norm (used by temporalgcn.py:38-68,162-173): D^-1/2 (A+I) D^-1/2 with remaining self loops. */
+  STMP_FLAVOR_GCN = 2,
+  /* ChebConvAttention.__norm__ (nn/attention/astgcn.py:82-110), propagated on the TRANSPOSED index
+   * (:167): dst=row', src=col', E'+2N entries. */
+  STMP_FLAVOR_CHEB_ATT = 3
+};
+
+enum stmp_norm { STMP_NORM_NONE = 0, STMP_NORM_SYM = 1, STMP_NORM_RW = 2 };
+
+enum stmp_plan_flags {
+  STMP_GCN_IMPROVED = 1u << 0,      /* GCNConv(improved=True): self-loop fill 2 instead of 1 */
+  STMP_GCN_NO_SELF_LOOPS = 1u << 1, /* GCNConv(add_self_loops=False) */
+  STMP_DCONV_ALLOW_DUPLICATES = 1u << 2 /* BatchedDConv semantics (scatter degrees, no dense adjacency):
+                                           duplicate edges are legal; DConv proper raises on them */
+};
+
+/* ---- plan ------------------------------------------------------------------------------------ */
+
+/* Build the cached operator(s) for a static graph on the device (stable radix sort to CSR by
+ * destination + CSR by source for the transposed/backward product, degree/Laplacian/GCN norms).
+ * Replaces the per-call renormalisation of dcrnn.py:59-77, PyG get_laplacian / gcn_norm and
+ * astgcn.py:82-110.  edge_index: int64 [2,E] row-major; edge_weight: [E] or NULL (=> ones).
+ * lambda_max: >0 to use it, <=0 / NaN => PyG default (CHEB: 2*max(w_hat); CHEB_ATT: 2.0).
+ * Setup path: allocates, and synchronises `stream` once to read validation flags. */
+int stmp_plan_create(int flavor, int64_t num_nodes, int64_t num_edges, const int64_t* edge_index,
+                     const float* edge_weight, int normalization, float lambda_max, uint32_t flags,
+                     void* stream, stmp_plan** out);
+void stmp_plan_destroy(stmp_plan* plan);
+
+/* Introspection (tests, bit-exact index parity): number of operators, nodes, entries of operator `op`. */
+int stmp_plan_num_ops(const stmp_plan* plan);
+int64_t stmp_plan_num_nodes(const stmp_plan* plan);
+int64_t stmp_plan_nnz(const stmp_plan* plan, int op);
+/* Copy operator `op` (transposed=0: CSR by destination; 1: CSR by source) into caller device buffers:
+ * rowptr[N+1], col[nnz], val[nnz], eid[nnz] (eid = position of the entry in the reference-order
+ * COO list, i.e. the order the reference's scatter_add_ visits it).  Any output may be NULL. */
+int stmp_plan_export(const stmp_plan* plan, int op, int transposed, int32_t* rowptr, int32_t* col,
+                     float* val, int32_t* eid, void* stream);
+
+/* ---- K1/K3: gather -> weighted scatter-add (SpMM) with fused Chebyshev axpby -------------------
+ * y[b,i,:] = alpha * sum_k val_k * x[b, col_k, :] + beta * z[b,i,:]        (z may be NULL)
+ * Replaces MessagePassing.propagate (x_j = index_select; norm*x_j; scatter_add_) at
+ * dcrnn.py:86-87,95-99,300-313, astgcn.py:169-175 and inside ChebConv/GCNConv, plus the
+ * `2*prop - T0` recurrence (dcrnn.py:96,100; astgcn.py:176).  Per destination the products are summed
+ * in the reference's edge order with separate multiply and add (no FMA), so results are bit-identical
+ * to the CPU scatter_add_ path.  x,y,z: [batch, N, f] with row strides ld* and batch strides bs*
+ * (elements).  att (nullable): [batch, N, N] spatial attention; the entry value becomes
+ * val * att[b, dst, src] (astgcn.py:156-157, first hop only).  transposed=1 applies A^T (backward). */
+int stmp_spmm(const stmp_plan* plan, int op, int transposed, int64_t batch, int64_t f,
+              const float* x, int64_t ldx, int64_t bsx, float* y, int64_t ldy, int64_t bsy,
+              float alpha, const float* z, int64_t ldz, int64_t bsz, float beta,
+              const float* att, void* stream);
+
+/* d(att)[b,dst,src] += val * <gy[b,dst,:], x[b,src,:]> for every entry of `op` (backward of the
+ * attention-weighted first hop, astgcn.py:156-170).  datt must be zero-initialised by the caller. */
+int stmp_spmm_att_grad(const stmp_plan* plan, int op, int64_t batch, int64_t f, const float* gy,
+                       int64_t ldg, int64_t bsg, const float* x, int64_t ldx, int64_t bsx, float* datt,
+                       void* stream);
+
+/* ---- K1-K5 fused: the DCRNN recurrence ---------------------------------------------------------
+ * For each window b: H_0 = h0[b] (or 0); for t in [0,T): H_t = DCRNN_cell(X[b,t], H_{t-1});
+ * out[b,t] = H_t.  One persistent CTA per window keeps graph, weights, [X|H] and both diffusion
+ * products in shared memory across all T steps.  Replaces BatchedDCRNN.forward (dcrnn.py:429-475)
+ * and, with B=T=1, DCRNN.forward (:194-219).  plan: STMP_FLAVOR_DCONV.
+ *   x: window b, step t starts at x + (win_start ? win_start[b] : b*x_bstride) ... see x_tstride:
+ *      addr = x + base_b + t*x_tstride, base_b = win_start ? win_start[b]*x_tstride : b*x_bstride
+ *      (win_start: int64 [B] device, index-batching over a resident series, signal/index_dataset.py:49-57)
+ *   w_z,w_r,w_h: DConv.weight [2,K,cin+cout,cout]; b_*: [cout] or NULL (dcrnn.py:26-37)
+ *   h0: [B,N,cout] or NULL; out: [B,T,N,cout]
+ *   stash (nullable): [B,T,3,N,cout] receives (Z,R,Htilde) per step for the backward pass.
+ * Returns STMP_EUNSUPPORTED when (N, nnz, cin, cout, K) do not fit the fused kernel. */
+int stmp_dcrnn_seq_fwd(const stmp_plan* plan, int64_t B, int64_t T, int64_t cin, int64_t cout, int64_t K,
+                       const float* x, const int64_t* win_start, int64_t x_bstride, int64_t x_tstride,
+                       const float* w_z, const float* w_r, const float* w_h, const float* b_z,
+                       const float* b_r, const float* b_h, const float* h0, float* out, float* stash,
+                       void* stream);
+/* 1 if stmp_dcrnn_seq_fwd can take this configuration on the current device, else 0. */
+int stmp_dcrnn_seq_supported(const stmp_plan* plan, int64_t cin, int64_t cout, int64_t K);
+
+/* ---- K5: gate epilogues for the tiled path -------------------------------------------------------
+ * GRU (dcrnn.py:172-192, gconv_gru.py:119-139, temporalgcn.py:82-102), n = number of elements:
+ *   stmp_gru_zr:   z = sigmoid(pz); r = sigmoid(pr); hr = h * r
+ *   stmp_gru_out:  ht = tanh(ph); hnew = z*h + (1-z)*ht
+ * LSTM with peepholes (gconv_lstm.py:168-202), rows x cout, w_c*, b_* are [cout]:
+ *   stmp_lstm_ifc: i = sig(pi + wci*c + bi); f = sig(pf + wcf*c + bf); t = tanh(pc + bc); cnew = f*c + i*t
+ *   stmp_lstm_oh:  o = sig(po + wco*cnew + bo); hnew = o * tanh(cnew)
+ */
+int stmp_gru_zr(int64_t n, const float* pz, const float* pr, const float* h, float* z, float* r, float* hr,
+                void* stream);
+int stmp_gru_out(int64_t n, const float* ph, const float* z, const float* h, float* ht, float* hnew,
+                 void* stream);
+int stmp_lstm_ifc(int64_t rows, int64_t cout, const float* pi, const float* pf, const float* pc,
+                  const float* c, const float* wci, const float* wcf, const float* bi, const float* bf,
+                  const float* bc, float* i, float* f, float* t, float* cnew, void* stream);
+int stmp_lstm_oh(int64_t rows, int64_t cout, const float* po, const float* cnew, const float* wco,
+                 const float* bo, float* o, float* hnew, void* stream);
+
+/* ---- K8: index-batching window gather -----------------------------------------------------------
+ * x[b] = series[start[b] : start[b]+h], y[b] = series[start[b]+h : start[b]+2h]   (index_dataset.py:49-57
+ * + DataLoader default collate), series [T_total, row_elems] resident on the device.  y may be NULL. */
+int stmp_window_gather(const float* series, int64_t t_total, int64_t row_elems, const int64_t* start,
+                       int64_t B, int64_t horizon, float* x, float* y, void* stream);
+
+/* ---- misc ---------------------------------------------------------------------------------------- */
+const char* stmp_last_error(void);
+/* "stmp <version> sm_100a" */
+const char* stmp_version(void);
+/* Number of kernels this library has launched in the calling process (bench.py's gpu_launches). */
+int64_t stmp_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STMP_H_ */

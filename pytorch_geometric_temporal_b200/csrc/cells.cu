@@ -1,0 +1,139 @@
+// cells.cu -- K5 gate epilogues for the tiled (large-graph) path and K8 window gather.
+// All HBM-bound elementwise kernels: float4-vectorised when the element count allows, grid-stride.
+#include "common.cuh"
+
+namespace stmp {
+namespace {
+
+constexpr int kT = 256;
+inline unsigned grid_for(long long n) {
+  long long b = (n + kT - 1) / kT;
+  if (b < 1) b = 1;
+  if (b > 148ll * 32) b = 148ll * 32;
+  return (unsigned)b;
+}
+
+__global__ void __launch_bounds__(kT) k_gru_zr(long long n, const float* __restrict__ pz, const float* __restrict__ pr,
+                                               const float* __restrict__ h, float* __restrict__ z, float* __restrict__ r,
+                                               float* __restrict__ hr) {
+  for (long long i = blockIdx.x * (long long)kT + threadIdx.x; i < n; i += (long long)gridDim.x * kT) {
+    float zv = sigmoidf_acc(pz[i]), rv = sigmoidf_acc(pr[i]);
+    z[i] = zv;
+    r[i] = rv;
+    hr[i] = h[i] * rv;
+  }
+}
+__global__ void __launch_bounds__(kT) k_gru_out(long long n, const float* __restrict__ ph, const float* __restrict__ z,
+                                                const float* __restrict__ h, float* __restrict__ ht, float* __restrict__ hnew) {
+  for (long long i = blockIdx.x * (long long)kT + threadIdx.x; i < n; i += (long long)gridDim.x * kT) {
+    float t = tanhf(ph[i]);
+    float zv = z[i];
+    if (ht) ht[i] = t;
+    hnew[i] = zv * h[i] + (1.0f - zv) * t;
+  }
+}
+__global__ void __launch_bounds__(kT) k_lstm_ifc(long long n, int cout, const float* __restrict__ pi, const float* __restrict__ pf,
+                                                 const float* __restrict__ pc, const float* __restrict__ c,
+                                                 const float* __restrict__ wci, const float* __restrict__ wcf,
+                                                 const float* __restrict__ bi, const float* __restrict__ bf,
+                                                 const float* __restrict__ bc, float* __restrict__ ig, float* __restrict__ fg,
+                                                 float* __restrict__ tg, float* __restrict__ cnew) {
+  for (long long i = blockIdx.x * (long long)kT + threadIdx.x; i < n; i += (long long)gridDim.x * kT) {
+    const int ch = (int)(i % cout);
+    const float cv = c[i];
+    // ((conv + w_c*C) + b): the reference adds the peephole then the bias (gconv_lstm.py:171-173)
+    const float iv = sigmoidf_acc(__fadd_rn(__fadd_rn(pi[i], __fmul_rn(wci[ch], cv)), bi[ch]));
+    const float fv = sigmoidf_acc(__fadd_rn(__fadd_rn(pf[i], __fmul_rn(wcf[ch], cv)), bf[ch]));
+    const float tv = tanhf(__fadd_rn(pc[i], bc[ch]));
+    if (ig) ig[i] = iv;
+    if (fg) fg[i] = fv;
+    if (tg) tg[i] = tv;
+    cnew[i] = __fadd_rn(__fmul_rn(fv, cv), __fmul_rn(iv, tv));
+  }
+}
+__global__ void __launch_bounds__(kT) k_lstm_oh(long long n, int cout, const float* __restrict__ po, const float* __restrict__ cnew,
+                                                const float* __restrict__ wco, const float* __restrict__ bo,
+                                                float* __restrict__ og, float* __restrict__ hnew) {
+  for (long long i = blockIdx.x * (long long)kT + threadIdx.x; i < n; i += (long long)gridDim.x * kT) {
+    const int ch = (int)(i % cout);
+    const float cv = cnew[i];
+    const float ov = sigmoidf_acc(__fadd_rn(__fadd_rn(po[i], __fmul_rn(wco[ch], cv)), bo[ch]));
+    if (og) og[i] = ov;
+    hnew[i] = ov * tanhf(cv);
+  }
+}
+
+// x[b, t, :] = series[start[b] + t, :]  for t in [0,h);  y[b, t, :] = series[start[b] + h + t, :]
+template <typename V>
+__global__ void __launch_bounds__(kT) k_window_gather(const V* __restrict__ series, long long row_v, const long long* __restrict__ start,
+                                                      long long B, int h, V* __restrict__ x, V* __restrict__ y) {
+  const long long per = (long long)h * row_v;
+  const long long total = B * per * (y ? 2 : 1);
+  for (long long i = blockIdx.x * (long long)kT + threadIdx.x; i < total; i += (long long)gridDim.x * kT) {
+    const long long half = i / (B * per);
+    const long long j = i - half * B * per;
+    const long long b = j / per, o = j - b * per;
+    const V v = series[(start[b] + half * h) * row_v + o];
+    (half ? y : x)[j] = v;
+  }
+}
+
+}  // namespace
+}  // namespace stmp
+
+using namespace stmp;
+
+extern "C" int stmp_gru_zr(int64_t n, const float* pz, const float* pr, const float* h, float* z, float* r, float* hr,
+                           void* stream) {
+  STMP_REQUIRE(n >= 0 && pz && pr && h && z && r && hr, STMP_EINVAL, "stmp_gru_zr: bad argument");
+  if (n == 0) return STMP_OK;
+  k_gru_zr<<<grid_for(n), kT, 0, (cudaStream_t)stream>>>(n, pz, pr, h, z, r, hr);
+  STMP_LAUNCH_OK("k_gru_zr");
+  return STMP_OK;
+}
+extern "C" int stmp_gru_out(int64_t n, const float* ph, const float* z, const float* h, float* ht, float* hnew,
+                            void* stream) {
+  STMP_REQUIRE(n >= 0 && ph && z && h && hnew, STMP_EINVAL, "stmp_gru_out: bad argument");
+  if (n == 0) return STMP_OK;
+  k_gru_out<<<grid_for(n), kT, 0, (cudaStream_t)stream>>>(n, ph, z, h, ht, hnew);
+  STMP_LAUNCH_OK("k_gru_out");
+  return STMP_OK;
+}
+extern "C" int stmp_lstm_ifc(int64_t rows, int64_t cout, const float* pi, const float* pf, const float* pc, const float* c,
+                             const float* wci, const float* wcf, const float* bi, const float* bf, const float* bc,
+                             float* i, float* f, float* t, float* cnew, void* stream) {
+  STMP_REQUIRE(rows >= 0 && cout > 0 && pi && pf && pc && c && wci && wcf && bi && bf && bc && cnew, STMP_EINVAL,
+               "stmp_lstm_ifc: bad argument");
+  if (rows == 0) return STMP_OK;
+  k_lstm_ifc<<<grid_for(rows * cout), kT, 0, (cudaStream_t)stream>>>(rows * cout, (int)cout, pi, pf, pc, c, wci, wcf, bi,
+                                                                      bf, bc, i, f, t, cnew);
+  STMP_LAUNCH_OK("k_lstm_ifc");
+  return STMP_OK;
+}
+extern "C" int stmp_lstm_oh(int64_t rows, int64_t cout, const float* po, const float* cnew, const float* wco,
+                            const float* bo, float* o, float* hnew, void* stream) {
+  STMP_REQUIRE(rows >= 0 && cout > 0 && po && cnew && wco && bo && hnew, STMP_EINVAL, "stmp_lstm_oh: bad argument");
+  if (rows == 0) return STMP_OK;
+  k_lstm_oh<<<grid_for(rows * cout), kT, 0, (cudaStream_t)stream>>>(rows * cout, (int)cout, po, cnew, wco, bo, o, hnew);
+  STMP_LAUNCH_OK("k_lstm_oh");
+  return STMP_OK;
+}
+extern "C" int stmp_window_gather(const float* series, int64_t t_total, int64_t row_elems, const int64_t* start, int64_t B,
+                                  int64_t horizon, float* x, float* y, void* stream) {
+  STMP_REQUIRE(series && start && x, STMP_EINVAL, "stmp_window_gather: NULL pointer");
+  STMP_REQUIRE(B >= 0 && horizon > 0 && row_elems > 0 && t_total >= (y ? 2 : 1) * horizon, STMP_EINVAL,
+               "stmp_window_gather: bad sizes");
+  if (B == 0) return STMP_OK;
+  const long long total = B * horizon * row_elems * (y ? 2 : 1);
+  auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (row_elems % 4 == 0 && al(series) && al(x) && (!y || al(y))) {
+    k_window_gather<float4><<<grid_for(total / 4), kT, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(series), row_elems / 4, (const long long*)start, B, (int)horizon,
+        reinterpret_cast<float4*>(x), reinterpret_cast<float4*>(y));
+  } else {
+    k_window_gather<float><<<grid_for(total), kT, 0, (cudaStream_t)stream>>>(series, row_elems, (const long long*)start, B,
+                                                                              (int)horizon, x, y);
+  }
+  STMP_LAUNCH_OK("k_window_gather");
+  return STMP_OK;
+}

@@ -1,0 +1,130 @@
+// common.cuh -- shared helpers for libstmp (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+
+#include "../../include/stmp.h"
+
+namespace stmp {
+
+// ---- error reporting (thread-local, no exceptions across the C ABI) ---------------------------------
+char* err_buf();
+int set_error(int code, const char* fmt, ...);
+extern std::atomic<long long> g_launches;
+inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+#define STMP_CUDA_OK(expr)                                                                    \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess)                                                                    \
+      return stmp::set_error(STMP_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                             __FILE__, __LINE__);                                             \
+  } while (0)
+
+#define STMP_LAUNCH_OK(name)                                                                  \
+  do {                                                                                        \
+    cudaError_t _e = cudaGetLastError();                                                      \
+    if (_e != cudaSuccess)                                                                    \
+      return stmp::set_error(STMP_ECUDA, "launch of %s failed: %s", name, cudaGetErrorString(_e)); \
+    stmp::count_launch();                                                                     \
+  } while (0)
+
+#define STMP_REQUIRE(cond, code, ...)                      \
+  do {                                                     \
+    if (!(cond)) return stmp::set_error(code, __VA_ARGS__); \
+  } while (0)
+
+// ---- plan layout -------------------------------------------------------------------------------------
+// One sparse operator in CSR form.  `cv[k]` packs (column index, value bits) so one 64-bit load
+// fetches an edge.  Entries of a row keep the reference's scatter order (stable sort).
+struct Csr {
+  int n = 0;
+  int nnz = 0;
+  int max_row_nnz = 0;
+  int* rowptr = nullptr;  // [n+1]
+  int2* cv = nullptr;     // [nnz] (col, __float_as_int(val))
+  int* eid = nullptr;     // [nnz] position in the reference-order COO list
+};
+
+}  // namespace stmp
+
+struct stmp_plan {
+  int flavor = 0;
+  int n = 0;
+  long long e = 0;
+  int n_ops = 0;
+  int normalization = 0;
+  unsigned flags = 0;
+  float lambda_max = 0.f;
+  stmp::Csr fwd[2];  // by destination
+  stmp::Csr bwd[2];  // by source (transposed product)
+  int device = 0;
+};
+
+namespace stmp {
+
+__host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// ---- small PTX wrappers (sm_100a) ---------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+// TMA 1-D bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP).
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// TMA 1-D bulk copy shared -> global (bulk async-group completion).
+__device__ __forceinline__ void tma_bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem),
+               "r"(smem_u32(src_smem)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void tma_store_wait() {
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+
+__device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+}  // namespace stmp

@@ -1,0 +1,431 @@
+// dcrnn_seq.cu -- K1..K5 fused: the whole DCRNN recurrence of one window in one persistent CTA.
+//
+// Reference path replaced: BatchedDCRNN.forward (nn/recurrent/dcrnn.py:429-475) = Python loop over T of
+// 3 x BatchedDConv (:258-325) + gates (:398-427); with B=T=1 it is DCRNN.forward (:194-219).
+//
+// Design (sm_100a):
+//  * grid = min(B, #SM) persistent CTAs; CTA b owns window b, b+grid, ...  Everything a window needs
+//    lives in shared memory for all T steps: both diffusion operators (CSR, (col,val) packed 8 B/edge),
+//    the three gates' weights, and the basis matrix S[N][NB*CP] = [U | P_o U | P_i U | ...] whose block 0
+//    is U = [H | X_t].  HBM traffic per window is the compulsory minimum: read X window once, write H_t.
+//  * X windows arrive by TMA 1-D bulk copies (cp.async.bulk -> mbarrier), double buffered: the next
+//    window's X streams in while the current one computes.
+//  * gather/scatter: a half-warp owns one (destination row, operator); lanes are float4-vectorised along
+//    the feature axis; per-destination accumulation is in registers in CSR order (no atomics).
+//  * z and r share the diffusion of [X|H] (the reference recomputes it per gate); only the H*R columns
+//    are re-diffused for the candidate.
+//  * contraction S @ [Wz|Wr] and S @ Wh in exact fp32 FFMA (strict-parity mode): warp w owns output
+//    channels 4w..4w+3 of every gate, lane l owns rows l, l+32, ...; A rows are read as float4 along K
+//    with LD/4 odd => conflict-free LDS.128; B is a warp-uniform broadcast.  The gate epilogue
+//    (sigmoid/tanh/Hadamard/convex combine) runs on the accumulators in registers.
+#include "common.cuh"
+
+namespace stmp {
+namespace {
+
+constexpr int kMaxSmem = 232448;  // 227 KB opt-in limit per CTA on sm_100
+
+struct DcrnnParams {
+  int N, CIN, K, T;
+  long long B;
+  int CP, NB, LD;
+  const int* rowptr[2];
+  const int2* cv[2];
+  int nnz[2];
+  const float* x;
+  const long long* win_start;
+  long long x_bstride, x_tstride;
+  const float* w[3];
+  const float* bias[3];
+  const float* h0;
+  float* out;
+  float* stash;
+  int off_S, off_W, off_bias, off_rowptr[2], off_cv[2], off_x[2], off_bar;
+  int x_floats;  // T*N*CIN
+  int use_tma;
+};
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+// One diffusion hop for every (row, op): dst block = 2*P_op*src - U (hop>=2) or P_op*src (hop 1).
+// LPR lanes per row, lane j handles float4 j of the CP-wide block; jmax = number of active float4s.
+template <int LPR>
+__device__ __forceinline__ void diffuse(float* S, const int* const* rowptr, const int2* const* cv, int N, int LD, int CP,
+                                        int hop, int jmax, int tid, int nthreads) {
+  const int j = tid & (LPR - 1);
+  const int group = tid / LPR;
+  const int ngroups = nthreads / LPR;
+  for (int task = group; task < 2 * N; task += ngroups) {
+    const int op = task >= N ? 1 : 0;
+    const int i = task - op * N;
+    const int sb = (hop == 1) ? 0 : (1 + 2 * (hop - 2) + op);
+    const int db = 1 + 2 * (hop - 1) + op;
+    const int* rp = rowptr[op];
+    const int2* ce = cv[op];
+    const int beg = rp[i], end = rp[i + 1];
+    if (j < jmax) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float* src = S + sb * CP + 4 * j;
+      int k = beg;
+      for (; k + 2 <= end; k += 2) {
+        int2 e0 = ce[k], e1 = ce[k + 1];
+        float4 x0 = ld4(src + e0.x * LD);
+        float4 x1 = ld4(src + e1.x * LD);
+        float w0 = __int_as_float(e0.y), w1 = __int_as_float(e1.y);
+        acc.x = fmaf(w0, x0.x, acc.x); acc.y = fmaf(w0, x0.y, acc.y); acc.z = fmaf(w0, x0.z, acc.z); acc.w = fmaf(w0, x0.w, acc.w);
+        acc.x = fmaf(w1, x1.x, acc.x); acc.y = fmaf(w1, x1.y, acc.y); acc.z = fmaf(w1, x1.z, acc.z); acc.w = fmaf(w1, x1.w, acc.w);
+      }
+      if (k < end) {
+        int2 e0 = ce[k];
+        float4 x0 = ld4(src + e0.x * LD);
+        float w0 = __int_as_float(e0.y);
+        acc.x = fmaf(w0, x0.x, acc.x); acc.y = fmaf(w0, x0.y, acc.y); acc.z = fmaf(w0, x0.z, acc.z); acc.w = fmaf(w0, x0.w, acc.w);
+      }
+      if (hop >= 2) {  // T_k = 2 P T_{k-1} - X : the reference never advances Tx_0 past X (dcrnn.py:80,106)
+        float4 u = ld4(S + i * LD + 4 * j);
+        acc.x = 2.0f * acc.x - u.x; acc.y = 2.0f * acc.y - u.y; acc.z = 2.0f * acc.z - u.z; acc.w = 2.0f * acc.w - u.w;
+      }
+      st4(S + i * LD + db * CP + 4 * j, acc);
+    }
+  }
+}
+
+template <int OUT, int RT>
+__global__ void __launch_bounds__(OUT * 8, 1) k_dcrnn_seq(const DcrnnParams p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  constexpr int NT = OUT * 8;
+  constexpr int WLD = 3 * OUT;
+  constexpr int LPR = (OUT + 4) / 4 <= 8 ? 8 : ((OUT + 4) / 4 <= 16 ? 16 : 32);
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int N = p.N, CIN = p.CIN, K = p.K, T = p.T, CP = p.CP, LD = p.LD;
+  const int C = OUT + CIN;
+
+  float* S = reinterpret_cast<float*>(smem + p.off_S);
+  float* W = reinterpret_cast<float*>(smem + p.off_W);
+  float* Bs = reinterpret_cast<float*>(smem + p.off_bias);
+  int* s_rowptr[2] = {reinterpret_cast<int*>(smem + p.off_rowptr[0]), reinterpret_cast<int*>(smem + p.off_rowptr[1])};
+  int2* s_cv[2] = {reinterpret_cast<int2*>(smem + p.off_cv[0]), reinterpret_cast<int2*>(smem + p.off_cv[1])};
+  float* xbuf[2] = {reinterpret_cast<float*>(smem + p.off_x[0]), reinterpret_cast<float*>(smem + p.off_x[1])};
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.off_bar);
+
+  const long long b_first = blockIdx.x;
+  if (b_first >= p.B) return;
+  const uint32_t x_bytes = (uint32_t)p.x_floats * 4u;
+  auto x_base = [&](long long b) -> const float* {
+    return p.x + (p.win_start ? p.win_start[b] * p.x_tstride : b * p.x_bstride);
+  };
+
+  // ---- one-time per CTA: barriers, first TMA, graph, weights, zero S --------------------------------
+  if (p.use_tma && tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    fence_mbar_init();
+    mbar_arrive_expect_tx(&bars[0], x_bytes);
+    tma_bulk_g2s(xbuf[0], x_base(b_first), x_bytes, &bars[0]);
+  }
+  for (int op = 0; op < 2; ++op) {
+    for (int i = tid; i <= N; i += NT) s_rowptr[op][i] = p.rowptr[op][i];
+    for (int i = tid; i < p.nnz[op]; i += NT) s_cv[op][i] = p.cv[op][i];
+  }
+  // weights -> Wcat[kidx][z|r|h], internal channel order [H(OUT) | X(CIN) | pad], block 0 = W[0,0]+W[1,0]
+  for (int idx = tid; idx < LD * WLD; idx += NT) {
+    const int kidx = idx / WLD, col = idx - kidx * WLD;
+    const int g = col / OUT, o = col - g * OUT;
+    const int blk = kidx / CP, ci = kidx - blk * CP;
+    float v = 0.f;
+    if (ci < C) {
+      const int ch = ci < OUT ? CIN + ci : ci - OUT;
+      const float* wg = p.w[g];
+      if (blk == 0) {
+        v = wg[((0 * K + 0) * C + ch) * OUT + o] + wg[((1 * K + 0) * C + ch) * OUT + o];
+      } else {
+        const int hop = (blk - 1) / 2 + 1, d = (blk - 1) & 1;
+        v = wg[((d * K + hop) * C + ch) * OUT + o];
+      }
+    }
+    W[idx] = v;
+  }
+  for (int idx = tid; idx < WLD; idx += NT) {
+    const int g = idx / OUT;
+    Bs[idx] = p.bias[g] ? p.bias[g][idx - g * OUT] : 0.f;
+  }
+  for (int idx = tid; idx < N * LD; idx += NT) S[idx] = 0.f;
+  __syncthreads();
+
+  const int c0 = warp * 4;
+  int rows[RT];
+  const float* Srow[RT];
+#pragma unroll
+  for (int i = 0; i < RT; ++i) {
+    rows[i] = lane + 32 * i;
+    Srow[i] = S + (rows[i] < N ? rows[i] : N - 1) * LD;
+  }
+  const int KG = LD / 4;
+  uint32_t phase[2] = {0u, 0u};
+  int it = 0;
+
+  for (long long b = b_first; b < p.B; b += gridDim.x, ++it) {
+    const int buf = it & 1;
+    const float* xw;
+    if (p.use_tma) {
+      mbar_wait(&bars[buf], phase[buf]);
+      phase[buf] ^= 1u;
+      const long long bn = b + gridDim.x;
+      if (tid == 0 && bn < p.B) {  // stream the next window in while this one computes
+        fence_proxy_async();
+        mbar_arrive_expect_tx(&bars[buf ^ 1], x_bytes);
+        tma_bulk_g2s(xbuf[buf ^ 1], x_base(bn), x_bytes, &bars[buf ^ 1]);
+      }
+      xw = xbuf[buf];
+    } else {
+      const float* xb = x_base(b);
+      for (int t = 0; t < T; ++t)
+        for (int idx = tid; idx < N * CIN; idx += NT) xbuf[0][t * N * CIN + idx] = __ldg(xb + t * p.x_tstride + idx);
+      xw = xbuf[0];
+    }
+    // H_0 and X_0 into block 0
+    for (int idx = tid; idx < N * OUT; idx += NT) {
+      const int n = idx / OUT, c = idx - n * OUT;
+      S[n * LD + c] = p.h0 ? __ldg(p.h0 + (b * N + n) * OUT + c) : 0.f;
+    }
+    __syncthreads();  // (non-TMA path: xbuf visible)
+    for (int idx = tid; idx < N * CIN; idx += NT) {
+      const int n = idx / CIN, c = idx - n * CIN;
+      S[n * LD + OUT + c] = xw[idx];
+    }
+    __syncthreads();
+
+    for (int t = 0; t < T; ++t) {
+      // ---- round 1: diffuse U = [H | X_t] ------------------------------------------------------------
+      for (int hop = 1; hop < K; ++hop) {
+        diffuse<LPR>(S, s_rowptr, s_cv, N, LD, CP, hop, CP / 4, tid, NT);
+        __syncthreads();
+      }
+      // ---- GEMM 1: [z|r] pre-activations -------------------------------------------------------------
+      float accz[RT][4], accr[RT][4];
+#pragma unroll
+      for (int i = 0; i < RT; ++i)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { accz[i][c] = 0.f; accr[i][c] = 0.f; }
+#pragma unroll 1
+      for (int kg = 0; kg < KG; ++kg) {
+        float4 a[RT];
+#pragma unroll
+        for (int i = 0; i < RT; ++i) a[i] = ld4(Srow[i] + 4 * kg);
+        const float* wrow = W + (4 * kg) * WLD + c0;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const float4 bz = ld4(wrow + kk * WLD);
+          const float4 br = ld4(wrow + kk * WLD + OUT);
+#pragma unroll
+          for (int i = 0; i < RT; ++i) {
+            const float av = kk == 0 ? a[i].x : (kk == 1 ? a[i].y : (kk == 2 ? a[i].z : a[i].w));
+            accz[i][0] = fmaf(av, bz.x, accz[i][0]); accz[i][1] = fmaf(av, bz.y, accz[i][1]);
+            accz[i][2] = fmaf(av, bz.z, accz[i][2]); accz[i][3] = fmaf(av, bz.w, accz[i][3]);
+            accr[i][0] = fmaf(av, br.x, accr[i][0]); accr[i][1] = fmaf(av, br.y, accr[i][1]);
+            accr[i][2] = fmaf(av, br.z, accr[i][2]); accr[i][3] = fmaf(av, br.w, accr[i][3]);
+          }
+        }
+      }
+      // gates; keep Z and H in registers, R only lives long enough to form H*R
+      float hreg[RT][4];
+      {
+        const float4 bz = ld4(Bs + c0), br = ld4(Bs + OUT + c0);
+        const float bzv[4] = {bz.x, bz.y, bz.z, bz.w}, brv[4] = {br.x, br.y, br.z, br.w};
+#pragma unroll
+        for (int i = 0; i < RT; ++i) {
+          const float4 h = ld4(Srow[i] + c0);
+          hreg[i][0] = h.x; hreg[i][1] = h.y; hreg[i][2] = h.z; hreg[i][3] = h.w;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            accz[i][c] = sigmoidf_acc(accz[i][c] + bzv[c]);
+            accr[i][c] = sigmoidf_acc(accr[i][c] + brv[c]);
+          }
+        }
+      }
+      __syncthreads();  // every warp is done reading block 0 as the GEMM A operand
+      const long long obase = (b * T + t) * (long long)N;
+#pragma unroll
+      for (int i = 0; i < RT; ++i) {
+        if (rows[i] < N) {
+          st4(S + rows[i] * LD + c0, make_float4(hreg[i][0] * accr[i][0], hreg[i][1] * accr[i][1],
+                                                 hreg[i][2] * accr[i][2], hreg[i][3] * accr[i][3]));
+          if (p.stash) {
+            float* sp = p.stash + ((obase * 3) + 0 * (long long)N + rows[i]) * OUT + c0;
+            st4(sp, make_float4(accz[i][0], accz[i][1], accz[i][2], accz[i][3]));
+            st4(sp + (long long)N * OUT, make_float4(accr[i][0], accr[i][1], accr[i][2], accr[i][3]));
+          }
+        }
+      }
+      __syncthreads();
+      // ---- round 2: re-diffuse only the H*R columns ---------------------------------------------------
+      for (int hop = 1; hop < K; ++hop) {
+        diffuse<LPR>(S, s_rowptr, s_cv, N, LD, CP, hop, OUT / 4, tid, NT);
+        __syncthreads();
+      }
+      // ---- GEMM 2: candidate --------------------------------------------------------------------------
+      float acch[RT][4];
+#pragma unroll
+      for (int i = 0; i < RT; ++i)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acch[i][c] = 0.f;
+#pragma unroll 1
+      for (int kg = 0; kg < KG; ++kg) {
+        float4 a[RT];
+#pragma unroll
+        for (int i = 0; i < RT; ++i) a[i] = ld4(Srow[i] + 4 * kg);
+        const float* wrow = W + (4 * kg) * WLD + 2 * OUT + c0;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const float4 bh = ld4(wrow + kk * WLD);
+#pragma unroll
+          for (int i = 0; i < RT; ++i) {
+            const float av = kk == 0 ? a[i].x : (kk == 1 ? a[i].y : (kk == 2 ? a[i].z : a[i].w));
+            acch[i][0] = fmaf(av, bh.x, acch[i][0]); acch[i][1] = fmaf(av, bh.y, acch[i][1]);
+            acch[i][2] = fmaf(av, bh.z, acch[i][2]); acch[i][3] = fmaf(av, bh.w, acch[i][3]);
+          }
+        }
+      }
+      __syncthreads();  // all reads of S for this step are done
+      {
+        const float4 bh = ld4(Bs + 2 * OUT + c0);
+        const float bhv[4] = {bh.x, bh.y, bh.z, bh.w};
+#pragma unroll
+        for (int i = 0; i < RT; ++i) {
+          if (rows[i] < N) {
+            float hn[4], ht[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              ht[c] = tanhf(acch[i][c] + bhv[c]);
+              hn[c] = accz[i][c] * hreg[i][c] + (1.0f - accz[i][c]) * ht[c];  // dcrnn.py:190-192
+            }
+            const float4 hv = make_float4(hn[0], hn[1], hn[2], hn[3]);
+            st4(S + rows[i] * LD + c0, hv);
+            st4(p.out + (obase + rows[i]) * OUT + c0, hv);
+            if (p.stash) st4(p.stash + ((obase * 3) + 2 * (long long)N + rows[i]) * OUT + c0, make_float4(ht[0], ht[1], ht[2], ht[3]));
+          }
+        }
+      }
+      if (t + 1 < T) {
+        const float* xt = xw + (t + 1) * N * CIN;
+        for (int idx = tid; idx < N * CIN; idx += NT) {
+          const int n = idx / CIN, c = idx - n * CIN;
+          S[n * LD + OUT + c] = xt[idx];
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+struct Layout {
+  DcrnnParams p;
+  int smem_bytes;
+};
+
+inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
+
+// Fills the shape-derived fields and the shared-memory carve-up; returns false if it cannot fit.
+bool make_layout(const stmp_plan* plan, int cin, int cout, int K, int T, Layout* L) {
+  DcrnnParams& p = L->p;
+  p.N = plan->n; p.CIN = cin; p.K = K; p.T = T;
+  p.CP = align_up(cout + cin, 4);
+  p.NB = 2 * K - 1;
+  p.LD = p.NB * p.CP;
+  int off = 0;
+  p.off_S = off; off += align_up(p.N * p.LD * 4, 128);
+  p.off_W = off; off += align_up(p.LD * 3 * cout * 4, 128);
+  p.off_bias = off; off += align_up(3 * cout * 4, 128);
+  for (int op = 0; op < 2; ++op) { p.off_rowptr[op] = off; off += align_up((p.N + 1) * 4, 16); }
+  for (int op = 0; op < 2; ++op) { p.off_cv[op] = off; off += align_up((plan->fwd[op].nnz > 0 ? plan->fwd[op].nnz : 1) * 8, 16); }
+  off = align_up(off, 128);
+  p.x_floats = T * p.N * cin;
+  for (int i = 0; i < 2; ++i) { p.off_x[i] = off; off += align_up(p.x_floats * 4, 128); }
+  p.off_bar = off; off += 16;
+  L->smem_bytes = off;
+  return off <= kMaxSmem;
+}
+
+template <int OUT, int RT>
+int launch(const Layout& L, int grid, cudaStream_t st) {
+  auto kern = k_dcrnn_seq<OUT, RT>;
+  STMP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.smem_bytes));
+  kern<<<grid, OUT * 8, L.smem_bytes, st>>>(L.p);
+  STMP_LAUNCH_OK("k_dcrnn_seq");
+  return STMP_OK;
+}
+
+template <int OUT>
+int launch_rt(const Layout& L, int grid, cudaStream_t st) {
+  const int need = (L.p.N + 31) / 32;
+  if (need <= 1) return launch<OUT, 1>(L, grid, st);
+  if (need <= 2) return launch<OUT, 2>(L, grid, st);
+  if (need <= 4) return launch<OUT, 4>(L, grid, st);
+  if (need <= 7) return launch<OUT, 7>(L, grid, st);
+  return set_error(STMP_EUNSUPPORTED, "fused DCRNN kernel: N=%d exceeds 224 rows", L.p.N);
+}
+
+bool shape_ok(const stmp_plan* plan, int64_t cin, int64_t cout, int64_t K) {
+  if (!plan || plan->flavor != STMP_FLAVOR_DCONV || plan->n_ops != 2) return false;
+  if (!(cout == 16 || cout == 32)) return false;
+  if (cin < 1 || cin > 4 || K < 1 || K > 4) return false;
+  if (plan->n > 224) return false;
+  return true;
+}
+
+}  // namespace
+}  // namespace stmp
+
+using namespace stmp;
+
+extern "C" int stmp_dcrnn_seq_supported(const stmp_plan* plan, int64_t cin, int64_t cout, int64_t K) {
+  if (!shape_ok(plan, cin, cout, K)) return 0;
+  Layout L;
+  return make_layout(plan, (int)cin, (int)cout, (int)K, 12, &L) ? 1 : 0;
+}
+
+extern "C" int stmp_dcrnn_seq_fwd(const stmp_plan* plan, int64_t B, int64_t T, int64_t cin, int64_t cout, int64_t K,
+                                  const float* x, const int64_t* win_start, int64_t x_bstride, int64_t x_tstride,
+                                  const float* w_z, const float* w_r, const float* w_h, const float* b_z,
+                                  const float* b_r, const float* b_h, const float* h0, float* out, float* stash,
+                                  void* stream) {
+  STMP_REQUIRE(plan != nullptr, STMP_EINVAL, "stmp_dcrnn_seq_fwd: plan is NULL");
+  STMP_REQUIRE(plan->flavor == STMP_FLAVOR_DCONV, STMP_EINVAL, "stmp_dcrnn_seq_fwd: plan is not a DConv plan");
+  STMP_REQUIRE(B >= 0 && T >= 0, STMP_EINVAL, "stmp_dcrnn_seq_fwd: negative B/T");
+  STMP_REQUIRE(K > 0, STMP_EINVAL, "K must be > 0");  // assert K > 0, dcrnn.py:23
+  STMP_REQUIRE(x && w_z && w_r && w_h && out, STMP_EINVAL, "stmp_dcrnn_seq_fwd: NULL tensor");
+  if (!shape_ok(plan, cin, cout, K))
+    return set_error(STMP_EUNSUPPORTED, "fused DCRNN kernel supports N<=224, cin<=4, cout in {16,32}, K<=4 (got N=%d cin=%lld cout=%lld K=%lld)",
+                     plan->n, (long long)cin, (long long)cout, (long long)K);
+  if (B == 0 || T == 0) return STMP_OK;
+  STMP_REQUIRE(T * (long long)plan->n * cin < (1ll << 24), STMP_ESHAPE, "window too long for the shared-memory X buffer");
+  Layout L;
+  if (!make_layout(plan, (int)cin, (int)cout, (int)K, (int)T, &L))
+    return set_error(STMP_EUNSUPPORTED, "fused DCRNN kernel needs %d B of shared memory (> %d)", L.smem_bytes, kMaxSmem);
+  DcrnnParams& p = L.p;
+  p.B = B;
+  for (int op = 0; op < 2; ++op) {
+    p.rowptr[op] = plan->fwd[op].rowptr;
+    p.cv[op] = plan->fwd[op].cv;
+    p.nnz[op] = plan->fwd[op].nnz;
+  }
+  p.x = x; p.win_start = reinterpret_cast<const long long*>(win_start); p.x_bstride = x_bstride; p.x_tstride = x_tstride;
+  p.w[0] = w_z; p.w[1] = w_r; p.w[2] = w_h;
+  p.bias[0] = b_z; p.bias[1] = b_r; p.bias[2] = b_h;
+  p.h0 = h0; p.out = out; p.stash = stash;
+  // TMA bulk copies need a contiguous window, 16-byte aligned start and size
+  const long long row_elems = (long long)plan->n * cin;
+  bool tma = (x_tstride == row_elems) && ((p.x_floats * 4) % 16 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  if (win_start) tma = tma && ((row_elems * 4) % 16 == 0);
+  else tma = tma && ((x_bstride * 4) % 16 == 0);
+  p.use_tma = tma ? 1 : 0;
+  int dev = 0, sms = 0;
+  STMP_CUDA_OK(cudaGetDevice(&dev));
+  STMP_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  int grid = (int)(B < sms ? B : sms);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (cout == 16) return launch_rt<16>(L, grid, st);
+  return launch_rt<32>(L, grid, st);
+}

@@ -1,0 +1,181 @@
+"""Autograd-aware wrappers over the C ABI (stmp_spmm, fused DCRNN sequence, gate epilogues)."""
+from typing import Optional
+
+import torch
+
+from . import _lib
+from .plan import GraphPlan, _require_cuda
+
+
+def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
+    _require_cuda(t, name)
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"{name} must be float32, got {t.dtype}")
+    return t.contiguous()
+
+
+def spmm_raw(plan: GraphPlan, op: int, x: torch.Tensor, transposed: bool = False, alpha: float = 1.0,
+             z: Optional[torch.Tensor] = None, beta: float = 0.0, att: Optional[torch.Tensor] = None,
+             out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """y = alpha * A_op x + beta * z on (N,F) or (B,N,F) tensors; no autograd."""
+    x = _f32c(x, "x")
+    squeeze = x.dim() == 2
+    x3 = x.unsqueeze(0) if squeeze else x
+    if x3.dim() != 3 or x3.size(1) != plan.num_nodes:
+        raise RuntimeError(f"expected (..., {plan.num_nodes}, F) features, got {tuple(x.shape)}")
+    B, N, F = x3.shape
+    y = torch.empty_like(x3) if out is None else out
+    z3 = None
+    if z is not None:
+        z3 = _f32c(z, "z")
+        z3 = z3.unsqueeze(0) if z3.dim() == 2 else z3
+    a3 = None
+    if att is not None:
+        a3 = _f32c(att, "att")
+        if a3.shape != (B, N, N):
+            raise RuntimeError(f"attention must be ({B},{N},{N}), got {tuple(a3.shape)}")
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().stmp_spmm(plan.handle, op, int(transposed), B, F, _lib.ptr(x3), F, N * F, _lib.ptr(y), F, N * F,
+                                  alpha, _lib.ptr(z3), F, N * F, beta, _lib.ptr(a3), _lib.stream_ptr())
+    _lib.check(rc)
+    return y.squeeze(0) if squeeze else y
+
+
+class _SpMM(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, z, att, plan, op, alpha, beta):
+        ctx.plan, ctx.op, ctx.alpha, ctx.beta = plan, op, alpha, beta
+        ctx.has_z, ctx.has_att = z is not None, att is not None
+        ctx.save_for_backward(x if att is not None else None, att)
+        return spmm_raw(plan, op, x, False, alpha, z, beta, att)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, att = ctx.saved_tensors
+        gy = gy.contiguous()
+        gx = gz = gatt = None
+        if ctx.needs_input_grad[0]:
+            gx = spmm_raw(ctx.plan, ctx.op, gy, True, ctx.alpha, None, 0.0, att)
+        if ctx.has_z and ctx.needs_input_grad[1]:
+            gz = gy * ctx.beta
+        if ctx.has_att and ctx.needs_input_grad[2]:
+            B, N, F = gy.shape
+            gatt = torch.zeros_like(att)
+            with torch.cuda.device(gy.device):
+                rc = _lib.lib().stmp_spmm_att_grad(ctx.plan.handle, ctx.op, B, F, _lib.ptr(gy), F, N * F,
+                                                   _lib.ptr(x.contiguous()), F, N * F, _lib.ptr(gatt), _lib.stream_ptr())
+            _lib.check(rc)
+            if ctx.alpha != 1.0:
+                gatt = gatt * ctx.alpha
+        return gx, gz, gatt, None, None, None, None
+
+
+def spmm(plan: GraphPlan, op: int, x: torch.Tensor, alpha: float = 1.0, z: Optional[torch.Tensor] = None,
+         beta: float = 0.0, att: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Differentiable y = alpha * A_op x + beta * z (gather -> weighted scatter-add, K1/K3)."""
+    return _SpMM.apply(x, z, att, plan, op, float(alpha), float(beta))
+
+
+def dcrnn_seq_supported(plan: GraphPlan, cin: int, cout: int, K: int) -> bool:
+    return bool(_lib.lib().stmp_dcrnn_seq_supported(plan.handle, cin, cout, K))
+
+
+def dcrnn_seq_fwd(plan: GraphPlan, x: torch.Tensor, wz, wr, wh, bz, br, bh, K: int, h0=None,
+                  win_start: Optional[torch.Tensor] = None, horizon: Optional[int] = None, stash: bool = False):
+    """Fused DCRNN recurrence.  x: (B,T,N,Cin) windows, or -- with win_start (int64 [B]) and horizon --
+    the resident series (T_total,N,Cin) from which window b = series[win_start[b]:win_start[b]+horizon]
+    is read in-kernel (index-batching).  Returns out (B,T,N,Cout) [, stash (B,T,3,N,Cout)]."""
+    x = _f32c(x, "X")
+    N = plan.num_nodes
+    cout = wz.size(-1)
+    if win_start is None:
+        if x.dim() != 4 or x.size(2) != N:
+            raise RuntimeError(f"X must be (B,T,{N},Cin), got {tuple(x.shape)}")
+        B, T, _, cin = x.shape
+        bstride, tstride = T * N * cin, N * cin
+        ws = None
+    else:
+        if x.dim() != 3 or x.size(1) != N:
+            raise RuntimeError(f"series must be (T_total,{N},Cin), got {tuple(x.shape)}")
+        _require_cuda(win_start, "win_start")
+        ws = win_start.to(torch.int64).contiguous()
+        B, T, cin = ws.numel(), int(horizon), x.size(2)
+        bstride, tstride = 0, N * cin
+    if wz.size(2) != cin + cout:
+        raise RuntimeError(f"DConv weight expects {wz.size(2)} input channels, got Cin+Cout={cin + cout}")
+    out = torch.empty((B, T, N, cout), dtype=torch.float32, device=x.device)
+    st = torch.empty((B, T, 3, N, cout), dtype=torch.float32, device=x.device) if stash else None
+    h0c = None if h0 is None else _f32c(h0, "H")
+    args = [_f32c(w.detach(), "weight") for w in (wz, wr, wh)]
+    bs = [None if b is None else _f32c(b.detach(), "bias") for b in (bz, br, bh)]
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().stmp_dcrnn_seq_fwd(plan.handle, B, T, cin, cout, K, _lib.ptr(x), _lib.ptr(ws), bstride, tstride,
+                                           _lib.ptr(args[0]), _lib.ptr(args[1]), _lib.ptr(args[2]), _lib.ptr(bs[0]),
+                                           _lib.ptr(bs[1]), _lib.ptr(bs[2]), _lib.ptr(h0c), _lib.ptr(out), _lib.ptr(st),
+                                           _lib.stream_ptr())
+    _lib.check(rc)
+    return (out, st) if stash else out
+
+
+def gru_zr(pz, pr, h):
+    pz, pr, h = _f32c(pz, "pz"), _f32c(pr, "pr"), _f32c(h, "h")
+    z, r, hr = torch.empty_like(pz), torch.empty_like(pz), torch.empty_like(pz)
+    with torch.cuda.device(pz.device):
+        _lib.check(_lib.lib().stmp_gru_zr(pz.numel(), _lib.ptr(pz), _lib.ptr(pr), _lib.ptr(h), _lib.ptr(z), _lib.ptr(r),
+                                          _lib.ptr(hr), _lib.stream_ptr()))
+    return z, r, hr
+
+
+def gru_out(ph, z, h):
+    ph, z, h = _f32c(ph, "ph"), _f32c(z, "z"), _f32c(h, "h")
+    hn = torch.empty_like(ph)
+    with torch.cuda.device(ph.device):
+        _lib.check(_lib.lib().stmp_gru_out(ph.numel(), _lib.ptr(ph), _lib.ptr(z), _lib.ptr(h), None, _lib.ptr(hn),
+                                           _lib.stream_ptr()))
+    return hn
+
+
+def lstm_gates(pi, pf, pc, po_fn, c, wci, wcf, wco, bi, bf, bc, bo):
+    """Returns (h_new, c_new).  `po_fn` is unused here; see nn.recurrent.gconv_lstm for the two-phase use."""
+    raise NotImplementedError
+
+
+def lstm_ifc(pi, pf, pc, c, wci, wcf, bi, bf, bc):
+    pi, pf, pc, c = (_f32c(t, "gate") for t in (pi, pf, pc, c))
+    cout = pi.size(-1)
+    rows = pi.numel() // cout
+    cn = torch.empty_like(pi)
+    v = [_f32c(t.detach().reshape(-1), "param") for t in (wci, wcf, bi, bf, bc)]
+    with torch.cuda.device(pi.device):
+        _lib.check(_lib.lib().stmp_lstm_ifc(rows, cout, _lib.ptr(pi), _lib.ptr(pf), _lib.ptr(pc), _lib.ptr(c), _lib.ptr(v[0]),
+                                            _lib.ptr(v[1]), _lib.ptr(v[2]), _lib.ptr(v[3]), _lib.ptr(v[4]), None, None, None,
+                                            _lib.ptr(cn), _lib.stream_ptr()))
+    return cn
+
+
+def lstm_oh(po, cnew, wco, bo):
+    po, cnew = _f32c(po, "po"), _f32c(cnew, "cnew")
+    cout = po.size(-1)
+    rows = po.numel() // cout
+    hn = torch.empty_like(po)
+    v = [_f32c(t.detach().reshape(-1), "param") for t in (wco, bo)]
+    with torch.cuda.device(po.device):
+        _lib.check(_lib.lib().stmp_lstm_oh(rows, cout, _lib.ptr(po), _lib.ptr(cnew), _lib.ptr(v[0]), _lib.ptr(v[1]), None,
+                                           _lib.ptr(hn), _lib.stream_ptr()))
+    return hn
+
+
+def window_gather(series: torch.Tensor, start: torch.Tensor, horizon: int, with_target: bool = True):
+    """x[b] = series[start[b]:start[b]+h], y[b] = series[start[b]+h:start[b]+2h] (index_dataset.py:49-57)."""
+    series = _f32c(series, "series")
+    _require_cuda(start, "start")
+    start = start.to(torch.int64).contiguous()
+    B = start.numel()
+    row = series[0].numel()
+    shape = (B, horizon) + tuple(series.shape[1:])
+    x = torch.empty(shape, dtype=torch.float32, device=series.device)
+    y = torch.empty(shape, dtype=torch.float32, device=series.device) if with_target else None
+    with torch.cuda.device(series.device):
+        _lib.check(_lib.lib().stmp_window_gather(_lib.ptr(series), series.size(0), row, _lib.ptr(start), B, horizon,
+                                                 _lib.ptr(x), _lib.ptr(y), _lib.stream_ptr()))
+    return (x, y) if with_target else x

@@ -1,0 +1,40 @@
+"""Minimal snapshot container standing in for torch_geometric.data.Data (the reference uses it purely
+as an attribute bag: signal/static_graph_temporal_signal.py:119-120; tests read .x/.edge_index/
+.edge_attr/.y).  Adds `.to(device)` / `.cuda()` so a snapshot can be moved in one call."""
+import torch
+
+
+class Data(object):
+    def __init__(self, x=None, edge_index=None, edge_attr=None, y=None, **kwargs):
+        self.x = x
+        self.edge_index = edge_index
+        self.edge_attr = edge_attr
+        self.y = y
+        self._keys = ["x", "edge_index", "edge_attr", "y"]
+        for k, v in kwargs.items():
+            setattr(self, k, v)
+            self._keys.append(k)
+
+    def keys(self):
+        return [k for k in self._keys if getattr(self, k) is not None]
+
+    def to(self, device, non_blocking=False):
+        out = Data()
+        out._keys = list(self._keys)
+        for k in self._keys:
+            v = getattr(self, k)
+            setattr(out, k, v.to(device, non_blocking=non_blocking) if torch.is_tensor(v) else v)
+        return out
+
+    def cuda(self, device=None, non_blocking=False):
+        return self.to(torch.device("cuda" if device is None else device), non_blocking)
+
+    @property
+    def num_nodes(self):
+        if self.x is not None:
+            return self.x.size(0)
+        return int(self.edge_index.max()) + 1
+
+    def __repr__(self):
+        parts = [f"{k}={list(getattr(self, k).shape) if torch.is_tensor(getattr(self, k)) else getattr(self, k)}" for k in self.keys()]
+        return f"Data({', '.join(parts)})"

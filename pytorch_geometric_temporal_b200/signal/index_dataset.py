@@ -1,0 +1,122 @@
+"""Index-batching data feed -- drop-in for signal/index_dataset.py (:8-57) plus the loader arithmetic of
+dataset/metr_la.py:194-234, re-designed for a GPU-resident series.
+
+* `IndexDataset(indices, data, horizon, lazy=False, gpu=False)`: same constructor / `__getitem__`
+  (x = data[i:i+h], y = data[i+h:i+2h]); `dask` is not required (lazy=True is rejected).
+* `IndexBatchLoader`: replaces `DataLoader(IndexDataset)` + default collate + per-batch H2D.  The whole
+  series stays in HBM; one launch of `stmp_window_gather` materialises a (B,h,N,F) batch, or -- for the
+  fused DCRNN kernel -- nothing is materialised and only the window starts are handed to the kernel.
+  Rank sharding follows torch DistributedSampler semantics (metr_la.py:220-228): seeded permutation per
+  epoch, padded to a multiple of world size, rank r takes perm[r::world].
+"""
+import math
+
+import numpy as np
+import torch
+
+from .. import ops
+
+
+class IndexDataset(torch.utils.data.Dataset):
+    def __init__(self, indices, data, horizon, lazy=False, gpu=False):
+        if lazy:
+            raise ValueError("lazy (Dask) index-batching is out of scope: the series is kept resident in HBM instead")
+        self.indices = indices
+        self.data = data
+        self.horizon = horizon
+        self.lazy = lazy
+        self.gpu = gpu
+
+    def __len__(self):
+        return self.indices.shape[0]
+
+    def __getitem__(self, x):
+        idx = self.indices[x]
+        y_start = idx + self.horizon
+        if self.gpu:
+            return self.data[idx:y_start, ...], self.data[y_start:y_start + self.horizon, ...]
+        return torch.from_numpy(self.data[idx:y_start, ...]), torch.from_numpy(self.data[y_start:y_start + self.horizon, ...])
+
+
+def shard_indices(n: int, world_size: int, rank: int, shuffle: bool, seed: int, epoch: int, drop_last: bool = False):
+    """torch.utils.data.DistributedSampler index selection (host, bit-exact): returns positions in [0,n)."""
+    if shuffle:
+        g = torch.Generator()
+        g.manual_seed(seed + epoch)
+        order = torch.randperm(n, generator=g).tolist()
+    else:
+        order = list(range(n))
+    if world_size <= 1:
+        return order
+    if drop_last and n % world_size != 0:
+        num = math.ceil((n - world_size) / world_size)
+    else:
+        num = math.ceil(n / world_size)
+    total = num * world_size
+    if not drop_last:
+        pad = total - len(order)
+        if pad <= len(order):
+            order += order[:pad]
+        else:
+            order += (order * math.ceil(pad / len(order)))[:pad]
+    else:
+        order = order[:total]
+    return order[rank:total:world_size]
+
+
+class IndexBatchLoader(object):
+    """Iterates batches of windows over a device-resident series.
+
+    Args:
+        series: (T_total, N, F) float tensor on the GPU (already normalised).
+        indices: 1-D array of window start positions (the reference's `x_train` etc.).
+        horizon: window length h (x = h steps, y = next h steps).
+        batch_size, shuffle, world_size, rank, seed: as DataLoader / DistributedSampler.
+        materialize: True -> yields (x, y) tensors (B,h,N,F) gathered by `stmp_window_gather`;
+                     False -> yields (start, None): int64 device tensor of window starts for kernels
+                     that read the series in place (BatchedDCRNN.forward_indexed).
+    """
+
+    def __init__(self, series, indices, horizon, batch_size, shuffle=False, world_size=1, rank=0, seed=0,
+                 drop_last=False, materialize=True):
+        if not series.is_cuda:
+            raise RuntimeError("IndexBatchLoader keeps the series resident on the GPU; move it with .cuda() first")
+        self.series = series.contiguous()
+        self.indices = np.asarray(indices, dtype=np.int64)
+        self.horizon, self.batch_size, self.shuffle = int(horizon), int(batch_size), shuffle
+        self.world_size, self.rank, self.seed, self.drop_last = world_size, rank, seed, drop_last
+        self.materialize = materialize
+        self.epoch = 0
+
+    def set_epoch(self, epoch: int):
+        self.epoch = epoch
+
+    def _positions(self):
+        return shard_indices(len(self.indices), self.world_size, self.rank, self.shuffle, self.seed, self.epoch)
+
+    def __len__(self):
+        n = len(self._positions())
+        return n // self.batch_size if self.drop_last else math.ceil(n / self.batch_size)
+
+    def __iter__(self):
+        pos = self._positions()
+        starts = torch.from_numpy(self.indices[pos]).pin_memory() if torch.cuda.is_available() else torch.from_numpy(self.indices[pos])
+        starts = starts.to(self.series.device, non_blocking=True)
+        n = starts.numel()
+        for s in range(0, n, self.batch_size):
+            st = starts[s:s + self.batch_size]
+            if self.drop_last and st.numel() < self.batch_size:
+                break
+            if self.materialize:
+                yield ops.window_gather(self.series, st, self.horizon, with_target=True)
+            else:
+                yield st, None
+
+
+def index_splits(t_total: int, lags: int, ratio=(0.7, 0.1, 0.2)):
+    """Window-start arrays as dataset/metr_la.py:204-213 builds them."""
+    x_i = np.arange(t_total - (2 * lags - 1))
+    n = x_i.shape[0]
+    n_tr, n_te = round(n * ratio[0]), round(n * ratio[2])
+    n_va = n - n_tr - n_te
+    return x_i[:n_tr], x_i[n_tr:n_tr + n_va], x_i[-n_te:]

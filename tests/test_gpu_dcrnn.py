@@ -1,0 +1,157 @@
+"""GPU parity of the DCRNN family through the public modules (which call the C ABI): fused sequence
+kernel and tiled path vs the CPU oracle and the committed reference goldens.
+Tolerance (strict fp32 mode): rtol=1e-4, atol=1e-5 per layer output."""
+import os
+
+import pytest
+import torch
+
+from oracle import recurrent as R
+from pytorch_geometric_temporal_b200 import _lib, ops
+from pytorch_geometric_temporal_b200.dataset import synthetic
+from pytorch_geometric_temporal_b200.nn.recurrent import DCRNN, BatchedDCRNN, DConv
+from pytorch_geometric_temporal_b200.plan import GraphPlan
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+RTOL, ATOL = 1e-4, 1e-5
+
+
+def _load(golden_dir, name):
+    return torch.load(os.path.join(golden_dir, name + ".pt"), weights_only=False)
+
+
+def _close(got, want, rtol=RTOL, atol=ATOL):
+    got = got.detach().cpu()
+    assert got.shape == want.shape
+    assert torch.allclose(got, want, rtol=rtol, atol=atol), f"max abs err {(got - want).abs().max():.3e}"
+
+
+def test_cfg2_batched_fused_vs_reference_golden(golden_dir):
+    g = _load(golden_dir, "dcrnn_cfg2_batched")
+    m = BatchedDCRNN(2, 32, 2).to(DEV)
+    m.load_state_dict(g["state"])
+    ei, ew = g["edge_index"].to(DEV), g["edge_weight"].to(DEV)
+    n0 = _lib.launch_count()
+    with torch.no_grad():
+        out = m(g["X"].to(DEV), ei, ew)
+    assert _lib.launch_count() > n0  # the CUDA library really ran
+    _close(out, g["out"])
+    # second call hits the plan cache and the same kernel
+    with torch.no_grad():
+        _close(m(g["X"].to(DEV), ei, ew), g["out"])
+
+
+def test_cfg2_batched_tiled_path_vs_golden(golden_dir):
+    g = _load(golden_dir, "dcrnn_cfg2_batched")
+    m = BatchedDCRNN(2, 32, 2).to(DEV)
+    m.load_state_dict(g["state"])
+    out = m(g["X"].to(DEV), g["edge_index"].to(DEV), g["edge_weight"].to(DEV))  # grad enabled -> tiled path
+    assert out.requires_grad
+    _close(out, g["out"])
+
+
+def test_cfg2_cell_vs_golden(golden_dir):
+    g = _load(golden_dir, "dcrnn_cfg2_cell")
+    m = DCRNN(2, 32, 2).to(DEV)
+    m.load_state_dict(g["state"])
+    ei, ew = g["edge_index"].to(DEV), g["edge_weight"].to(DEV)
+    with torch.no_grad():
+        _close(m(g["X"].to(DEV), ei, ew, g["H"].to(DEV)), g["out"])
+        _close(m(g["X"].to(DEV), ei), g["out_noew_noh"])  # edge_weight=None, H=None
+    _close(m(g["X"].to(DEV), ei, ew, g["H"].to(DEV)), g["out"])  # tiled
+
+
+@pytest.mark.parametrize("K", [1, 3, 4])
+def test_small_graph_K_fused_and_tiled_and_grads(golden_dir, K):
+    g = _load(golden_dir, f"dcrnn_small_K{K}")
+    m = DCRNN(3, 16, K).to(DEV)
+    m.load_state_dict(g["state"])
+    ei, ew = g["edge_index"].to(DEV), g["edge_weight"].to(DEV)
+    with torch.no_grad():
+        _close(m(g["X"].to(DEV), ei, ew, g["H"].to(DEV)), g["out"])  # fused
+    X = g["X"].to(DEV).requires_grad_(True)
+    H = g["H"].to(DEV).requires_grad_(True)
+    out = m(X, ei, ew, H)  # tiled + autograd through the transposed SpMM
+    _close(out, g["out"])
+    w = torch.linspace(-1, 1, out.numel(), device=DEV).view_as(out)
+    (out * w).sum().backward()
+    _close(X.grad, g["gX"], 1e-3, 1e-5)
+    _close(H.grad, g["gH"], 1e-3, 1e-5)
+    for k, p in m.named_parameters():
+        _close(p.grad, g["grads"][k], 1e-3, 1e-5)
+
+
+def test_small_batched_K3(golden_dir):
+    g = _load(golden_dir, "dcrnn_small_batched_K3")
+    m = BatchedDCRNN(3, 16, 3).to(DEV)
+    m.load_state_dict(g["state"])
+    with torch.no_grad():
+        _close(m(g["X"].to(DEV), g["edge_index"].to(DEV), g["edge_weight"].to(DEV)), g["out"])
+
+
+@pytest.mark.parametrize("B", [1, 5, 300])
+def test_fused_vs_oracle_many_windows_and_index_batching(B):
+    """More windows than SMs (persistent loop + TMA double buffering) and the in-kernel window gather."""
+    ei, ew, series = synthetic.metr_la_like(0, 400)
+    ei_t, ew_t, s_t = torch.from_numpy(ei), torch.from_numpy(ew), torch.from_numpy(series)
+    torch.manual_seed(B)
+    m = BatchedDCRNN(2, 32, 2)
+    starts = torch.randint(0, 400 - 12, (B,))
+    X = torch.stack([s_t[s:s + 12] for s in starts.tolist()])
+    nb = min(B, 4)  # oracle on a few windows only (seconds)
+    want = R.batched_dcrnn(m.state_dict(), X[:nb], ei_t, ew_t)
+    mg = m.to(DEV)
+    with torch.no_grad():
+        out = mg(X.to(DEV), ei_t.to(DEV), ew_t.to(DEV))
+        out_idx = mg.forward_indexed(s_t.to(DEV), starts.to(DEV), 12, ei_t.to(DEV), ew_t.to(DEV))
+    _close(out[:nb], want)
+    assert torch.equal(out, out_idx)  # same kernel, X read in place from the resident series
+    # windows are independent: permuting the batch permutes the output
+    perm = torch.randperm(B)
+    with torch.no_grad():
+        assert torch.equal(mg(X[perm].to(DEV), ei_t.to(DEV), ew_t.to(DEV)), out[perm.to(DEV)])
+
+
+def test_fused_recurrence_equals_chained_cells():
+    """Size-independent property: T fused steps == T chained single-step calls with H carried."""
+    ei, ew, series = synthetic.metr_la_like(0, 32)
+    ei_t, ew_t = torch.from_numpy(ei).to(DEV), torch.from_numpy(ew).to(DEV)
+    torch.manual_seed(0)
+    mb = BatchedDCRNN(2, 32, 2).to(DEV)
+    mc = DCRNN(2, 32, 2).to(DEV)
+    mc.load_state_dict(mb.state_dict())
+    X = torch.from_numpy(series[:12]).to(DEV)
+    with torch.no_grad():
+        seq = mb(X.unsqueeze(0), ei_t, ew_t)[0]
+        H = None
+        for t in range(12):
+            H = mc(X[t], ei_t, ew_t, H)
+            assert torch.allclose(H, seq[t], rtol=1e-5, atol=1e-6)
+
+
+def test_dconv_layer_vs_oracle():
+    ei, ew, _ = synthetic.metr_la_like(0, 16)
+    ei_t, ew_t = torch.from_numpy(ei), torch.from_numpy(ew)
+    torch.manual_seed(3)
+    conv = DConv(34, 32, 3)
+    x = torch.randn(207, 34)
+    want = R.dconv(x, R.dconv_operators(ei_t, ew_t, False, 207), conv.weight.detach(), conv.bias.detach())
+    got = conv.to(DEV)(x.to(DEV), ei_t.to(DEV), ew_t.to(DEV))
+    _close(got, want)
+
+
+def test_unsupported_shapes_fall_back_to_tiled_not_cpu():
+    ei, ew, _ = synthetic.pems_bay_like(0, 16)  # N=325 > 224 rows: fused kernel refuses
+    ei_t, ew_t = torch.from_numpy(ei), torch.from_numpy(ew)
+    torch.manual_seed(0)
+    m = BatchedDCRNN(2, 32, 2)
+    X = torch.randn(2, 3, 325, 2)
+    want = R.batched_dcrnn(m.state_dict(), X, ei_t, ew_t)
+    plan = GraphPlan(_lib.FLAVOR_DCONV, ei_t.to(DEV), ew_t.to(DEV), 325, flags=_lib.DCONV_ALLOW_DUPLICATES)
+    assert not ops.dcrnn_seq_supported(plan, 2, 32, 2)
+    n0 = _lib.launch_count()
+    with torch.no_grad():
+        got = m.to(DEV)(X.to(DEV), ei_t.to(DEV), ew_t.to(DEV))
+    assert _lib.launch_count() > n0
+    _close(got, want)

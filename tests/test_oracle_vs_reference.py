@@ -1,0 +1,84 @@
+"""In-container pin of the oracle's MODULE logic: the functional restatement (oracle/recurrent.py,
+oracle/attention.py) must reproduce the UNMODIFIED reference modules (imported from /root/reference on
+top of oracle/stubs) bit-for-bit.  Skipped where /root/reference is absent (the GPU box), which is why
+the same comparison is also frozen into tests/golden/*.pt (see test_goldens_cpu.py)."""
+import pytest
+import torch
+
+from oracle import refload, recurrent as R, attention as A, pyg
+
+pytestmark = pytest.mark.skipif(not refload.available(), reason="/root/reference not present")
+
+
+def _graph(n=12, e=40, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    row = torch.randint(0, n, (e,), generator=g)
+    col = torch.randint(0, n, (e,), generator=g)
+    pairs = {(int(r), int(c)) for r, c in zip(row, col)} | {(i, i) for i in range(n)} | {(i, (i + 1) % n) for i in range(n)}
+    ei = torch.tensor(sorted(pairs)).t().contiguous()
+    return ei, torch.rand(ei.size(1), generator=g) * 0.9 + 0.1
+
+
+@pytest.mark.parametrize("K", [1, 2, 3, 4])
+def test_dcrnn(K):
+    ei, ew = _graph()
+    m = refload.load("nn.recurrent.dcrnn")
+    torch.manual_seed(K)
+    ref = m.DCRNN(2, 8, K)
+    X, H = torch.randn(12, 2), torch.randn(12, 8)
+    with torch.no_grad():
+        assert torch.equal(ref(X, ei, ew, H), R.dcrnn_cell(ref.state_dict(), X, ei, ew, H))
+        assert torch.equal(ref(X, ei), R.dcrnn_cell(ref.state_dict(), X, ei))
+        refb = m.BatchedDCRNN(2, 8, K)
+        Xb = torch.randn(3, 4, 12, 2)
+        assert torch.equal(refb(Xb, ei, ew), R.batched_dcrnn(refb.state_dict(), Xb, ei, ew))
+
+
+@pytest.mark.parametrize("K", [1, 2, 3, 4])
+@pytest.mark.parametrize("norm", ["sym", "rw", None])
+def test_gconv(K, norm):
+    ei, ew = _graph()
+    lm = None if norm == "sym" else torch.tensor(2.3)
+    X, H, C = torch.randn(12, 4), torch.randn(12, 8), torch.randn(12, 8)
+    with torch.no_grad():
+        ref = refload.load("nn.recurrent.gconv_gru").GConvGRU(4, 8, K, normalization=norm)
+        assert torch.equal(ref(X, ei, ew, H, lm), R.gconv_gru_cell(ref.state_dict(), X, ei, ew, H, lm, norm))
+        ref = refload.load("nn.recurrent.gconv_lstm").GConvLSTM(4, 8, K, normalization=norm)
+        a, b = ref(X, ei, ew, H, C, lm), R.gconv_lstm_cell(ref.state_dict(), X, ei, ew, H, C, lm, norm)
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+
+
+def test_tgcn_family():
+    ei, ew = _graph()
+    m = refload.load("nn.recurrent.temporalgcn")
+    a = refload.load("nn.recurrent.attentiontemporalgcn")
+    X, H = torch.randn(12, 4), torch.randn(12, 8)
+    with torch.no_grad():
+        for improved in (False, True):
+            for asl in (True, False):
+                ref = m.TGCN(4, 8, improved=improved, add_self_loops=asl)
+                assert torch.equal(ref(X, ei, ew, H), R.tgcn_cell(ref.state_dict(), X, ei, ew, H, improved, asl))
+        ref = m.TGCN2(4, 8, 3)
+        Xb, Hb = torch.randn(3, 12, 4), torch.randn(3, 12, 8)
+        assert torch.equal(ref(Xb, ei, ew, Hb), R.tgcn_cell(ref.state_dict(), Xb, ei, ew, Hb))
+        ref = a.A3TGCN2(4, 8, 6, 3)
+        Xp = torch.randn(3, 12, 4, 6)
+        assert torch.equal(ref(Xp, ei, ew), R.a3tgcn(ref.state_dict(), Xp, ei, ew))
+        ref = a.A3TGCN(4, 8, 6)
+        assert torch.equal(ref(Xp[0], ei, ew), R.a3tgcn(ref.state_dict(), Xp[0], ei, ew))
+
+
+@pytest.mark.parametrize("norm", ["sym", None, "rw"])
+def test_astgcn(norm):
+    ei, _ = _graph()
+    und = sorted({(a, b) for a, b in ei.t().tolist() if a != b} | {(b, a) for a, b in ei.t().tolist() if a != b})
+    eiu = torch.tensor(und).t().contiguous()
+    ref = refload.load("nn.attention.astgcn").ASTGCN(2, 1, 3, 8, 8, 2, 4, 6, 12, normalization=norm)
+    Xa = torch.randn(3, 12, 1, 6)
+    lm = None
+    if norm != "sym":
+        lm = pyg.LaplacianLambdaMax()(pyg.Data(edge_index=eiu, edge_attr=None, num_nodes=12)).lambda_max
+    with torch.no_grad():
+        want = ref(Xa, eiu)
+        got = A.astgcn(ref.state_dict(), Xa, eiu, 2, norm, 2, lm)
+    assert torch.allclose(want, got, rtol=1e-6, atol=1e-6)  # diag-scale vs dense matmul: 1 ulp
