@@ -125,6 +125,7 @@ __device__ __forceinline__ void tma_store_wait() {
   asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
 }
 
-__device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+// 1/(1+e^-x): __frcp_rn is the correctly rounded reciprocal == IEEE 1.0f/y, without the division slow path.
+__device__ __forceinline__ float sigmoidf_acc(float x) { return __frcp_rn(1.0f + expf(-x)); }
 
 }  // namespace stmp

@@ -18,6 +18,8 @@
 //    channels 4w..4w+3 of every gate, lane l owns rows l, l+32, ...; A rows are read as float4 along K
 //    with LD/4 odd => conflict-free LDS.128; B is a warp-uniform broadcast.  The gate epilogue
 //    (sigmoid/tanh/Hadamard/convex combine) runs on the accumulators in registers.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace stmp {
@@ -47,56 +49,89 @@ struct DcrnnParams {
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void fma4(float4& acc, float w, const float4& x) {
+  acc.x = fmaf(w, x.x, acc.x); acc.y = fmaf(w, x.y, acc.y); acc.z = fmaf(w, x.z, acc.z); acc.w = fmaf(w, x.w, acc.w);
+}
 
-// One diffusion hop for every (row, op): dst block = 2*P_op*src - U (hop>=2) or P_op*src (hop 1).
-// LPR lanes per row, lane j handles float4 j of the CP-wide block; jmax = number of active float4s.
-template <int LPR>
-__device__ __forceinline__ void diffuse(float* S, const int* const* rowptr, const int2* const* cv, int N, int LD, int CP,
-                                        int hop, int jmax, int tid, int nthreads) {
+// Accumulate one destination row of one operator for the float4 column `col4` of source block `sb`:
+// sum_k val_k * S[col_k][sb*CP + col4 .. +3].  Edges are fetched 4 at a time (one 64-bit LDS each), then the
+// 4 gathers are issued back to back so their shared-memory latencies overlap; the tail is predicated
+// (weight 0, index clamped) instead of branching.
+__device__ __forceinline__ float4 gather_row(const float* __restrict__ Scol, const int2* __restrict__ ce, int beg, int end, int LD) {
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int k = beg; k < end; k += 4) {
+    int2 e[4];
+    float w[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int kk = k + u < end ? k + u : end - 1;
+      e[u] = ce[kk];
+      w[u] = k + u < end ? __int_as_float(e[u].y) : 0.f;
+    }
+    float4 x[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) x[u] = ld4(Scol + e[u].x * LD);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) fma4(acc, w[u], x[u]);
+  }
+  return acc;
+}
+
+// One diffusion hop.  H columns: LPR = OUT/4 lanes per (row, op) task, lane j owns float4 j, so a warp
+// covers 32/LPR destination rows per pass and every gather is one full 128-byte shared-memory wavefront.
+// X columns (one float4 at column OUT): one thread per (row, op) task, only when `with_x`.
+// dst block = P_op * src (hop 1) or 2 * P_op * src - U (hop >= 2; the reference never advances Tx_0 past
+// X, dcrnn.py:80,106).
+template <int OUT, int NT>
+__device__ __forceinline__ void diffuse(float* S, const int* rp0, const int* rp1, const int2* cv0, const int2* cv1, int N,
+                                        int LD, int CP, int hop, bool with_x, int tid) {
+  constexpr int LPR = OUT / 4;
   const int j = tid & (LPR - 1);
-  const int group = tid / LPR;
-  const int ngroups = nthreads / LPR;
-  for (int task = group; task < 2 * N; task += ngroups) {
+  for (int task = tid / LPR; task < 2 * N; task += NT / LPR) {
     const int op = task >= N ? 1 : 0;
     const int i = task - op * N;
+    const int* rp = op ? rp1 : rp0;
+    const int2* ce = op ? cv1 : cv0;
     const int sb = (hop == 1) ? 0 : (1 + 2 * (hop - 2) + op);
     const int db = 1 + 2 * (hop - 1) + op;
-    const int* rp = rowptr[op];
-    const int2* ce = cv[op];
-    const int beg = rp[i], end = rp[i + 1];
-    if (j < jmax) {
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      const float* src = S + sb * CP + 4 * j;
-      int k = beg;
-      for (; k + 2 <= end; k += 2) {
-        int2 e0 = ce[k], e1 = ce[k + 1];
-        float4 x0 = ld4(src + e0.x * LD);
-        float4 x1 = ld4(src + e1.x * LD);
-        float w0 = __int_as_float(e0.y), w1 = __int_as_float(e1.y);
-        acc.x = fmaf(w0, x0.x, acc.x); acc.y = fmaf(w0, x0.y, acc.y); acc.z = fmaf(w0, x0.z, acc.z); acc.w = fmaf(w0, x0.w, acc.w);
-        acc.x = fmaf(w1, x1.x, acc.x); acc.y = fmaf(w1, x1.y, acc.y); acc.z = fmaf(w1, x1.z, acc.z); acc.w = fmaf(w1, x1.w, acc.w);
-      }
-      if (k < end) {
-        int2 e0 = ce[k];
-        float4 x0 = ld4(src + e0.x * LD);
-        float w0 = __int_as_float(e0.y);
-        acc.x = fmaf(w0, x0.x, acc.x); acc.y = fmaf(w0, x0.y, acc.y); acc.z = fmaf(w0, x0.z, acc.z); acc.w = fmaf(w0, x0.w, acc.w);
-      }
-      if (hop >= 2) {  // T_k = 2 P T_{k-1} - X : the reference never advances Tx_0 past X (dcrnn.py:80,106)
-        float4 u = ld4(S + i * LD + 4 * j);
+    float4 acc = gather_row(S + sb * CP + 4 * j, ce, rp[i], rp[i + 1], LD);
+    if (hop >= 2) {
+      const float4 u = ld4(S + i * LD + 4 * j);
+      acc.x = 2.0f * acc.x - u.x; acc.y = 2.0f * acc.y - u.y; acc.z = 2.0f * acc.z - u.z; acc.w = 2.0f * acc.w - u.w;
+    }
+    st4(S + i * LD + db * CP + 4 * j, acc);
+  }
+  if (with_x) {
+    for (int task = tid; task < 2 * N; task += NT) {
+      const int op = task >= N ? 1 : 0;
+      const int i = task - op * N;
+      const int* rp = op ? rp1 : rp0;
+      const int2* ce = op ? cv1 : cv0;
+      const int sb = (hop == 1) ? 0 : (1 + 2 * (hop - 2) + op);
+      const int db = 1 + 2 * (hop - 1) + op;
+      float4 acc = gather_row(S + sb * CP + OUT, ce, rp[i], rp[i + 1], LD);
+      if (hop >= 2) {
+        const float4 u = ld4(S + i * LD + OUT);
         acc.x = 2.0f * acc.x - u.x; acc.y = 2.0f * acc.y - u.y; acc.z = 2.0f * acc.z - u.z; acc.w = 2.0f * acc.w - u.w;
       }
-      st4(S + i * LD + db * CP + 4 * j, acc);
+      st4(S + i * LD + db * CP + OUT, acc);
     }
   }
 }
 
-template <int OUT, int RT>
-__global__ void __launch_bounds__(OUT * 8, 1) k_dcrnn_seq(const DcrnnParams p) {
+// Thread mapping of the contraction: warp w owns rows [w*RQ*RT, (w+1)*RQ*RT); inside the warp lane =
+// (cg, rq) with cg = lane % CG the group of 4 output channels and rq = lane / CG the row phase; the
+// thread owns rows w*RQ*RT + rq + RQ*i (i < RT) x channels 4cg..4cg+3 of EVERY gate, so Z, H and H~ of an
+// element meet in one thread's registers.  A (rows of S, float4 along K): RQ distinct rows per LDS.128,
+// consecutive rows are LD words apart with LD/4 odd => distinct bank groups, one wavefront.  B (weights):
+// CG distinct consecutive float4 = <= 128 B, one wavefront.
+template <int OUT, int RT, int NW>
+__global__ void __launch_bounds__(NW * 32, 1) k_dcrnn_seq(const DcrnnParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
-  constexpr int NT = OUT * 8;
+  constexpr int NT = NW * 32;
   constexpr int WLD = 3 * OUT;
-  constexpr int LPR = (OUT + 4) / 4 <= 8 ? 8 : ((OUT + 4) / 4 <= 16 ? 16 : 32);
+  constexpr int CG = OUT / 4;
+  constexpr int RQ = 32 / CG;
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   const int N = p.N, CIN = p.CIN, K = p.K, T = p.T, CP = p.CP, LD = p.LD;
@@ -105,9 +140,12 @@ __global__ void __launch_bounds__(OUT * 8, 1) k_dcrnn_seq(const DcrnnParams p) {
   float* S = reinterpret_cast<float*>(smem + p.off_S);
   float* W = reinterpret_cast<float*>(smem + p.off_W);
   float* Bs = reinterpret_cast<float*>(smem + p.off_bias);
-  int* s_rowptr[2] = {reinterpret_cast<int*>(smem + p.off_rowptr[0]), reinterpret_cast<int*>(smem + p.off_rowptr[1])};
-  int2* s_cv[2] = {reinterpret_cast<int2*>(smem + p.off_cv[0]), reinterpret_cast<int2*>(smem + p.off_cv[1])};
-  float* xbuf[2] = {reinterpret_cast<float*>(smem + p.off_x[0]), reinterpret_cast<float*>(smem + p.off_x[1])};
+  int* rp0 = reinterpret_cast<int*>(smem + p.off_rowptr[0]);
+  int* rp1 = reinterpret_cast<int*>(smem + p.off_rowptr[1]);
+  int2* cv0 = reinterpret_cast<int2*>(smem + p.off_cv[0]);
+  int2* cv1 = reinterpret_cast<int2*>(smem + p.off_cv[1]);
+  float* xbuf0 = reinterpret_cast<float*>(smem + p.off_x[0]);
+  float* xbuf1 = reinterpret_cast<float*>(smem + p.off_x[1]);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.off_bar);
 
   const long long b_first = blockIdx.x;
@@ -123,12 +161,11 @@ __global__ void __launch_bounds__(OUT * 8, 1) k_dcrnn_seq(const DcrnnParams p) {
     mbar_init(&bars[1], 1);
     fence_mbar_init();
     mbar_arrive_expect_tx(&bars[0], x_bytes);
-    tma_bulk_g2s(xbuf[0], x_base(b_first), x_bytes, &bars[0]);
+    tma_bulk_g2s(xbuf0, x_base(b_first), x_bytes, &bars[0]);
   }
-  for (int op = 0; op < 2; ++op) {
-    for (int i = tid; i <= N; i += NT) s_rowptr[op][i] = p.rowptr[op][i];
-    for (int i = tid; i < p.nnz[op]; i += NT) s_cv[op][i] = p.cv[op][i];
-  }
+  for (int i = tid; i <= N; i += NT) { rp0[i] = p.rowptr[0][i]; rp1[i] = p.rowptr[1][i]; }
+  for (int i = tid; i < p.nnz[0]; i += NT) cv0[i] = p.cv[0][i];
+  for (int i = tid; i < p.nnz[1]; i += NT) cv1[i] = p.cv[1][i];
   // weights -> Wcat[kidx][z|r|h], internal channel order [H(OUT) | X(CIN) | pad], block 0 = W[0,0]+W[1,0]
   for (int idx = tid; idx < LD * WLD; idx += NT) {
     const int kidx = idx / WLD, col = idx - kidx * WLD;
@@ -137,7 +174,7 @@ __global__ void __launch_bounds__(OUT * 8, 1) k_dcrnn_seq(const DcrnnParams p) {
     float v = 0.f;
     if (ci < C) {
       const int ch = ci < OUT ? CIN + ci : ci - OUT;
-      const float* wg = p.w[g];
+      const float* wg = g == 0 ? p.w[0] : (g == 1 ? p.w[1] : p.w[2]);
       if (blk == 0) {
         v = wg[((0 * K + 0) * C + ch) * OUT + o] + wg[((1 * K + 0) * C + ch) * OUT + o];
       } else {
@@ -149,41 +186,42 @@ __global__ void __launch_bounds__(OUT * 8, 1) k_dcrnn_seq(const DcrnnParams p) {
   }
   for (int idx = tid; idx < WLD; idx += NT) {
     const int g = idx / OUT;
-    Bs[idx] = p.bias[g] ? p.bias[g][idx - g * OUT] : 0.f;
+    const float* bg = g == 0 ? p.bias[0] : (g == 1 ? p.bias[1] : p.bias[2]);
+    Bs[idx] = bg ? bg[idx - g * OUT] : 0.f;
   }
   for (int idx = tid; idx < N * LD; idx += NT) S[idx] = 0.f;
   __syncthreads();
 
-  const int c0 = warp * 4;
-  int rows[RT];
-  const float* Srow[RT];
+  const int cg = lane % CG, rq = lane / CG;
+  const int c0 = cg * 4;
+  const int row0 = warp * (RQ * RT) + rq;
+  int soff[RT];  // clamped row offsets (rows >= N read row N-1, their results are discarded)
 #pragma unroll
   for (int i = 0; i < RT; ++i) {
-    rows[i] = lane + 32 * i;
-    Srow[i] = S + (rows[i] < N ? rows[i] : N - 1) * LD;
+    const int r = row0 + RQ * i;
+    soff[i] = (r < N ? r : N - 1) * LD;
   }
   const int KG = LD / 4;
-  uint32_t phase[2] = {0u, 0u};
+  uint32_t phase0 = 0u, phase1 = 0u;
   int it = 0;
 
   for (long long b = b_first; b < p.B; b += gridDim.x, ++it) {
     const int buf = it & 1;
     const float* xw;
     if (p.use_tma) {
-      mbar_wait(&bars[buf], phase[buf]);
-      phase[buf] ^= 1u;
+      if (buf == 0) { mbar_wait(&bars[0], phase0); phase0 ^= 1u; } else { mbar_wait(&bars[1], phase1); phase1 ^= 1u; }
       const long long bn = b + gridDim.x;
       if (tid == 0 && bn < p.B) {  // stream the next window in while this one computes
         fence_proxy_async();
         mbar_arrive_expect_tx(&bars[buf ^ 1], x_bytes);
-        tma_bulk_g2s(xbuf[buf ^ 1], x_base(bn), x_bytes, &bars[buf ^ 1]);
+        tma_bulk_g2s(buf ? xbuf0 : xbuf1, x_base(bn), x_bytes, &bars[buf ^ 1]);
       }
-      xw = xbuf[buf];
+      xw = buf ? xbuf1 : xbuf0;
     } else {
       const float* xb = x_base(b);
       for (int t = 0; t < T; ++t)
-        for (int idx = tid; idx < N * CIN; idx += NT) xbuf[0][t * N * CIN + idx] = __ldg(xb + t * p.x_tstride + idx);
-      xw = xbuf[0];
+        for (int idx = tid; idx < N * CIN; idx += NT) xbuf0[t * N * CIN + idx] = __ldg(xb + t * p.x_tstride + idx);
+      xw = xbuf0;
     }
     // H_0 and X_0 into block 0
     for (int idx = tid; idx < N * OUT; idx += NT) {
@@ -200,7 +238,7 @@ __global__ void __launch_bounds__(OUT * 8, 1) k_dcrnn_seq(const DcrnnParams p) {
     for (int t = 0; t < T; ++t) {
       // ---- round 1: diffuse U = [H | X_t] ------------------------------------------------------------
       for (int hop = 1; hop < K; ++hop) {
-        diffuse<LPR>(S, s_rowptr, s_cv, N, LD, CP, hop, CP / 4, tid, NT);
+        diffuse<OUT, NT>(S, rp0, rp1, cv0, cv1, N, LD, CP, hop, true, tid);
         __syncthreads();
       }
       // ---- GEMM 1: [z|r] pre-activations -------------------------------------------------------------
@@ -213,7 +251,7 @@ __global__ void __launch_bounds__(OUT * 8, 1) k_dcrnn_seq(const DcrnnParams p) {
       for (int kg = 0; kg < KG; ++kg) {
         float4 a[RT];
 #pragma unroll
-        for (int i = 0; i < RT; ++i) a[i] = ld4(Srow[i] + 4 * kg);
+        for (int i = 0; i < RT; ++i) a[i] = ld4(S + soff[i] + 4 * kg);
         const float* wrow = W + (4 * kg) * WLD + c0;
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
@@ -236,7 +274,7 @@ __global__ void __launch_bounds__(OUT * 8, 1) k_dcrnn_seq(const DcrnnParams p) {
         const float bzv[4] = {bz.x, bz.y, bz.z, bz.w}, brv[4] = {br.x, br.y, br.z, br.w};
 #pragma unroll
         for (int i = 0; i < RT; ++i) {
-          const float4 h = ld4(Srow[i] + c0);
+          const float4 h = ld4(S + soff[i] + c0);
           hreg[i][0] = h.x; hreg[i][1] = h.y; hreg[i][2] = h.z; hreg[i][3] = h.w;
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
@@ -249,11 +287,12 @@ __global__ void __launch_bounds__(OUT * 8, 1) k_dcrnn_seq(const DcrnnParams p) {
       const long long obase = (b * T + t) * (long long)N;
 #pragma unroll
       for (int i = 0; i < RT; ++i) {
-        if (rows[i] < N) {
-          st4(S + rows[i] * LD + c0, make_float4(hreg[i][0] * accr[i][0], hreg[i][1] * accr[i][1],
-                                                 hreg[i][2] * accr[i][2], hreg[i][3] * accr[i][3]));
+        const int r = row0 + RQ * i;
+        if (r < N) {
+          st4(S + r * LD + c0, make_float4(hreg[i][0] * accr[i][0], hreg[i][1] * accr[i][1],
+                                           hreg[i][2] * accr[i][2], hreg[i][3] * accr[i][3]));
           if (p.stash) {
-            float* sp = p.stash + ((obase * 3) + 0 * (long long)N + rows[i]) * OUT + c0;
+            float* sp = p.stash + ((obase * 3) + r) * OUT + c0;
             st4(sp, make_float4(accz[i][0], accz[i][1], accz[i][2], accz[i][3]));
             st4(sp + (long long)N * OUT, make_float4(accr[i][0], accr[i][1], accr[i][2], accr[i][3]));
           }
@@ -262,7 +301,7 @@ __global__ void __launch_bounds__(OUT * 8, 1) k_dcrnn_seq(const DcrnnParams p) {
       __syncthreads();
       // ---- round 2: re-diffuse only the H*R columns ---------------------------------------------------
       for (int hop = 1; hop < K; ++hop) {
-        diffuse<LPR>(S, s_rowptr, s_cv, N, LD, CP, hop, OUT / 4, tid, NT);
+        diffuse<OUT, NT>(S, rp0, rp1, cv0, cv1, N, LD, CP, hop, false, tid);
         __syncthreads();
       }
       // ---- GEMM 2: candidate --------------------------------------------------------------------------
@@ -275,7 +314,7 @@ __global__ void __launch_bounds__(OUT * 8, 1) k_dcrnn_seq(const DcrnnParams p) {
       for (int kg = 0; kg < KG; ++kg) {
         float4 a[RT];
 #pragma unroll
-        for (int i = 0; i < RT; ++i) a[i] = ld4(Srow[i] + 4 * kg);
+        for (int i = 0; i < RT; ++i) a[i] = ld4(S + soff[i] + 4 * kg);
         const float* wrow = W + (4 * kg) * WLD + 2 * OUT + c0;
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
@@ -294,7 +333,8 @@ __global__ void __launch_bounds__(OUT * 8, 1) k_dcrnn_seq(const DcrnnParams p) {
         const float bhv[4] = {bh.x, bh.y, bh.z, bh.w};
 #pragma unroll
         for (int i = 0; i < RT; ++i) {
-          if (rows[i] < N) {
+          const int r = row0 + RQ * i;
+          if (r < N) {
             float hn[4], ht[4];
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
@@ -302,9 +342,9 @@ __global__ void __launch_bounds__(OUT * 8, 1) k_dcrnn_seq(const DcrnnParams p) {
               hn[c] = accz[i][c] * hreg[i][c] + (1.0f - accz[i][c]) * ht[c];  // dcrnn.py:190-192
             }
             const float4 hv = make_float4(hn[0], hn[1], hn[2], hn[3]);
-            st4(S + rows[i] * LD + c0, hv);
-            st4(p.out + (obase + rows[i]) * OUT + c0, hv);
-            if (p.stash) st4(p.stash + ((obase * 3) + 2 * (long long)N + rows[i]) * OUT + c0, make_float4(ht[0], ht[1], ht[2], ht[3]));
+            st4(S + r * LD + c0, hv);
+            st4(p.out + (obase + r) * OUT + c0, hv);
+            if (p.stash) st4(p.stash + ((obase * 3) + 2 * (long long)N + r) * OUT + c0, make_float4(ht[0], ht[1], ht[2], ht[3]));
           }
         }
       }
@@ -348,30 +388,34 @@ bool make_layout(const stmp_plan* plan, int cin, int cout, int K, int T, Layout*
   return off <= kMaxSmem;
 }
 
-template <int OUT, int RT>
+template <int OUT, int RT, int NW>
 int launch(const Layout& L, int grid, cudaStream_t st) {
-  auto kern = k_dcrnn_seq<OUT, RT>;
+  auto kern = k_dcrnn_seq<OUT, RT, NW>;
   STMP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.smem_bytes));
-  kern<<<grid, OUT * 8, L.smem_bytes, st>>>(L.p);
+  kern<<<grid, NW * 32, L.smem_bytes, st>>>(L.p);
   STMP_LAUNCH_OK("k_dcrnn_seq");
   return STMP_OK;
 }
 
+// rows covered = NW * (128/OUT) * RT
 template <int OUT>
-int launch_rt(const Layout& L, int grid, cudaStream_t st) {
-  const int need = (L.p.N + 31) / 32;
-  if (need <= 1) return launch<OUT, 1>(L, grid, st);
-  if (need <= 2) return launch<OUT, 2>(L, grid, st);
-  if (need <= 4) return launch<OUT, 4>(L, grid, st);
-  if (need <= 7) return launch<OUT, 7>(L, grid, st);
-  return set_error(STMP_EUNSUPPORTED, "fused DCRNN kernel: N=%d exceeds 224 rows", L.p.N);
+int launch_rt(const Layout& L, int grid, cudaStream_t st, int variant) {
+  constexpr int RQ = 128 / OUT;
+  const int n = L.p.N;
+  if (variant == 1 && n <= 16 * RQ * 4) return launch<OUT, 4, 16>(L, grid, st);  // 16 warps x 4 row tiles
+  if (n <= 8 * RQ * 1) return launch<OUT, 1, 8>(L, grid, st);
+  if (n <= 8 * RQ * 2) return launch<OUT, 2, 8>(L, grid, st);
+  if (n <= 8 * RQ * 4) return launch<OUT, 4, 8>(L, grid, st);
+  if (n <= 8 * RQ * 7) return launch<OUT, 7, 8>(L, grid, st);
+  if (n <= 16 * RQ * 4) return launch<OUT, 4, 16>(L, grid, st);
+  return set_error(STMP_EUNSUPPORTED, "fused DCRNN kernel: N=%d exceeds the row capacity", n);
 }
 
 bool shape_ok(const stmp_plan* plan, int64_t cin, int64_t cout, int64_t K) {
   if (!plan || plan->flavor != STMP_FLAVOR_DCONV || plan->n_ops != 2) return false;
   if (!(cout == 16 || cout == 32)) return false;
   if (cin < 1 || cin > 4 || K < 1 || K > 4) return false;
-  if (plan->n > 224) return false;
+  if (plan->n > 16 * (128 / (int)cout) * 4) return false;
   return true;
 }
 
@@ -397,7 +441,7 @@ extern "C" int stmp_dcrnn_seq_fwd(const stmp_plan* plan, int64_t B, int64_t T, i
   STMP_REQUIRE(K > 0, STMP_EINVAL, "K must be > 0");  // assert K > 0, dcrnn.py:23
   STMP_REQUIRE(x && w_z && w_r && w_h && out, STMP_EINVAL, "stmp_dcrnn_seq_fwd: NULL tensor");
   if (!shape_ok(plan, cin, cout, K))
-    return set_error(STMP_EUNSUPPORTED, "fused DCRNN kernel supports N<=224, cin<=4, cout in {16,32}, K<=4 (got N=%d cin=%lld cout=%lld K=%lld)",
+    return set_error(STMP_EUNSUPPORTED, "fused DCRNN kernel supports N<=256 (cout 32), cin<=4, cout in {16,32}, K<=4 (got N=%d cin=%lld cout=%lld K=%lld)",
                      plan->n, (long long)cin, (long long)cout, (long long)K);
   if (B == 0 || T == 0) return STMP_OK;
   STMP_REQUIRE(T * (long long)plan->n * cin < (1ll << 24), STMP_ESHAPE, "window too long for the shared-memory X buffer");
@@ -426,6 +470,11 @@ extern "C" int stmp_dcrnn_seq_fwd(const stmp_plan* plan, int64_t B, int64_t T, i
   STMP_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   int grid = (int)(B < sms ? B : sms);
   cudaStream_t st = (cudaStream_t)stream;
-  if (cout == 16) return launch_rt<16>(L, grid, st);
-  return launch_rt<32>(L, grid, st);
+  static int variant = -1;
+  if (variant < 0) {
+    const char* v = getenv("STMP_DCRNN_VARIANT");
+    variant = v ? atoi(v) : 0;
+  }
+  if (cout == 16) return launch_rt<16>(L, grid, st, variant);
+  return launch_rt<32>(L, grid, st, variant);
 }
