@@ -49,52 +49,71 @@ struct DcrnnParams {
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+// Packed fp32 FMA (sm_100 FFMA2): two independent fp32 FMAs per instruction.  A scalar multiplicand is
+// passed as (a,a); ptxas folds it into the .F32 broadcast operand form, so no extra moves are issued.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
 __device__ __forceinline__ void fma4(float4& acc, float w, const float4& x) {
-  acc.x = fmaf(w, x.x, acc.x); acc.y = fmaf(w, x.y, acc.y); acc.z = fmaf(w, x.z, acc.z); acc.w = fmaf(w, x.w, acc.w);
+  const float2 ww = make_float2(w, w);
+  const float2 lo = ffma2(ww, make_float2(x.x, x.y), make_float2(acc.x, acc.y));
+  const float2 hi = ffma2(ww, make_float2(x.z, x.w), make_float2(acc.z, acc.w));
+  acc = make_float4(lo.x, lo.y, hi.x, hi.y);
 }
 
-// Accumulate one destination row of one operator for the float4 column `col4` of source block `sb`:
-// sum_k val_k * S[col_k][sb*CP + col4 .. +3].  Edges are fetched 4 at a time (one 64-bit LDS each), then the
-// 4 gathers are issued back to back so their shared-memory latencies overlap; the tail is predicated
-// (weight 0, index clamped) instead of branching.
-__device__ __forceinline__ float4 gather_row(const float* __restrict__ Scol, const int2* __restrict__ ce, int beg, int end, int LD) {
+// Shared-memory form of the two operators, built once per CTA from the plan's CSR:
+//   * every (row, op) task's edge list is padded to a multiple of 4 with (self, 0.0f) entries, so the
+//     gather loop has no tail predication;
+//   * the column index is pre-multiplied by LD (element offset of the source row in S);
+//   * tasks are ordered by descending group count, so the quarter-warps of a warp (consecutive slots)
+//     walk rows of equal length -- no divergence inside a warp pass.
+struct GraphSmem {
+  const int2* ce;      // padded (src_row*LD, val) entries
+  const int* gstart;   // [2N+1] first padded entry of task
+  const int* order;    // [2N] task ids (op*N + row) sorted by descending padded length
+};
+
+// sum over the padded edge list of one task for the float4 at S[src*LD + coff .. +3]
+__device__ __forceinline__ float4 gather_row(const float* __restrict__ Sc, const int2* __restrict__ ce, int beg, int end) {
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int k = beg; k < end; k += 4) {
-    int2 e[4];
-    float w[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int kk = k + u < end ? k + u : end - 1;
-      e[u] = ce[kk];
-      w[u] = k + u < end ? __int_as_float(e[u].y) : 0.f;
-    }
-    float4 x[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) x[u] = ld4(Scol + e[u].x * LD);
-#pragma unroll
-    for (int u = 0; u < 4; ++u) fma4(acc, w[u], x[u]);
+    const int4 e01 = *reinterpret_cast<const int4*>(ce + k);      // two edges per 128-bit load
+    const int4 e23 = *reinterpret_cast<const int4*>(ce + k + 2);
+    const float4 x0 = ld4(Sc + e01.x);
+    const float4 x1 = ld4(Sc + e01.z);
+    const float4 x2 = ld4(Sc + e23.x);
+    const float4 x3 = ld4(Sc + e23.z);
+    fma4(acc, __int_as_float(e01.y), x0);
+    fma4(acc, __int_as_float(e01.w), x1);
+    fma4(acc, __int_as_float(e23.y), x2);
+    fma4(acc, __int_as_float(e23.w), x3);
   }
   return acc;
 }
 
-// One diffusion hop.  H columns: LPR = OUT/4 lanes per (row, op) task, lane j owns float4 j, so a warp
-// covers 32/LPR destination rows per pass and every gather is one full 128-byte shared-memory wavefront.
-// X columns (one float4 at column OUT): one thread per (row, op) task, only when `with_x`.
+// One diffusion hop.  H columns: LPR = OUT/4 lanes per task, lane j owns float4 j, so a warp covers
+// 32/LPR destination rows per pass and every gather is one full 128-byte shared-memory wavefront.
+// X columns (one float4 at column OUT): one thread per task, only when `with_x`.
 // dst block = P_op * src (hop 1) or 2 * P_op * src - U (hop >= 2; the reference never advances Tx_0 past
 // X, dcrnn.py:80,106).
 template <int OUT, int NT>
-__device__ __forceinline__ void diffuse(float* S, const int* rp0, const int* rp1, const int2* cv0, const int2* cv1, int N,
-                                        int LD, int CP, int hop, bool with_x, int tid) {
+__device__ __forceinline__ void diffuse(float* S, const GraphSmem g, int N, int LD, int CP, int hop, bool with_x, int tid) {
   constexpr int LPR = OUT / 4;
   const int j = tid & (LPR - 1);
-  for (int task = tid / LPR; task < 2 * N; task += NT / LPR) {
+  for (int slot = tid / LPR; slot < 2 * N; slot += NT / LPR) {
+    const int task = g.order[slot];
     const int op = task >= N ? 1 : 0;
     const int i = task - op * N;
-    const int* rp = op ? rp1 : rp0;
-    const int2* ce = op ? cv1 : cv0;
     const int sb = (hop == 1) ? 0 : (1 + 2 * (hop - 2) + op);
     const int db = 1 + 2 * (hop - 1) + op;
-    float4 acc = gather_row(S + sb * CP + 4 * j, ce, rp[i], rp[i + 1], LD);
+    float4 acc = gather_row(S + sb * CP + 4 * j, g.ce, g.gstart[task], g.gstart[task + 1]);
     if (hop >= 2) {
       const float4 u = ld4(S + i * LD + 4 * j);
       acc.x = 2.0f * acc.x - u.x; acc.y = 2.0f * acc.y - u.y; acc.z = 2.0f * acc.z - u.z; acc.w = 2.0f * acc.w - u.w;
@@ -102,14 +121,13 @@ __device__ __forceinline__ void diffuse(float* S, const int* rp0, const int* rp1
     st4(S + i * LD + db * CP + 4 * j, acc);
   }
   if (with_x) {
-    for (int task = tid; task < 2 * N; task += NT) {
+    for (int slot = tid; slot < 2 * N; slot += NT) {
+      const int task = g.order[slot];
       const int op = task >= N ? 1 : 0;
       const int i = task - op * N;
-      const int* rp = op ? rp1 : rp0;
-      const int2* ce = op ? cv1 : cv0;
       const int sb = (hop == 1) ? 0 : (1 + 2 * (hop - 2) + op);
       const int db = 1 + 2 * (hop - 1) + op;
-      float4 acc = gather_row(S + sb * CP + OUT, ce, rp[i], rp[i + 1], LD);
+      float4 acc = gather_row(S + sb * CP + OUT, g.ce, g.gstart[task], g.gstart[task + 1]);
       if (hop >= 2) {
         const float4 u = ld4(S + i * LD + OUT);
         acc.x = 2.0f * acc.x - u.x; acc.y = 2.0f * acc.y - u.y; acc.z = 2.0f * acc.z - u.z; acc.w = 2.0f * acc.w - u.w;
@@ -140,10 +158,9 @@ __global__ void __launch_bounds__(NW * 32, 1) k_dcrnn_seq(const DcrnnParams p) {
   float* S = reinterpret_cast<float*>(smem + p.off_S);
   float* W = reinterpret_cast<float*>(smem + p.off_W);
   float* Bs = reinterpret_cast<float*>(smem + p.off_bias);
-  int* rp0 = reinterpret_cast<int*>(smem + p.off_rowptr[0]);
-  int* rp1 = reinterpret_cast<int*>(smem + p.off_rowptr[1]);
-  int2* cv0 = reinterpret_cast<int2*>(smem + p.off_cv[0]);
-  int2* cv1 = reinterpret_cast<int2*>(smem + p.off_cv[1]);
+  int2* s_ce = reinterpret_cast<int2*>(smem + p.off_cv[0]);
+  int* s_gstart = reinterpret_cast<int*>(smem + p.off_rowptr[0]);
+  int* s_order = reinterpret_cast<int*>(smem + p.off_rowptr[1]);
   float* xbuf0 = reinterpret_cast<float*>(smem + p.off_x[0]);
   float* xbuf1 = reinterpret_cast<float*>(smem + p.off_x[1]);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.off_bar);
@@ -163,9 +180,46 @@ __global__ void __launch_bounds__(NW * 32, 1) k_dcrnn_seq(const DcrnnParams p) {
     mbar_arrive_expect_tx(&bars[0], x_bytes);
     tma_bulk_g2s(xbuf0, x_base(b_first), x_bytes, &bars[0]);
   }
-  for (int i = tid; i <= N; i += NT) { rp0[i] = p.rowptr[0][i]; rp1[i] = p.rowptr[1][i]; }
-  for (int i = tid; i < p.nnz[0]; i += NT) cv0[i] = p.cv[0][i];
-  for (int i = tid; i < p.nnz[1]; i += NT) cv1[i] = p.cv[1][i];
+  // graph -> padded, pre-scaled, length-sorted shared-memory form (see GraphSmem)
+  {
+    int* s_len = s_order;  // reuse as scratch until the sort writes it
+    for (int task = tid; task < 2 * N; task += NT) {
+      const int op = task >= N ? 1 : 0, i = task - op * N;
+      const int* rp = op ? p.rowptr[1] : p.rowptr[0];
+      s_len[task] = (rp[i + 1] - rp[i] + 3) & ~3;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int run = 0;
+      for (int task = 0; task < 2 * N; ++task) { s_gstart[task] = run; run += s_len[task]; }
+      s_gstart[2 * N] = run;
+    }
+    __syncthreads();
+    for (int task = tid; task < 2 * N; task += NT) {
+      const int op = task >= N ? 1 : 0, i = task - op * N;
+      const int* rp = op ? p.rowptr[1] : p.rowptr[0];
+      const int2* cv = op ? p.cv[1] : p.cv[0];
+      const int beg = rp[i], len = rp[i + 1] - beg, plen = s_gstart[task + 1] - s_gstart[task];
+      int2* dst = s_ce + s_gstart[task];
+      for (int k = 0; k < plen; ++k) {
+        int2 e = k < len ? cv[beg + k] : make_int2(i, 0);
+        e.x *= LD;
+        dst[k] = e;
+      }
+    }
+    __syncthreads();
+    // order tasks by descending padded length (rank = number of tasks that sort before this one)
+    for (int task = tid; task < 2 * N; task += NT) {
+      const int len = s_gstart[task + 1] - s_gstart[task];
+      int rank = 0;
+      for (int o = 0; o < 2 * N; ++o) {
+        const int lo = s_gstart[o + 1] - s_gstart[o];
+        rank += (lo > len) || (lo == len && o < task);
+      }
+      s_order[rank] = task;
+    }
+  }
+  const GraphSmem gs{s_ce, s_gstart, s_order};
   // weights -> Wcat[kidx][z|r|h], internal channel order [H(OUT) | X(CIN) | pad], block 0 = W[0,0]+W[1,0]
   for (int idx = tid; idx < LD * WLD; idx += NT) {
     const int kidx = idx / WLD, col = idx - kidx * WLD;
@@ -238,15 +292,15 @@ __global__ void __launch_bounds__(NW * 32, 1) k_dcrnn_seq(const DcrnnParams p) {
     for (int t = 0; t < T; ++t) {
       // ---- round 1: diffuse U = [H | X_t] ------------------------------------------------------------
       for (int hop = 1; hop < K; ++hop) {
-        diffuse<OUT, NT>(S, rp0, rp1, cv0, cv1, N, LD, CP, hop, true, tid);
+        diffuse<OUT, NT>(S, gs, N, LD, CP, hop, true, tid);
         __syncthreads();
       }
       // ---- GEMM 1: [z|r] pre-activations -------------------------------------------------------------
-      float accz[RT][4], accr[RT][4];
+      float2 accz[RT][2], accr[RT][2];
 #pragma unroll
       for (int i = 0; i < RT; ++i)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) { accz[i][c] = 0.f; accr[i][c] = 0.f; }
+        for (int c = 0; c < 2; ++c) { accz[i][c] = make_float2(0.f, 0.f); accr[i][c] = make_float2(0.f, 0.f); }
 #pragma unroll 1
       for (int kg = 0; kg < KG; ++kg) {
         float4 a[RT];
@@ -260,15 +314,16 @@ __global__ void __launch_bounds__(NW * 32, 1) k_dcrnn_seq(const DcrnnParams p) {
 #pragma unroll
           for (int i = 0; i < RT; ++i) {
             const float av = kk == 0 ? a[i].x : (kk == 1 ? a[i].y : (kk == 2 ? a[i].z : a[i].w));
-            accz[i][0] = fmaf(av, bz.x, accz[i][0]); accz[i][1] = fmaf(av, bz.y, accz[i][1]);
-            accz[i][2] = fmaf(av, bz.z, accz[i][2]); accz[i][3] = fmaf(av, bz.w, accz[i][3]);
-            accr[i][0] = fmaf(av, br.x, accr[i][0]); accr[i][1] = fmaf(av, br.y, accr[i][1]);
-            accr[i][2] = fmaf(av, br.z, accr[i][2]); accr[i][3] = fmaf(av, br.w, accr[i][3]);
+            const float2 aa = make_float2(av, av);
+            accz[i][0] = ffma2(aa, make_float2(bz.x, bz.y), accz[i][0]);
+            accz[i][1] = ffma2(aa, make_float2(bz.z, bz.w), accz[i][1]);
+            accr[i][0] = ffma2(aa, make_float2(br.x, br.y), accr[i][0]);
+            accr[i][1] = ffma2(aa, make_float2(br.z, br.w), accr[i][1]);
           }
         }
       }
       // gates; keep Z and H in registers, R only lives long enough to form H*R
-      float hreg[RT][4];
+      float hreg[RT][4], zreg[RT][4], rreg[RT][4];
       {
         const float4 bz = ld4(Bs + c0), br = ld4(Bs + OUT + c0);
         const float bzv[4] = {bz.x, bz.y, bz.z, bz.w}, brv[4] = {br.x, br.y, br.z, br.w};
@@ -276,10 +331,12 @@ __global__ void __launch_bounds__(NW * 32, 1) k_dcrnn_seq(const DcrnnParams p) {
         for (int i = 0; i < RT; ++i) {
           const float4 h = ld4(S + soff[i] + c0);
           hreg[i][0] = h.x; hreg[i][1] = h.y; hreg[i][2] = h.z; hreg[i][3] = h.w;
+          const float pz[4] = {accz[i][0].x, accz[i][0].y, accz[i][1].x, accz[i][1].y};
+          const float pr[4] = {accr[i][0].x, accr[i][0].y, accr[i][1].x, accr[i][1].y};
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
-            accz[i][c] = sigmoidf_acc(accz[i][c] + bzv[c]);
-            accr[i][c] = sigmoidf_acc(accr[i][c] + brv[c]);
+            zreg[i][c] = sigmoidf_acc(pz[c] + bzv[c]);
+            rreg[i][c] = sigmoidf_acc(pr[c] + brv[c]);
           }
         }
       }
@@ -289,27 +346,25 @@ __global__ void __launch_bounds__(NW * 32, 1) k_dcrnn_seq(const DcrnnParams p) {
       for (int i = 0; i < RT; ++i) {
         const int r = row0 + RQ * i;
         if (r < N) {
-          st4(S + r * LD + c0, make_float4(hreg[i][0] * accr[i][0], hreg[i][1] * accr[i][1],
-                                           hreg[i][2] * accr[i][2], hreg[i][3] * accr[i][3]));
+          st4(S + r * LD + c0, make_float4(hreg[i][0] * rreg[i][0], hreg[i][1] * rreg[i][1],
+                                           hreg[i][2] * rreg[i][2], hreg[i][3] * rreg[i][3]));
           if (p.stash) {
             float* sp = p.stash + ((obase * 3) + r) * OUT + c0;
-            st4(sp, make_float4(accz[i][0], accz[i][1], accz[i][2], accz[i][3]));
-            st4(sp + (long long)N * OUT, make_float4(accr[i][0], accr[i][1], accr[i][2], accr[i][3]));
+            st4(sp, make_float4(zreg[i][0], zreg[i][1], zreg[i][2], zreg[i][3]));
+            st4(sp + (long long)N * OUT, make_float4(rreg[i][0], rreg[i][1], rreg[i][2], rreg[i][3]));
           }
         }
       }
       __syncthreads();
       // ---- round 2: re-diffuse only the H*R columns ---------------------------------------------------
       for (int hop = 1; hop < K; ++hop) {
-        diffuse<OUT, NT>(S, rp0, rp1, cv0, cv1, N, LD, CP, hop, false, tid);
+        diffuse<OUT, NT>(S, gs, N, LD, CP, hop, false, tid);
         __syncthreads();
       }
       // ---- GEMM 2: candidate --------------------------------------------------------------------------
-      float acch[RT][4];
+      float2 acch[RT][2];
 #pragma unroll
-      for (int i = 0; i < RT; ++i)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) acch[i][c] = 0.f;
+      for (int i = 0; i < RT; ++i) { acch[i][0] = make_float2(0.f, 0.f); acch[i][1] = make_float2(0.f, 0.f); }
 #pragma unroll 1
       for (int kg = 0; kg < KG; ++kg) {
         float4 a[RT];
@@ -322,8 +377,9 @@ __global__ void __launch_bounds__(NW * 32, 1) k_dcrnn_seq(const DcrnnParams p) {
 #pragma unroll
           for (int i = 0; i < RT; ++i) {
             const float av = kk == 0 ? a[i].x : (kk == 1 ? a[i].y : (kk == 2 ? a[i].z : a[i].w));
-            acch[i][0] = fmaf(av, bh.x, acch[i][0]); acch[i][1] = fmaf(av, bh.y, acch[i][1]);
-            acch[i][2] = fmaf(av, bh.z, acch[i][2]); acch[i][3] = fmaf(av, bh.w, acch[i][3]);
+            const float2 aa = make_float2(av, av);
+            acch[i][0] = ffma2(aa, make_float2(bh.x, bh.y), acch[i][0]);
+            acch[i][1] = ffma2(aa, make_float2(bh.z, bh.w), acch[i][1]);
           }
         }
       }
@@ -336,10 +392,11 @@ __global__ void __launch_bounds__(NW * 32, 1) k_dcrnn_seq(const DcrnnParams p) {
           const int r = row0 + RQ * i;
           if (r < N) {
             float hn[4], ht[4];
+            const float ph[4] = {acch[i][0].x, acch[i][0].y, acch[i][1].x, acch[i][1].y};
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-              ht[c] = tanhf(acch[i][c] + bhv[c]);
-              hn[c] = accz[i][c] * hreg[i][c] + (1.0f - accz[i][c]) * ht[c];  // dcrnn.py:190-192
+              ht[c] = tanhf(ph[c] + bhv[c]);
+              hn[c] = zreg[i][c] * hreg[i][c] + (1.0f - zreg[i][c]) * ht[c];  // dcrnn.py:190-192
             }
             const float4 hv = make_float4(hn[0], hn[1], hn[2], hn[3]);
             st4(S + r * LD + c0, hv);
@@ -378,8 +435,11 @@ bool make_layout(const stmp_plan* plan, int cin, int cout, int K, int T, Layout*
   p.off_S = off; off += align_up(p.N * p.LD * 4, 128);
   p.off_W = off; off += align_up(p.LD * 3 * cout * 4, 128);
   p.off_bias = off; off += align_up(3 * cout * 4, 128);
-  for (int op = 0; op < 2; ++op) { p.off_rowptr[op] = off; off += align_up((p.N + 1) * 4, 16); }
-  for (int op = 0; op < 2; ++op) { p.off_cv[op] = off; off += align_up((plan->fwd[op].nnz > 0 ? plan->fwd[op].nnz : 1) * 8, 16); }
+  // off_rowptr[0] = gstart[2N+1], off_rowptr[1] = order[2N]; off_cv[0] = padded edge entries (<= nnz + 3 per task)
+  p.off_rowptr[0] = off; off += align_up((2 * p.N + 1) * 4, 16);
+  p.off_rowptr[1] = off; off += align_up(2 * p.N * 4, 16);
+  p.off_cv[0] = off; off += align_up((plan->fwd[0].nnz + plan->fwd[1].nnz + 6 * p.N + 4) * 8, 16);
+  p.off_cv[1] = off;
   off = align_up(off, 128);
   p.x_floats = T * p.N * cin;
   for (int i = 0; i < 2; ++i) { p.off_x[i] = off; off += align_up(p.x_floats * 4, 128); }
