@@ -1,0 +1,224 @@
+"""ASTGCN -- drop-in for torch_geometric_temporal/nn/attention/astgcn.py (ChebConvAttention :16-199,
+SpatialAttention :201-262, TemporalAttention :264-328, ASTGCNBlock :330-481, ASTGCN :483-610).
+Same constructors, forward signatures, `__repr__` and state_dict keys (`_blocklist.{i}.
+_temporal_attention.{_U1,_U2,_U3,_be,_Ve}`, `._spatial_attention.{_W1,_W2,_W3,_bs,_Vs}`,
+`._chebconv_attention.{_weight,_bias}`, `._time_convolution.*`, `._residual_convolution.*`,
+`._layer_norm.*`, `_final_conv.*`).
+
+What runs where
+* graph work (the hot path): attention-weighted gather/scatter `norm * S[b,row,col]` and the Chebyshev
+  recurrence go through `stmp_spmm` on a cached CHEB_ATT plan; the reference's per-timestep Python loop
+  (:442-450) is folded into the feature axis (the attention matrix is shared by all T timesteps), so one
+  launch per hop covers every timestep; the dense `(I*S)^T @ x` used for a diagonal scale (:160-165) is
+  a broadcast multiply;
+* dense attention products / convolutions / LayerNorm are true dense GEMM-class work and stay on
+  cuBLAS/cuDNN through torch.
+* lambda_max for normalization != "sym": the reference calls scipy ARPACK on the host in EVERY block
+  forward (:437-438); here it is computed once per static graph and cached.
+"""
+from typing import List, Optional, Union
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+from torch.nn import Parameter
+
+from ... import _lib, ops
+from ...plan import PlanCache, _require_cuda
+
+
+def laplacian_lambda_max(edge_index: torch.Tensor, num_nodes: int, normalization: Optional[str]) -> float:
+    """torch_geometric.transforms.LaplacianLambdaMax (is_undirected=False): largest-magnitude eigenvalue of
+    the (normalised) Laplacian via scipy `eigs`.  One-time host computation per static graph."""
+    import numpy as np
+    from scipy.sparse import coo_matrix
+    from scipy.sparse.linalg import eigs
+    ei = edge_index.detach().cpu()
+    keep = ei[0] != ei[1]
+    row, col = ei[0][keep].numpy(), ei[1][keep].numpy()
+    w = np.ones(row.shape[0], dtype=np.float64)
+    deg = np.bincount(row, weights=w, minlength=num_nodes)
+    if normalization is None:
+        vals, r, c = np.concatenate([-w, deg]), np.concatenate([row, np.arange(num_nodes)]), np.concatenate([col, np.arange(num_nodes)])
+    else:
+        with np.errstate(divide="ignore"):
+            if normalization == "sym":
+                d = np.where(deg > 0, deg ** -0.5, 0.0)
+                wn = d[row] * w * d[col]
+            else:
+                d = np.where(deg > 0, 1.0 / deg, 0.0)
+                wn = d[row] * w
+        vals = np.concatenate([-wn, np.ones(num_nodes)])
+        r, c = np.concatenate([row, np.arange(num_nodes)]), np.concatenate([col, np.arange(num_nodes)])
+    L = coo_matrix((vals.astype(np.float32).astype(np.float64), (r, c)), shape=(num_nodes, num_nodes))
+    lam = eigs(L, k=1, which="LM", return_eigenvectors=False)
+    return float(lam.real[0])
+
+
+class ChebConvAttention(nn.Module):
+    def __init__(self, in_channels: int, out_channels: int, K: int, normalization: Optional[str] = None, bias: bool = True,
+                 **kwargs):
+        super().__init__()
+        assert K > 0
+        assert normalization in [None, "sym", "rw"], "Invalid normalization"
+        self._in_channels, self._out_channels, self._normalization = in_channels, out_channels, normalization
+        self._weight = Parameter(torch.empty(K, in_channels, out_channels))
+        if bias:
+            self._bias = Parameter(torch.empty(out_channels))
+        else:
+            self.register_parameter("_bias", None)
+        self._plans = PlanCache(max_entries=16)
+        self._reset_parameters()
+
+    def _reset_parameters(self):
+        nn.init.xavier_uniform_(self._weight)
+        if self._bias is not None:
+            nn.init.uniform_(self._bias)
+
+    def _plan(self, edge_index, edge_weight, num_nodes, lambda_max):
+        lam = None if lambda_max is None else float(lambda_max)
+        return self._plans.get(_lib.FLAVOR_CHEB_ATT, edge_index, edge_weight, num_nodes, self._normalization, lam)
+
+    def forward(self, x: torch.FloatTensor, edge_index: torch.LongTensor, spatial_attention: torch.FloatTensor,
+                edge_weight=None, batch=None, lambda_max=None) -> torch.FloatTensor:
+        """x (B,N,Fin) -- or (B,N,T,Fin) to process every timestep of a block in one pass --,
+        spatial_attention (B,N,N) -> (B,N,[T,]Fout)."""
+        if self._normalization != "sym" and lambda_max is None:
+            raise ValueError("You need to pass `lambda_max` to `forward() in`case the normalization is non-symmetric.")
+        if batch is not None:
+            raise ValueError("multi-graph mini-batches (`batch`) are not supported by the static-graph engine")
+        _require_cuda(x, "x")
+        B, N = x.shape[0], x.shape[1]
+        plan = self._plan(edge_index, edge_weight, N, lambda_max)
+        xs = x.reshape(B, N, -1)                                    # timesteps folded into the feature axis
+        S = spatial_attention.contiguous()
+        T0 = torch.diagonal(S, dim1=1, dim2=2).unsqueeze(-1) * xs   # (I*S)^T @ x            :160-165
+        Ts = [T0]
+        K = self._weight.size(0)
+        if K > 1:
+            Ts.append(ops.spmm(plan, 0, T0.contiguous(), att=S))   # norm * S[b,row,col]    :156-157,169-171
+        for _ in range(2, K):
+            Ts.append(ops.spmm(plan, 0, Ts[-1], alpha=2.0, z=Ts[-2], beta=-1.0))   # plain norm   :174-178
+        out = 0
+        for k in range(K):
+            out = out + torch.matmul(Ts[k].reshape(x.shape), self._weight[k])
+        if self._bias is not None:
+            out = out + self._bias
+        return out
+
+    def __repr__(self):
+        return "{}({}, {}, K={}, normalization={})".format(self.__class__.__name__, self._in_channels, self._out_channels,
+                                                           self._weight.size(0), self._normalization)
+
+
+class SpatialAttention(nn.Module):
+    def __init__(self, in_channels: int, num_of_vertices: int, num_of_timesteps: int):
+        super().__init__()
+        self._W1 = nn.Parameter(torch.FloatTensor(num_of_timesteps))
+        self._W2 = nn.Parameter(torch.FloatTensor(in_channels, num_of_timesteps))
+        self._W3 = nn.Parameter(torch.FloatTensor(in_channels))
+        self._bs = nn.Parameter(torch.FloatTensor(1, num_of_vertices, num_of_vertices))
+        self._Vs = nn.Parameter(torch.FloatTensor(num_of_vertices, num_of_vertices))
+        _reset(self)
+
+    def forward(self, X: torch.FloatTensor) -> torch.FloatTensor:
+        LHS = torch.matmul(torch.matmul(X, self._W1), self._W2)
+        RHS = torch.matmul(self._W3, X).transpose(-1, -2)
+        S = torch.matmul(self._Vs, torch.sigmoid(torch.matmul(LHS, RHS) + self._bs))
+        return F.softmax(S, dim=1)
+
+
+class TemporalAttention(nn.Module):
+    def __init__(self, in_channels: int, num_of_vertices: int, num_of_timesteps: int):
+        super().__init__()
+        self._U1 = nn.Parameter(torch.FloatTensor(num_of_vertices))
+        self._U2 = nn.Parameter(torch.FloatTensor(in_channels, num_of_vertices))
+        self._U3 = nn.Parameter(torch.FloatTensor(in_channels))
+        self._be = nn.Parameter(torch.FloatTensor(1, num_of_timesteps, num_of_timesteps))
+        self._Ve = nn.Parameter(torch.FloatTensor(num_of_timesteps, num_of_timesteps))
+        _reset(self)
+
+    def forward(self, X: torch.FloatTensor) -> torch.FloatTensor:
+        LHS = torch.matmul(torch.matmul(X.permute(0, 3, 2, 1), self._U1), self._U2)
+        RHS = torch.matmul(self._U3, X)
+        E = torch.matmul(self._Ve, torch.sigmoid(torch.matmul(LHS, RHS) + self._be))
+        return F.softmax(E, dim=1)
+
+
+def _reset(module):
+    """xavier_uniform for dim>1, uniform(0,1) otherwise -- applied to EVERY parameter (astgcn.py:401-406)."""
+    for p in module.parameters():
+        if p.dim() > 1:
+            nn.init.xavier_uniform_(p)
+        else:
+            nn.init.uniform_(p)
+
+
+class ASTGCNBlock(nn.Module):
+    def __init__(self, in_channels: int, K: int, nb_chev_filter: int, nb_time_filter: int, time_strides: int,
+                 num_of_vertices: int, num_of_timesteps: int, normalization: Optional[str] = None, bias: bool = True):
+        super().__init__()
+        self._temporal_attention = TemporalAttention(in_channels, num_of_vertices, num_of_timesteps)
+        self._spatial_attention = SpatialAttention(in_channels, num_of_vertices, num_of_timesteps)
+        self._chebconv_attention = ChebConvAttention(in_channels, nb_chev_filter, K, normalization, bias)
+        self._time_convolution = nn.Conv2d(nb_chev_filter, nb_time_filter, kernel_size=(1, 3), stride=(1, time_strides), padding=(0, 1))
+        self._residual_convolution = nn.Conv2d(in_channels, nb_time_filter, kernel_size=(1, 1), stride=(1, time_strides))
+        self._layer_norm = nn.LayerNorm(nb_time_filter)
+        self._normalization = normalization
+        self._lam_cache = {}
+        _reset(self)
+
+    def _lambda_max(self, edge_index, num_nodes):
+        if self._normalization == "sym":
+            return None
+        key = (edge_index.data_ptr(), edge_index._version, tuple(edge_index.shape))
+        hit = self._lam_cache.get(key)
+        if hit is None:
+            if len(self._lam_cache) > 16:
+                self._lam_cache.clear()
+            # the reference calls LaplacianLambdaMax() with ITS default normalization=None whatever the block's
+            # normalization is (astgcn.py:437-438): lambda_max of L = D - A.  Reproduced.
+            hit = (laplacian_lambda_max(edge_index, num_nodes, None), edge_index)
+            self._lam_cache[key] = hit
+        return hit[0]
+
+    def forward(self, X: torch.FloatTensor, edge_index: Union[torch.LongTensor, List[torch.LongTensor]]) -> torch.FloatTensor:
+        B, N, Fi, T = X.shape
+        E = self._temporal_attention(X)
+        X_tilde = torch.matmul(X.reshape(B, -1, T), E).reshape(B, N, Fi, T)
+        S = self._spatial_attention(X_tilde)
+        if not isinstance(edge_index, list):
+            lam = self._lambda_max(edge_index, N)
+            # all T timesteps in one pass: (B,N,F,T) -> (B,N,T,F)
+            X_hat = self._chebconv_attention(X.permute(0, 1, 3, 2).contiguous(), edge_index, S, lambda_max=lam)
+            X_hat = F.relu(X_hat.permute(0, 1, 3, 2))             # (B,N,Fc,T)
+        else:
+            hats = []
+            for t in range(T):
+                lam = self._lambda_max(edge_index[t], N)
+                hats.append(self._chebconv_attention(X[:, :, :, t].contiguous(), edge_index[t], S, lambda_max=lam).unsqueeze(-1))
+            X_hat = F.relu(torch.cat(hats, dim=-1))
+        X_hat = self._time_convolution(X_hat.permute(0, 2, 1, 3))
+        Xr = self._residual_convolution(X.permute(0, 2, 1, 3))
+        Y = self._layer_norm(F.relu(Xr + X_hat).permute(0, 3, 2, 1))
+        return Y.permute(0, 2, 3, 1)
+
+
+class ASTGCN(nn.Module):
+    def __init__(self, nb_block: int, in_channels: int, K: int, nb_chev_filter: int, nb_time_filter: int, time_strides: int,
+                 num_for_predict: int, len_input: int, num_of_vertices: int, normalization: Optional[str] = None,
+                 bias: bool = True):
+        super().__init__()
+        self._blocklist = nn.ModuleList([ASTGCNBlock(in_channels, K, nb_chev_filter, nb_time_filter, time_strides,
+                                                     num_of_vertices, len_input, normalization, bias)])
+        self._blocklist.extend([ASTGCNBlock(nb_time_filter, K, nb_chev_filter, nb_time_filter, 1, num_of_vertices,
+                                            len_input // time_strides, normalization, bias) for _ in range(nb_block - 1)])
+        self._final_conv = nn.Conv2d(int(len_input / time_strides), num_for_predict, kernel_size=(1, nb_time_filter))
+        _reset(self)
+
+    def forward(self, X: torch.FloatTensor, edge_index: torch.LongTensor) -> torch.FloatTensor:
+        _require_cuda(X, "X")
+        for block in self._blocklist:
+            X = block(X, edge_index)
+        X = self._final_conv(X.permute(0, 3, 1, 2))
+        return X[:, :, :, -1].permute(0, 2, 1)

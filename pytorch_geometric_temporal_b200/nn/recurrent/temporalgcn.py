@@ -1,0 +1,68 @@
+"""TGCN / TGCN2 -- drop-in for torch_geometric_temporal/nn/recurrent/temporalgcn.py (:5-130, :133-233).
+state_dict keys `conv_{z,r,h}.lin.weight (out,in)`, `conv_{z,r,h}.bias`, `linear_{z,r,h}.{weight,bias}`.
+The reference runs three GCNConvs (each: gcn_norm + lin + propagate of `out` channels); since
+A^(X W) = (A^ X) W, one SpMM on the `in` channels feeds all three gates."""
+import torch
+
+from ... import _lib, ops
+from ...plan import PlanCache, _require_cuda
+from ._cheb import _Lin
+
+
+class GCNParams(torch.nn.Module):
+    """Holder with GCNConv's keys: `lin.weight (out,in)` glorot, `bias (out)` zeros."""
+
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.lin = _Lin(in_channels, out_channels)
+        self.bias = torch.nn.Parameter(torch.zeros(out_channels))
+
+
+class TGCN(torch.nn.Module):
+    def __init__(self, in_channels: int, out_channels: int, improved: bool = False, cached: bool = False,
+                 add_self_loops: bool = True):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.improved, self.cached, self.add_self_loops = improved, cached, add_self_loops
+        for g in "zrh":  # creation order as the reference: conv then linear, per gate (:36-76)
+            setattr(self, f"conv_{g}", GCNParams(in_channels, out_channels))
+            setattr(self, f"linear_{g}", torch.nn.Linear(2 * out_channels, out_channels))
+        self._plans = PlanCache()
+
+    def _plan(self, edge_index, edge_weight, num_nodes):
+        flags = (_lib.GCN_IMPROVED if self.improved else 0) | (0 if self.add_self_loops else _lib.GCN_NO_SELF_LOOPS)
+        return self._plans.get(_lib.FLAVOR_GCN, edge_index, edge_weight, num_nodes, flags=flags)
+
+    def _gcn_all(self, plan, X):
+        """[GCN_z(X) | GCN_r(X) | GCN_h(X)] = (A^ X) [Wz|Wr|Wh]^T + [bz|br|bh]."""
+        AX = ops.spmm(plan, 0, X)
+        W = torch.cat([self.conv_z.lin.weight, self.conv_r.lin.weight, self.conv_h.lin.weight], dim=0)
+        b = torch.cat([self.conv_z.bias, self.conv_r.bias, self.conv_h.bias])
+        return torch.nn.functional.linear(AX, W, b)
+
+    def _cell(self, G, H):
+        Co = self.out_channels
+        Gz, Gr, Gh = G[..., :Co], G[..., Co:2 * Co], G[..., 2 * Co:]
+        lin = lambda l, a, b: torch.matmul(a, l.weight[:, :Co].t()) + torch.matmul(b, l.weight[:, Co:].t()) + l.bias
+        Z = torch.sigmoid(lin(self.linear_z, Gz, H))
+        R = torch.sigmoid(lin(self.linear_r, Gr, H))
+        Ht = torch.tanh(lin(self.linear_h, Gh, H * R))
+        return Z * H + (1 - Z) * Ht
+
+    def forward(self, X: torch.FloatTensor, edge_index: torch.LongTensor, edge_weight: torch.FloatTensor = None,
+                H: torch.FloatTensor = None) -> torch.FloatTensor:
+        _require_cuda(X, "X")
+        if H is None:
+            H = torch.zeros(*X.shape[:-1], self.out_channels, device=X.device, dtype=X.dtype)
+        plan = self._plan(edge_index, edge_weight, X.size(-2))
+        return self._cell(self._gcn_all(plan, X), H)
+
+
+class TGCN2(TGCN):
+    """Batched variant (temporalgcn.py:133-233): X (B,N,F), H (B,N,out); `batch_size` kept for signature
+    compatibility only (as in the reference, :147-148)."""
+
+    def __init__(self, in_channels: int, out_channels: int, batch_size: int, improved: bool = False, cached: bool = False,
+                 add_self_loops: bool = True):
+        super().__init__(in_channels, out_channels, improved, cached, add_self_loops)
+        self.batch_size = batch_size

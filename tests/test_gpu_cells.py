@@ -1,0 +1,165 @@
+"""GPU parity of the ChebConv / GCNConv cells and ASTGCN through the public modules, against the committed
+reference goldens (tests/golden/make_goldens.py).  Strict fp32: rtol=1e-4, atol=1e-5."""
+import os
+
+import pytest
+import torch
+
+from oracle import recurrent as R
+from pytorch_geometric_temporal_b200 import _lib
+from pytorch_geometric_temporal_b200.dataset import ChickenpoxDatasetLoader, synthetic
+from pytorch_geometric_temporal_b200.nn.attention import ASTGCN, ChebConvAttention
+from pytorch_geometric_temporal_b200.nn.recurrent import A3TGCN, A3TGCN2, GConvGRU, GConvLSTM, TGCN, TGCN2
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _load(golden_dir, name):
+    return torch.load(os.path.join(golden_dir, name + ".pt"), weights_only=False)
+
+
+def _close(got, want, rtol=1e-4, atol=1e-5):
+    got = got.detach().cpu()
+    assert got.shape == want.shape
+    assert torch.allclose(got, want, rtol=rtol, atol=atol), f"max abs err {(got - want).abs().max():.3e}"
+
+
+def test_gconv_gru_goldens(golden_dir):
+    g = _load(golden_dir, "gconv_gru_small")
+    ei, ew = g["edge_index"].to(DEV), g["edge_weight"].to(DEV)
+    for name, c in g["cases"].items():
+        m = GConvGRU(4, 16, c["K"], normalization=c["normalization"]).to(DEV)
+        m.load_state_dict(c["state"])
+        lm = None if c["lambda_max"] is None else c["lambda_max"].to(DEV)
+        n0 = _lib.launch_count()
+        with torch.no_grad():
+            _close(m(c["X"].to(DEV), ei, ew, c["H"].to(DEV), lm), c["out"])     # fused gate kernels
+        assert c["K"] == 1 or _lib.launch_count() > n0
+        _close(m(c["X"].to(DEV), ei, ew, c["H"].to(DEV), lm), c["out"])         # autograd path
+
+
+def test_gconv_lstm_goldens(golden_dir):
+    g = _load(golden_dir, "gconv_lstm_small")
+    ei, ew = g["edge_index"].to(DEV), g["edge_weight"].to(DEV)
+    for c in g["cases"].values():
+        m = GConvLSTM(4, 16, c["K"]).to(DEV)
+        m.load_state_dict(c["state"])
+        with torch.no_grad():
+            h, cc = m(c["X"].to(DEV), ei, ew, c["H"].to(DEV), c["C"].to(DEV))
+            _close(h, c["outH"]); _close(cc, c["outC"])
+            h, cc = m(c["X"].to(DEV), ei)                                         # no weights, no state
+            _close(h, c["outH0"]); _close(cc, c["outC0"])
+        h, cc = m(c["X"].to(DEV), ei, ew, c["H"].to(DEV), c["C"].to(DEV))        # autograd path
+        _close(h, c["outH"]); _close(cc, c["outC"])
+
+
+def test_gconv_gru_chickenpox_recurrence_config1():
+    """BASELINE config 1: GConvGRU on the chickenpox signal (20 nodes, 4 lags), H carried over snapshots."""
+    ds = ChickenpoxDatasetLoader().get_dataset(lags=4)
+    torch.manual_seed(0)
+    m = GConvGRU(4, 32, 2)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    mg = m.to(DEV)
+    Hc, Hg = None, None
+    for t, snap in enumerate(ds):
+        if t == 12:
+            break
+        Hc = R.gconv_gru_cell(sd, snap.x, snap.edge_index, snap.edge_attr, Hc)
+        s = snap.to(DEV)
+        with torch.no_grad():
+            Hg = mg(s.x, s.edge_index, s.edge_attr, Hg)
+        _close(Hg, Hc)
+
+
+def test_gconv_lstm_large_graph_vs_oracle():
+    """cfg5 shape class: N=10^4, E=10^5, 64 hidden, K=3 (tiled path: SpMM kernels + cuBLAS)."""
+    ei, ew = synthetic.large_graph(10000, 100000, 0)
+    ei, ew = torch.from_numpy(ei), torch.from_numpy(ew)
+    torch.manual_seed(0)
+    m = GConvLSTM(64, 64, 3)
+    X, H, C = torch.randn(10000, 64), torch.randn(10000, 64) * 0.5, torch.randn(10000, 64) * 0.5
+    wh, wc = R.gconv_lstm_cell(m.state_dict(), X, ei, ew, H, C)
+    with torch.no_grad():
+        h, c = m.to(DEV)(X.to(DEV), ei.to(DEV), ew.to(DEV), H.to(DEV), C.to(DEV))
+    _close(h, wh); _close(c, wc)
+
+
+def test_tgcn_goldens(golden_dir):
+    g = _load(golden_dir, "tgcn_small")
+    ei, ew = g["edge_index"].to(DEV), g["edge_weight"].to(DEV)
+    for c in g["cases"].values():
+        m = TGCN(4, 16, improved=c["improved"], add_self_loops=c["add_self_loops"]).to(DEV)
+        m.load_state_dict(c["state"])
+        _close(m(c["X"].to(DEV), ei, ew, c["H"].to(DEV)), c["out"])
+        m2 = TGCN2(4, 16, 3, improved=c["improved"], add_self_loops=c["add_self_loops"]).to(DEV)
+        m2.load_state_dict(c["state2"])
+        _close(m2(c["X2"].to(DEV), ei, ew, c["H2"].to(DEV)), c["out2"])
+
+
+def test_a3tgcn_goldens(golden_dir):
+    g = _load(golden_dir, "a3tgcn_small")
+    ei, ew = g["edge_index"].to(DEV), g["edge_weight"].to(DEV)
+    m = A3TGCN2(2, 16, 6, 3).to(DEV)
+    m.load_state_dict(g["state"])
+    _close(m(g["X"].to(DEV), ei, ew), g["out"])
+    _close(m(g["X"].to(DEV), ei, ew, torch.full((3, 40, 16), 0.3, device=DEV)), g["outH"])
+    m1 = A3TGCN(2, 16, 6).to(DEV)
+    m1.load_state_dict(g["state1"])
+    _close(m1(g["X1"].to(DEV), ei, ew), g["out1"])
+
+
+def test_a3tgcn2_config3_shape_vs_oracle():
+    """BASELINE config 3: A3TGCN2 on the PEMS-BAY shape (325 nodes, batch 64, 12 periods)."""
+    ei, ew, _ = synthetic.pems_bay_like(0, 16)
+    ei, ew = torch.from_numpy(ei), torch.from_numpy(ew)
+    torch.manual_seed(0)
+    m = A3TGCN2(2, 32, 12, 64)
+    X = torch.randn(8, 325, 2, 12)  # oracle on 8 of the 64 batch rows (seconds on CPU)
+    want = R.a3tgcn(m.state_dict(), X, ei, ew)
+    got = m.to(DEV)(X.to(DEV), ei.to(DEV), ew.to(DEV))
+    _close(got, want)
+
+
+def test_astgcn_goldens(golden_dir):
+    g = _load(golden_dir, "astgcn_small")
+    ei = g["edge_index"].to(DEV)
+    for c in g["cases"].values():
+        m = ASTGCN(**g["ctor"], normalization=c["normalization"]).to(DEV)
+        m.load_state_dict(c["state"])
+        n0 = _lib.launch_count()
+        with torch.no_grad():
+            out = m(c["X"].to(DEV), ei)
+        assert _lib.launch_count() > n0
+        _close(out, c["out"], rtol=2e-4, atol=2e-5)   # 2 blocks of softmax/LayerNorm amplify cuBLAS-vs-CPU GEMM rounding
+        # per-timestep edge_index LIST path (astgcn.py:453-471)
+        with torch.no_grad():
+            out_l = m(c["X"].to(DEV), [ei] * c["X"].shape[-1])
+        _close(out_l, c["out"], rtol=2e-4, atol=2e-5)
+
+
+def test_chebconv_attention_errors_and_repr():
+    conv = ChebConvAttention(2, 3, 3, None).to(DEV)
+    assert repr(conv) == "ChebConvAttention(2, 3, K=3, normalization=None)"   # test/attention_test.py:197
+    x, S = torch.randn(2, 4, 2, device=DEV), torch.rand(2, 4, 4, device=DEV)
+    ei = torch.tensor([[0, 0, 0, 1, 2, 3], [1, 2, 3, 0, 0, 0]], device=DEV)
+    with pytest.raises(ValueError):
+        conv(x, ei, S)                       # lambda_max mandatory unless "sym" (astgcn.py:135-139)
+    assert conv(x, ei, S, lambda_max=2.0).shape == (2, 4, 3)
+    with pytest.raises(AssertionError):
+        ChebConvAttention(2, 3, 3, "bogus")
+
+
+def test_astgcn_backward_runs_and_matches_oracle_grad(golden_dir):
+    """Training path: gradients flow through the attention-weighted SpMM (stmp_spmm_att_grad)."""
+    from oracle import attention as A
+    g = _load(golden_dir, "astgcn_small")
+    c = g["cases"]["sym"]
+    p = {k: v.clone().requires_grad_(True) for k, v in c["state"].items()}
+    out = A.astgcn(p, c["X"], g["edge_index"], g["ctor"]["nb_block"], "sym", g["ctor"]["time_strides"])
+    out.square().sum().backward()
+    m = ASTGCN(**g["ctor"], normalization="sym").to(DEV)
+    m.load_state_dict(c["state"])
+    m(c["X"].to(DEV), g["edge_index"].to(DEV)).square().sum().backward()
+    for k, prm in m.named_parameters():
+        _close(prm.grad, p[k].grad, rtol=2e-3, atol=2e-4)
