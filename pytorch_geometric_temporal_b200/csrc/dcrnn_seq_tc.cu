@@ -1,0 +1,424 @@
+// dcrnn_seq_tc.cu -- fused DCRNN recurrence with the dense contraction on the 5th-gen tensor cores.
+//
+// Same contract as k_dcrnn_seq (dcrnn_seq.cu) for K=2, Cout=32, Cin<=4, N<=255; what changes is WHERE the
+// S @ [Wz|Wr] and S @ Wh contractions run: `tcgen05.mma.kind::f16` with accumulators in TMEM instead of
+// FFMA in registers (the FFMA contraction is 58% of a step in the FFMA kernel, profiles/r01_dcrnn_seq_v3).
+//
+// fp32 accuracy on fp16 tensor cores: every fp32 operand v is split on the fly into hi = fp16(v) and
+// lo = fp16(v - hi) (22 mantissa bits together; products of fp16 pairs are exact in the fp32 accumulator) and
+// the product is formed as lo*hi + hi*lo + hi*hi -- three MMAs.  Validated stand-alone in tools/tc_probe.cu:
+// max |err| 6e-6 vs fp64 on K=112 dot products, the same order as an fp32 FMA chain (3e-6).
+//
+// Shared memory (<= 227 KB), all operands written by hand in the canonical K-major SWIZZLE_128B layout
+// (row pitch 128 B = 64 fp16, 16-byte chunk index XOR (row % 8), 8-row atoms of 1024 B):
+//   A_hi / A_lo : 2 K-panels x 208 rows   k = [H|H*R (32) , P_o H (32)] , [P_i H (32), X(4) P_oX(4) P_iX(4) 0(4)]
+//   B_hi / B_lo : 2 K-panels x 96 rows    rows = output channels of z | r | h, same k order (7 k-steps of 16)
+//   U  fp32 [N][36] = [H | X] : the gather source of the diffusion (tensor cores only see the fp16 split)
+//   graph (padded / pre-scaled / length-sorted, dcrnn_common.cuh), biases, 4 mbarriers.
+// TMEM (256 columns): z|r accumulators of the two 128-row tiles at columns [0,64) [64,128), candidate at
+// [128,160) [160,192).  TMEM lane == row, so thread (warp w, lane l) owns row 128*(w/4) + 32*(w%4) + l for the
+// whole step: it reads its 64+32 accumulator columns with tcgen05.ld, applies the gates, keeps Z and H in
+// registers, and writes H*R / H_t back as fp32 (U), as fp16 hi/lo (A panel) and to HBM.
+#include <cuda_fp16.h>
+
+#include <cstdlib>
+
+#include "common.cuh"
+#include "dcrnn_common.cuh"
+
+namespace stmp {
+namespace {
+
+constexpr int kMaxSmemTc = 232448;
+constexpr int TC_NT = 256;
+constexpr int TC_UP = 36;                  // U row pitch (floats): [H(32) | X(4)]
+constexpr int TC_AROWS = 208;              // rows stored per A panel (tile 1 over-reads into the next buffer: harmless)
+constexpr int TC_PANEL_A = TC_AROWS * 128;
+constexpr int TC_PANEL_B = 96 * 128;
+constexpr int TC_TMEM_COLS = 256;
+
+struct TcParams {
+  int N, CIN, T;
+  long long B;
+  const int* rowptr[2];
+  const int2* cv[2];
+  const float* x;
+  const long long* win_start;
+  long long x_bstride, x_tstride;
+  const float* w[3];
+  const float* bias[3];
+  const float* h0;
+  float* out;
+  float* stash;
+  int off_A, off_B, off_U, off_gstart, off_order, off_ce, off_bias, off_bar;
+};
+
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  // cute::UMMA::SmemDescriptor: start>>4 [0,14) | LBO>>4 [16,30) (unused: swizzled K-major) | SBO>>4 [32,46) = 1024 B |
+  // version [46,48) = 1 (sm_100) | layout_type [61,64) = 2 (SWIZZLE_128B)
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ constexpr uint32_t umma_idesc_f16(int m, int n) {
+  // cute::UMMA::InstrDescriptor: c_format [4,6) = 1 (F32); a/b_format = 0 (F16); a/b_major = 0 (K); n>>3 at [17,23); m>>4 at [24,29)
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,"
+      "%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]),
+        "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]),
+        "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// byte offset of element (row, kin) inside a K-panel (kin in [0,64))
+__device__ __forceinline__ int sw128(int row, int kin) { return row * 128 + ((((kin >> 3) ^ (row & 7))) << 4) + ((kin & 7) << 1); }
+
+__device__ __forceinline__ uint32_t pack_h2(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
+
+// split 4 floats into fp16 hi/lo and store them (8 B each) at k offset `kin` (multiple of 4) of `row`
+__device__ __forceinline__ void store_split4(unsigned char* a_hi, unsigned char* a_lo, int row, int kin, float4 v) {
+  const __half2 h01 = __floats2half2_rn(v.x, v.y), h23 = __floats2half2_rn(v.z, v.w);
+  const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+  const __half2 l01 = __floats2half2_rn(v.x - f01.x, v.y - f01.y), l23 = __floats2half2_rn(v.z - f23.x, v.w - f23.y);
+  const int off = sw128(row, kin);
+  *reinterpret_cast<uint2*>(a_hi + off) = make_uint2(pack_h2(h01), pack_h2(h23));
+  *reinterpret_cast<uint2*>(a_lo + off) = make_uint2(pack_h2(l01), pack_h2(l23));
+}
+// split 32 floats (one row's H-like vector) into panel 0, k 0..31 : 4 swizzled 16-byte chunks for hi and for lo
+__device__ __forceinline__ void store_split_row32(unsigned char* a_hi, unsigned char* a_lo, int row, const float (&v)[32]) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint32_t hw[4], lw[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float a = v[8 * c + 2 * j], b = v[8 * c + 2 * j + 1];
+      const __half2 h = __floats2half2_rn(a, b);
+      const float2 f = __half22float2(h);
+      hw[j] = pack_h2(h);
+      lw[j] = pack_h2(__floats2half2_rn(a - f.x, b - f.y));
+    }
+    const int off = row * 128 + ((c ^ (row & 7)) << 4);
+    *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+    *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+  }
+}
+
+// fast, accurate-enough gates (abs err ~2e-7): ex2.approx + rcp.approx
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float tanh_fast(float x) { return 2.0f * __fdividef(1.0f, 1.0f + __expf(-2.0f * x)) - 1.0f; }
+
+// One diffusion round: gather fp32 rows of U, write the products as fp16 hi/lo into the A panels.
+//   op 0 (P_o): H part -> panel 0 k 32..63, X part -> panel 1 k 36..39
+//   op 1 (P_i): H part -> panel 1 k 0..31,  X part -> panel 1 k 40..43
+__device__ __forceinline__ void diffuse_tc(const float* U, const GraphSmem g, int N, unsigned char* a_hi, unsigned char* a_lo,
+                                           bool with_x, int tid) {
+  const int j = tid & 7;
+  for (int slot = tid >> 3; slot < 2 * N; slot += TC_NT / 8) {
+    const int task = g.order[slot];
+    const int op = task >= N ? 1 : 0;
+    const int i = task - op * N;
+    const float4 acc = gather_row(U + 4 * j, g.ce, g.gstart[task], g.gstart[task + 1]);
+    const int pb = op ? TC_PANEL_A : 0;
+    store_split4(a_hi + pb, a_lo + pb, i, (op ? 0 : 32) + 4 * j, acc);
+  }
+  if (with_x) {
+    for (int slot = tid; slot < 2 * N; slot += TC_NT) {
+      const int task = g.order[slot];
+      const int op = task >= N ? 1 : 0;
+      const int i = task - op * N;
+      const float4 acc = gather_row(U + 32, g.ce, g.gstart[task], g.gstart[task + 1]);
+      store_split4(a_hi + TC_PANEL_A, a_lo + TC_PANEL_A, i, op ? 40 : 36, acc);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(TC_NT, 1) k_dcrnn_seq_tc(const TcParams p) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int N = p.N, CIN = p.CIN, T = p.T;
+  const int C = 32 + CIN;
+
+  unsigned char* a_hi = smem + p.off_A;
+  unsigned char* a_lo = a_hi + 2 * TC_PANEL_A;
+  unsigned char* b_hi = smem + p.off_B;
+  unsigned char* b_lo = b_hi + 2 * TC_PANEL_B;
+  float* U = reinterpret_cast<float*>(smem + p.off_U);
+  int* s_gstart = reinterpret_cast<int*>(smem + p.off_gstart);
+  int* s_order = reinterpret_cast<int*>(smem + p.off_order);
+  int2* s_ce = reinterpret_cast<int2*>(smem + p.off_ce);
+  float* Bs = reinterpret_cast<float*>(smem + p.off_bias);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.off_bar);   // [4]: gemm1 tile0/1, gemm2 tile0/1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+
+  if (blockIdx.x >= p.B) return;
+
+  // ---- one-time per CTA ------------------------------------------------------------------------------------
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TC_TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+    for (int i = 0; i < 4; ++i) mbar_init(&bars[i], 1);
+    fence_mbar_init();
+  }
+  {  // zero A (pad columns / rows must be finite) and B
+    uint4* z = reinterpret_cast<uint4*>(a_hi);
+    for (int i = tid; i < (4 * TC_PANEL_A + 4 * TC_PANEL_B) / 16; i += TC_NT) z[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < N * TC_UP; i += TC_NT) U[i] = 0.f;
+  }
+  stage_graph<TC_NT>(p.rowptr[0], p.rowptr[1], p.cv[0], p.cv[1], N, TC_UP, s_ce, s_gstart, s_order, tid);
+  __syncthreads();
+  // weights -> B operand (fp16 hi/lo, swizzled).  Row n = gate*32 + out channel; k order as the A panels.
+  for (int idx = tid; idx < 96 * 112; idx += TC_NT) {
+    const int n = idx / 112, kk = idx - n * 112;
+    const int gte = n >> 5, o = n & 31;
+    const int panel = kk >= 64 ? 1 : 0, kin = kk - 64 * panel;
+    int blk, ch;  // blk 0: U, 1: P_o, 2: P_i ; ch = reference channel index or -1
+    if (panel == 0) { blk = kin < 32 ? 0 : 1; ch = CIN + (kin & 31); }
+    else if (kin < 32) { blk = 2; ch = CIN + kin; }
+    else { const int q = kin - 32; blk = q >> 2; const int c = q & 3; ch = (blk < 3 && c < CIN) ? c : -1; }
+    float v = 0.f;
+    if (ch >= 0) {
+      const float* wg = gte == 0 ? p.w[0] : (gte == 1 ? p.w[1] : p.w[2]);
+      if (blk == 0) v = wg[((0 * 2 + 0) * C + ch) * 32 + o] + wg[((1 * 2 + 0) * C + ch) * 32 + o];
+      else v = wg[(((blk - 1) * 2 + 1) * C + ch) * 32 + o];
+    }
+    const __half h = __float2half_rn(v);
+    const __half l = __float2half_rn(v - __half2float(h));
+    const int off = panel * TC_PANEL_B + sw128(n, kin);
+    *reinterpret_cast<__half*>(b_hi + off) = h;
+    *reinterpret_cast<__half*>(b_lo + off) = l;
+  }
+  for (int idx = tid; idx < 96; idx += TC_NT) {
+    const int gte = idx >> 5;
+    const float* bg = gte == 0 ? p.bias[0] : (gte == 1 ? p.bias[1] : p.bias[2]);
+    Bs[idx] = bg ? bg[idx & 31] : 0.f;
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  const GraphSmem gs{s_ce, s_gstart, s_order};
+  const int tile = warp >> 2, q = warp & 3;
+  const int row = tile * 128 + q * 32 + lane;        // TMEM lane == row
+  const bool live = row < N;
+  const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
+  const uint32_t a_hi_s = smem_u32(a_hi), a_lo_s = smem_u32(a_lo), b_hi_s = smem_u32(b_hi), b_lo_s = smem_u32(b_lo);
+  constexpr uint32_t ID64 = umma_idesc_f16(128, 64), ID32 = umma_idesc_f16(128, 32);
+  uint32_t parity = 0;
+
+  // issue the 3 x 7 MMAs of one (tile, gemm) and commit them to `bar`          (one thread)
+  auto issue = [&](int tl, int gm, uint64_t* bar) {
+    const uint32_t dcol = gm == 0 ? 64u * tl : 128u + 32u * tl;
+    uint32_t acc = 0;
+#pragma unroll
+    for (int pass = 0; pass < 3; ++pass) {           // lo*hi, hi*lo, hi*hi (small terms first)
+      const uint32_t ab = (pass == 0 ? a_lo_s : a_hi_s) + tl * (128 * 128);
+      const uint32_t bb = (pass == 1 ? b_lo_s : b_hi_s) + (gm ? 64 * 128 : 0);
+#pragma unroll
+      for (int ks = 0; ks < 7; ++ks) {
+        const int panel = ks >> 2, kin = (ks & 3) * 16;
+        umma_f16(tmem + dcol, umma_desc(ab + panel * TC_PANEL_A + kin * 2), umma_desc(bb + panel * TC_PANEL_B + kin * 2),
+                 gm == 0 ? ID64 : ID32, acc);
+        acc = 1;
+      }
+    }
+    umma_commit(bar);
+  };
+
+  auto x_base = [&](long long b) -> const float* { return p.x + (p.win_start ? p.win_start[b] * p.x_tstride : b * p.x_bstride); };
+
+  for (long long b = blockIdx.x; b < p.B; b += gridDim.x) {
+    const float* xb = x_base(b);
+    // ---- window prologue: H_0 and X_0 into U (fp32) and the A panels (fp16 hi/lo) -------------------------------
+    float hreg[32];
+    float xn[4] = {0.f, 0.f, 0.f, 0.f};
+    if (live) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const float4 h = p.h0 ? __ldg(reinterpret_cast<const float4*>(p.h0 + (b * N + row) * 32) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        hreg[4 * c] = h.x; hreg[4 * c + 1] = h.y; hreg[4 * c + 2] = h.z; hreg[4 * c + 3] = h.w;
+        st4(U + row * TC_UP + 4 * c, h);
+      }
+      store_split_row32(a_hi, a_lo, row, hreg);
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (c < CIN) xn[c] = __ldg(xb + row * CIN + c);
+      const float4 xv = make_float4(xn[0], xn[1], xn[2], xn[3]);
+      st4(U + row * TC_UP + 32, xv);
+      store_split4(a_hi + TC_PANEL_A, a_lo + TC_PANEL_A, row, 32, xv);
+    }
+    __syncthreads();
+
+    for (int t = 0; t < T; ++t) {
+      // prefetch X_{t+1} (consumed at the end of the step)
+      if (live && t + 1 < T) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (c < CIN) xn[c] = __ldg(xb + (t + 1) * p.x_tstride + row * CIN + c);
+      }
+      // ---- round 1: diffuse [H | X_t] -----------------------------------------------------------------------
+      diffuse_tc(U, gs, N, a_hi, a_lo, true, tid);
+      fence_proxy_async();
+      tc_fence_before();
+      __syncthreads();
+      tc_fence_after();
+      if (tid == 0) { issue(0, 0, &bars[0]); issue(1, 0, &bars[1]); }
+      // ---- epilogue 1: z, r gates; H*R ------------------------------------------------------------------------
+      mbar_wait(&bars[tile], parity);
+      tc_fence_after();
+      float zreg[32];
+      {
+        uint32_t vz[32], vr[32];
+        tmem_ld32(trow + 64 * tile, vz);
+        tmem_ld32(trow + 64 * tile + 32, vr);
+        tmem_ld_wait();
+        const long long obase = (b * T + t) * (long long)N;
+        float hr[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          zreg[c] = sigmoid_fast(__uint_as_float(vz[c]) + Bs[c]);
+          const float r = sigmoid_fast(__uint_as_float(vr[c]) + Bs[32 + c]);
+          hr[c] = hreg[c] * r;
+          vr[c] = __float_as_uint(r);
+        }
+        if (live) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) st4(U + row * TC_UP + 4 * c, make_float4(hr[4 * c], hr[4 * c + 1], hr[4 * c + 2], hr[4 * c + 3]));
+          store_split_row32(a_hi, a_lo, row, hr);
+          if (p.stash) {
+            float* sp = p.stash + ((obase * 3) + row) * 32;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              st4(sp + 4 * c, make_float4(zreg[4 * c], zreg[4 * c + 1], zreg[4 * c + 2], zreg[4 * c + 3]));
+              st4(sp + (long long)N * 32 + 4 * c, make_float4(__uint_as_float(vr[4 * c]), __uint_as_float(vr[4 * c + 1]),
+                                                              __uint_as_float(vr[4 * c + 2]), __uint_as_float(vr[4 * c + 3])));
+            }
+          }
+        }
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      __syncthreads();
+      tc_fence_after();
+      // ---- round 2: re-diffuse the H*R columns -----------------------------------------------------------------
+      diffuse_tc(U, gs, N, a_hi, a_lo, false, tid);
+      fence_proxy_async();
+      tc_fence_before();
+      __syncthreads();
+      tc_fence_after();
+      if (tid == 0) { issue(0, 1, &bars[2]); issue(1, 1, &bars[3]); }
+      // ---- epilogue 2: candidate, H_t ----------------------------------------------------------------------------
+      mbar_wait(&bars[2 + tile], parity);
+      tc_fence_after();
+      {
+        uint32_t vh[32];
+        tmem_ld32(trow + 128 + 32 * tile, vh);
+        tmem_ld_wait();
+        const long long obase = (b * T + t) * (long long)N;
+        float ht[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          ht[c] = tanh_fast(__uint_as_float(vh[c]) + Bs[64 + c]);
+          hreg[c] = zreg[c] * hreg[c] + (1.0f - zreg[c]) * ht[c];   // dcrnn.py:190-192
+        }
+        if (live) {
+          float* op = p.out + (obase + row) * 32;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float4 hv = make_float4(hreg[4 * c], hreg[4 * c + 1], hreg[4 * c + 2], hreg[4 * c + 3]);
+            st4(U + row * TC_UP + 4 * c, hv);
+            st4(op + 4 * c, hv);
+          }
+          store_split_row32(a_hi, a_lo, row, hreg);
+          if (p.stash) {
+            float* sp = p.stash + ((obase * 3) + 2 * (long long)N + row) * 32;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) st4(sp + 4 * c, make_float4(ht[4 * c], ht[4 * c + 1], ht[4 * c + 2], ht[4 * c + 3]));
+          }
+          if (t + 1 < T) {
+            const float4 xv = make_float4(xn[0], xn[1], xn[2], xn[3]);
+            st4(U + row * TC_UP + 32, xv);
+            store_split4(a_hi + TC_PANEL_A, a_lo + TC_PANEL_A, row, 32, xv);
+          }
+        }
+      }
+      parity ^= 1u;
+      fence_proxy_async();
+      tc_fence_before();
+      __syncthreads();
+      tc_fence_after();
+    }
+  }
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TC_TMEM_COLS));
+}
+
+inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
+
+bool tc_layout(const stmp_plan* plan, TcParams* p, int* smem_bytes) {
+  const int N = plan->n;
+  int off = 0;
+  p->off_A = off; off += 4 * TC_PANEL_A;
+  p->off_B = off; off += 4 * TC_PANEL_B;
+  p->off_U = off; off += align_up(N * TC_UP * 4, 16);
+  p->off_gstart = off; off += align_up((2 * N + 1) * 4, 16);
+  p->off_order = off; off += align_up(2 * N * 4, 16);
+  p->off_ce = off; off += align_up((plan->fwd[0].nnz + plan->fwd[1].nnz + 6 * N + 4) * 8, 16);
+  p->off_bias = off; off += 96 * 4;
+  p->off_bar = off; off += 64;
+  *smem_bytes = off;
+  return off <= kMaxSmemTc;
+}
+
+}  // namespace
+
+bool dcrnn_tc_supported(const stmp_plan* plan, long long cin, long long cout, long long K) {
+  if (!plan || plan->flavor != STMP_FLAVOR_DCONV || plan->n_ops != 2) return false;
+  if (K != 2 || cout != 32 || cin < 1 || cin > 4) return false;
+  if (plan->n > TC_AROWS - 1 || plan->n < 1) return false;
+  TcParams p;
+  int smem = 0;
+  p.N = plan->n;
+  return tc_layout(plan, &p, &smem);
+}
+
+int dcrnn_tc_launch(const stmp_plan* plan, long long B, long long T, long long cin, const float* x, const long long* win_start,
+                    long long x_bstride, long long x_tstride, const float* w_z, const float* w_r, const float* w_h, const float* b_z,
+                    const float* b_r, const float* b_h, const float* h0, float* out, float* stash, cudaStream_t st) {
+  TcParams p;
+  int smem = 0;
+  p.N = plan->n; p.CIN = (int)cin; p.T = (int)T; p.B = B;
+  if (!tc_layout(plan, &p, &smem)) return set_error(STMP_EUNSUPPORTED, "tcgen05 DCRNN kernel needs %d B of shared memory", smem);
+  for (int op = 0; op < 2; ++op) { p.rowptr[op] = plan->fwd[op].rowptr; p.cv[op] = plan->fwd[op].cv; }
+  p.x = x; p.win_start = win_start; p.x_bstride = x_bstride; p.x_tstride = x_tstride;
+  p.w[0] = w_z; p.w[1] = w_r; p.w[2] = w_h; p.bias[0] = b_z; p.bias[1] = b_r; p.bias[2] = b_h;
+  p.h0 = h0; p.out = out; p.stash = stash;
+  int dev = 0, sms = 0;
+  STMP_CUDA_OK(cudaGetDevice(&dev));
+  STMP_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int grid = (int)(B < sms ? B : sms);
+  STMP_CUDA_OK(cudaFuncSetAttribute(k_dcrnn_seq_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  k_dcrnn_seq_tc<<<grid, TC_NT, smem, st>>>(p);
+  STMP_LAUNCH_OK("k_dcrnn_seq_tc");
+  return STMP_OK;
+}
+
+}  // namespace stmp
