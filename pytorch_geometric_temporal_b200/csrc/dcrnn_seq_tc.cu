@@ -18,7 +18,8 @@
 // TMEM (256 columns): z|r accumulators of the two 128-row tiles at columns [0,64) [64,128), candidate at
 // [128,160) [160,192).  TMEM lane == row, so thread (warp w, lane l) owns row 128*(w/4) + 32*(w%4) + l for the
 // whole step: it reads its 64+32 accumulator columns with tcgen05.ld, applies the gates, keeps Z and H in
-// registers, and writes H*R / H_t back as fp32 (U), as fp16 hi/lo (A panel) and to HBM.
+// registers, and writes H*R / H_t back as fp32 (U), as fp16 hi/lo (A panel) and to HBM.  16 warps: each row is
+// shared by two threads (channel halves), which also doubles the warps available to hide the gather latency.
 #include <cuda_fp16.h>
 
 #include <cstdlib>
@@ -30,7 +31,7 @@ namespace stmp {
 namespace {
 
 constexpr int kMaxSmemTc = 232448;
-constexpr int TC_NT = 256;
+constexpr int TC_NT_MAX = 512;             // 16 warps: 2 row tiles x 4 lane quadrants x 2 channel halves (HALVES=2)
 constexpr int TC_UP = 36;                  // U row pitch (floats): [H(32) | X(4)]
 constexpr int TC_AROWS = 208;              // rows stored per A panel (tile 1 over-reads into the next buffer: harmless)
 constexpr int TC_PANEL_A = TC_AROWS * 128;
@@ -84,6 +85,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         "=r"(v[30]), "=r"(v[31])
       : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+template <int CW> __device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t (&v)[CW]);
+template <> __device__ __forceinline__ void tmem_ld<32>(uint32_t taddr, uint32_t (&v)[32]) { tmem_ld32(taddr, v); }
+template <> __device__ __forceinline__ void tmem_ld<16>(uint32_t taddr, uint32_t (&v)[16]) { tmem_ld16(taddr, v); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // byte offset of element (row, kin) inside a K-panel (kin in [0,64))
@@ -119,6 +130,45 @@ __device__ __forceinline__ void store_split_row32(unsigned char* a_hi, unsigned 
   }
 }
 
+// same for one channel half (16 floats -> chunks 2*half, 2*half+1 of panel 0)
+__device__ __forceinline__ void store_split_row16(unsigned char* a_hi, unsigned char* a_lo, int row, int half, const float (&v)[16]) {
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    uint32_t hw[4], lw[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float a = v[8 * c + 2 * j], b = v[8 * c + 2 * j + 1];
+      const __half2 h = __floats2half2_rn(a, b);
+      const float2 f = __half22float2(h);
+      hw[j] = pack_h2(h);
+      lw[j] = pack_h2(__floats2half2_rn(a - f.x, b - f.y));
+    }
+    const int off = row * 128 + (((2 * half + c) ^ (row & 7)) << 4);
+    *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+    *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+  }
+}
+
+// CW = 32 (whole row) or 16 (channel half `half`): chunks [half*CW/8, +CW/8) of panel 0
+template <int CW>
+__device__ __forceinline__ void store_split_row(unsigned char* a_hi, unsigned char* a_lo, int row, int half, const float (&v)[CW]) {
+#pragma unroll
+  for (int c = 0; c < CW / 8; ++c) {
+    uint32_t hw[4], lw[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float a = v[8 * c + 2 * j], b = v[8 * c + 2 * j + 1];
+      const __half2 h = __floats2half2_rn(a, b);
+      const float2 f = __half22float2(h);
+      hw[j] = pack_h2(h);
+      lw[j] = pack_h2(__floats2half2_rn(a - f.x, b - f.y));
+    }
+    const int off = row * 128 + (((half * (CW / 8) + c) ^ (row & 7)) << 4);
+    *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+    *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+  }
+}
+
 // fast, accurate-enough gates (abs err ~2e-7): ex2.approx + rcp.approx
 __device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float tanh_fast(float x) { return 2.0f * __fdividef(1.0f, 1.0f + __expf(-2.0f * x)) - 1.0f; }
@@ -126,6 +176,7 @@ __device__ __forceinline__ float tanh_fast(float x) { return 2.0f * __fdividef(1
 // One diffusion round: gather fp32 rows of U, write the products as fp16 hi/lo into the A panels.
 //   op 0 (P_o): H part -> panel 0 k 32..63, X part -> panel 1 k 36..39
 //   op 1 (P_i): H part -> panel 1 k 0..31,  X part -> panel 1 k 40..43
+template <int TC_NT>
 __device__ __forceinline__ void diffuse_tc(const float* U, const GraphSmem g, int N, unsigned char* a_hi, unsigned char* a_lo,
                                            bool with_x, int tid) {
   const int j = tid & 7;
@@ -148,7 +199,10 @@ __device__ __forceinline__ void diffuse_tc(const float* U, const GraphSmem g, in
   }
 }
 
-__global__ void __launch_bounds__(TC_NT, 1) k_dcrnn_seq_tc(const TcParams p) {
+template <int HALVES>
+__global__ void __launch_bounds__(256 * HALVES, 1) k_dcrnn_seq_tc(const TcParams p) {
+  constexpr int TC_NT = 256 * HALVES;
+  constexpr int CW = 32 / HALVES;   // channels per thread
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int N = p.N, CIN = p.CIN, T = p.T;
@@ -217,8 +271,10 @@ __global__ void __launch_bounds__(TC_NT, 1) k_dcrnn_seq_tc(const TcParams p) {
   const uint32_t tmem = *tmem_slot;
 
   const GraphSmem gs{s_ce, s_gstart, s_order};
-  const int tile = warp >> 2, q = warp & 3;
-  const int row = tile * 128 + q * 32 + lane;        // TMEM lane == row
+  // thread = (row, channel half): warp = half*8 + tile*4 + q ; TMEM lane == row, a warp may only touch lanes 32*(warp%4)..
+  const int half = HALVES == 2 ? (warp >> 3) : 0, tile = (warp >> 2) & 1, q = warp & 3;
+  const int row = tile * 128 + q * 32 + lane;
+  const int ch0 = CW * half;
   const bool live = row < N;
   const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
   const uint32_t a_hi_s = smem_u32(a_hi), a_lo_s = smem_u32(a_lo), b_hi_s = smem_u32(b_hi), b_lo_s = smem_u32(b_lo);
@@ -249,34 +305,36 @@ __global__ void __launch_bounds__(TC_NT, 1) k_dcrnn_seq_tc(const TcParams p) {
   for (long long b = blockIdx.x; b < p.B; b += gridDim.x) {
     const float* xb = x_base(b);
     // ---- window prologue: H_0 and X_0 into U (fp32) and the A panels (fp16 hi/lo) -------------------------------
-    float hreg[32];
+    float hreg[CW];
     float xn[4] = {0.f, 0.f, 0.f, 0.f};
     if (live) {
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const float4 h = p.h0 ? __ldg(reinterpret_cast<const float4*>(p.h0 + (b * N + row) * 32) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int c = 0; c < CW / 4; ++c) {
+        const float4 h = p.h0 ? __ldg(reinterpret_cast<const float4*>(p.h0 + (b * N + row) * 32 + ch0) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
         hreg[4 * c] = h.x; hreg[4 * c + 1] = h.y; hreg[4 * c + 2] = h.z; hreg[4 * c + 3] = h.w;
-        st4(U + row * TC_UP + 4 * c, h);
+        st4(U + row * TC_UP + ch0 + 4 * c, h);
       }
-      store_split_row32(a_hi, a_lo, row, hreg);
+      store_split_row<CW>(a_hi, a_lo, row, half, hreg);
+      if (half == 0) {
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
-        if (c < CIN) xn[c] = __ldg(xb + row * CIN + c);
-      const float4 xv = make_float4(xn[0], xn[1], xn[2], xn[3]);
-      st4(U + row * TC_UP + 32, xv);
-      store_split4(a_hi + TC_PANEL_A, a_lo + TC_PANEL_A, row, 32, xv);
+        for (int c = 0; c < 4; ++c)
+          if (c < CIN) xn[c] = __ldg(xb + row * CIN + c);
+        const float4 xv = make_float4(xn[0], xn[1], xn[2], xn[3]);
+        st4(U + row * TC_UP + 32, xv);
+        store_split4(a_hi + TC_PANEL_A, a_lo + TC_PANEL_A, row, 32, xv);
+      }
     }
     __syncthreads();
 
     for (int t = 0; t < T; ++t) {
       // prefetch X_{t+1} (consumed at the end of the step)
-      if (live && t + 1 < T) {
+      if (live && half == 0 && t + 1 < T) {
 #pragma unroll
         for (int c = 0; c < 4; ++c)
           if (c < CIN) xn[c] = __ldg(xb + (t + 1) * p.x_tstride + row * CIN + c);
       }
       // ---- round 1: diffuse [H | X_t] -----------------------------------------------------------------------
-      diffuse_tc(U, gs, N, a_hi, a_lo, true, tid);
+      diffuse_tc<TC_NT>(U, gs, N, a_hi, a_lo, true, tid);
       fence_proxy_async();
       tc_fence_before();
       __syncthreads();
@@ -285,29 +343,29 @@ __global__ void __launch_bounds__(TC_NT, 1) k_dcrnn_seq_tc(const TcParams p) {
       // ---- epilogue 1: z, r gates; H*R ------------------------------------------------------------------------
       mbar_wait(&bars[tile], parity);
       tc_fence_after();
-      float zreg[32];
+      float zreg[CW];
+      const long long obase = (b * T + t) * (long long)N;
       {
-        uint32_t vz[32], vr[32];
-        tmem_ld32(trow + 64 * tile, vz);
-        tmem_ld32(trow + 64 * tile + 32, vr);
+        uint32_t vz[CW], vr[CW];
+        tmem_ld<CW>(trow + 64 * tile + ch0, vz);
+        tmem_ld<CW>(trow + 64 * tile + 32 + ch0, vr);
         tmem_ld_wait();
-        const long long obase = (b * T + t) * (long long)N;
-        float hr[32];
+        float hr[CW];
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          zreg[c] = sigmoid_fast(__uint_as_float(vz[c]) + Bs[c]);
-          const float r = sigmoid_fast(__uint_as_float(vr[c]) + Bs[32 + c]);
+        for (int c = 0; c < CW; ++c) {
+          zreg[c] = sigmoid_fast(__uint_as_float(vz[c]) + Bs[ch0 + c]);
+          const float r = sigmoid_fast(__uint_as_float(vr[c]) + Bs[32 + ch0 + c]);
           hr[c] = hreg[c] * r;
           vr[c] = __float_as_uint(r);
         }
         if (live) {
 #pragma unroll
-          for (int c = 0; c < 8; ++c) st4(U + row * TC_UP + 4 * c, make_float4(hr[4 * c], hr[4 * c + 1], hr[4 * c + 2], hr[4 * c + 3]));
-          store_split_row32(a_hi, a_lo, row, hr);
+          for (int c = 0; c < CW / 4; ++c) st4(U + row * TC_UP + ch0 + 4 * c, make_float4(hr[4 * c], hr[4 * c + 1], hr[4 * c + 2], hr[4 * c + 3]));
+          store_split_row<CW>(a_hi, a_lo, row, half, hr);
           if (p.stash) {
-            float* sp = p.stash + ((obase * 3) + row) * 32;
+            float* sp = p.stash + ((obase * 3) + row) * 32 + ch0;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
+            for (int c = 0; c < CW / 4; ++c) {
               st4(sp + 4 * c, make_float4(zreg[4 * c], zreg[4 * c + 1], zreg[4 * c + 2], zreg[4 * c + 3]));
               st4(sp + (long long)N * 32 + 4 * c, make_float4(__uint_as_float(vr[4 * c]), __uint_as_float(vr[4 * c + 1]),
                                                               __uint_as_float(vr[4 * c + 2]), __uint_as_float(vr[4 * c + 3])));
@@ -320,7 +378,7 @@ __global__ void __launch_bounds__(TC_NT, 1) k_dcrnn_seq_tc(const TcParams p) {
       __syncthreads();
       tc_fence_after();
       // ---- round 2: re-diffuse the H*R columns -----------------------------------------------------------------
-      diffuse_tc(U, gs, N, a_hi, a_lo, false, tid);
+      diffuse_tc<TC_NT>(U, gs, N, a_hi, a_lo, false, tid);
       fence_proxy_async();
       tc_fence_before();
       __syncthreads();
@@ -330,31 +388,30 @@ __global__ void __launch_bounds__(TC_NT, 1) k_dcrnn_seq_tc(const TcParams p) {
       mbar_wait(&bars[2 + tile], parity);
       tc_fence_after();
       {
-        uint32_t vh[32];
-        tmem_ld32(trow + 128 + 32 * tile, vh);
+        uint32_t vh[CW];
+        tmem_ld<CW>(trow + 128 + 32 * tile + ch0, vh);
         tmem_ld_wait();
-        const long long obase = (b * T + t) * (long long)N;
-        float ht[32];
+        float ht[CW];
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          ht[c] = tanh_fast(__uint_as_float(vh[c]) + Bs[64 + c]);
+        for (int c = 0; c < CW; ++c) {
+          ht[c] = tanh_fast(__uint_as_float(vh[c]) + Bs[64 + ch0 + c]);
           hreg[c] = zreg[c] * hreg[c] + (1.0f - zreg[c]) * ht[c];   // dcrnn.py:190-192
         }
         if (live) {
-          float* op = p.out + (obase + row) * 32;
+          float* op = p.out + (obase + row) * 32 + ch0;
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
+          for (int c = 0; c < CW / 4; ++c) {
             const float4 hv = make_float4(hreg[4 * c], hreg[4 * c + 1], hreg[4 * c + 2], hreg[4 * c + 3]);
-            st4(U + row * TC_UP + 4 * c, hv);
+            st4(U + row * TC_UP + ch0 + 4 * c, hv);
             st4(op + 4 * c, hv);
           }
-          store_split_row32(a_hi, a_lo, row, hreg);
+          store_split_row<CW>(a_hi, a_lo, row, half, hreg);
           if (p.stash) {
-            float* sp = p.stash + ((obase * 3) + 2 * (long long)N + row) * 32;
+            float* sp = p.stash + ((obase * 3) + 2 * (long long)N + row) * 32 + ch0;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) st4(sp + 4 * c, make_float4(ht[4 * c], ht[4 * c + 1], ht[4 * c + 2], ht[4 * c + 3]));
+            for (int c = 0; c < CW / 4; ++c) st4(sp + 4 * c, make_float4(ht[4 * c], ht[4 * c + 1], ht[4 * c + 2], ht[4 * c + 3]));
           }
-          if (t + 1 < T) {
+          if (half == 0 && t + 1 < T) {
             const float4 xv = make_float4(xn[0], xn[1], xn[2], xn[3]);
             st4(U + row * TC_UP + 32, xv);
             store_split4(a_hi + TC_PANEL_A, a_lo + TC_PANEL_A, row, 32, xv);
@@ -415,8 +472,18 @@ int dcrnn_tc_launch(const stmp_plan* plan, long long B, long long T, long long c
   STMP_CUDA_OK(cudaGetDevice(&dev));
   STMP_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int grid = (int)(B < sms ? B : sms);
-  STMP_CUDA_OK(cudaFuncSetAttribute(k_dcrnn_seq_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  k_dcrnn_seq_tc<<<grid, TC_NT, smem, st>>>(p);
+  static int halves = -1;
+  if (halves < 0) {
+    const char* v = getenv("STMP_DCRNN_TC_HALVES");
+    halves = (v && atoi(v) == 1) ? 1 : 2;   // default: 16 warps (two channel halves per row)
+  }
+  if (halves == 2) {
+    STMP_CUDA_OK(cudaFuncSetAttribute(k_dcrnn_seq_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    k_dcrnn_seq_tc<2><<<grid, 512, smem, st>>>(p);
+  } else {
+    STMP_CUDA_OK(cudaFuncSetAttribute(k_dcrnn_seq_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    k_dcrnn_seq_tc<1><<<grid, 256, smem, st>>>(p);
+  }
   STMP_LAUNCH_OK("k_dcrnn_seq_tc");
   return STMP_OK;
 }

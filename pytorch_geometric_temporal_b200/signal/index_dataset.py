@@ -120,3 +120,53 @@ def index_splits(t_total: int, lags: int, ratio=(0.7, 0.1, 0.2)):
     n_tr, n_te = round(n * ratio[0]), round(n * ratio[2])
     n_va = n - n_tr - n_te
     return x_i[:n_tr], x_i[n_tr:n_tr + n_va], x_i[-n_te:]
+
+
+class DevicePrefetcher(object):
+    """Wraps an iterator of pinned host batches (tensors or tuples of tensors): the H2D copy of batch i+1 is
+    issued on a side stream while batch i is being consumed on the current stream.  Replaces the per-batch
+    blocking `.to(device)` of the reference's training loops (examples/indexBatching/DCRNN/pems_ddp.py:104-108)."""
+
+    def __init__(self, it, device):
+        self.it, self.device = iter(it), torch.device(device)
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self.bufs, self.slot = [None, None], 0   # two staging buffers per tensor position
+        self.next = None
+        self._preload()
+
+    def _to_dev(self, t, pos):
+        key = (pos, tuple(t.shape), t.dtype)
+        bank = self.bufs[self.slot]
+        if bank is None:
+            bank = self.bufs[self.slot] = {}
+        buf = bank.get(key)
+        if buf is None:
+            buf = bank[key] = torch.empty(t.shape, dtype=t.dtype, device=self.device)
+        buf.copy_(t, non_blocking=True)
+        return buf
+
+    def _preload(self):
+        try:
+            batch = next(self.it)
+        except StopIteration:
+            self.next = None
+            return
+        with torch.cuda.stream(self.copy_stream):
+            # the staging buffer of this slot was last read two batches ago on the compute stream
+            self.copy_stream.wait_stream(torch.cuda.current_stream(self.device))
+            if torch.is_tensor(batch):
+                self.next = self._to_dev(batch, 0)
+            else:
+                self.next = tuple(self._to_dev(t, i) for i, t in enumerate(batch))
+        self.slot ^= 1
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        if self.next is None:
+            raise StopIteration
+        torch.cuda.current_stream(self.device).wait_stream(self.copy_stream)
+        batch = self.next
+        self._preload()
+        return batch
