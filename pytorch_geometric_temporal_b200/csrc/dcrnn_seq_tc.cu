@@ -92,7 +92,13 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
         "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr));
+}
 template <int CW> __device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t (&v)[CW]);
+template <> __device__ __forceinline__ void tmem_ld<8>(uint32_t taddr, uint32_t (&v)[8]) { tmem_ld8(taddr, v); }
 template <> __device__ __forceinline__ void tmem_ld<32>(uint32_t taddr, uint32_t (&v)[32]) { tmem_ld32(taddr, v); }
 template <> __device__ __forceinline__ void tmem_ld<16>(uint32_t taddr, uint32_t (&v)[16]) { tmem_ld16(taddr, v); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
@@ -178,9 +184,9 @@ __device__ __forceinline__ float tanh_fast(float x) { return 2.0f * __fdividef(1
 //   op 1 (P_i): H part -> panel 1 k 0..31,  X part -> panel 1 k 40..43
 template <int TC_NT>
 __device__ __forceinline__ void diffuse_tc(const float* U, const GraphSmem g, int N, unsigned char* a_hi, unsigned char* a_lo,
-                                           bool with_x, int tid) {
+                                           bool with_x, int tid, int s_beg, int s_end) {
   const int j = tid & 7;
-  for (int slot = tid >> 3; slot < 2 * N; slot += TC_NT / 8) {
+  for (int slot = s_beg + (tid >> 3); slot < s_end; slot += TC_NT / 8) {
     const int task = g.order[slot];
     const int op = task >= N ? 1 : 0;
     const int i = task - op * N;
@@ -189,7 +195,7 @@ __device__ __forceinline__ void diffuse_tc(const float* U, const GraphSmem g, in
     store_split4(a_hi + pb, a_lo + pb, i, (op ? 0 : 32) + 4 * j, acc);
   }
   if (with_x) {
-    for (int slot = tid; slot < 2 * N; slot += TC_NT) {
+    for (int slot = s_beg + tid; slot < s_end; slot += TC_NT) {
       const int task = g.order[slot];
       const int op = task >= N ? 1 : 0;
       const int i = task - op * N;
@@ -334,7 +340,7 @@ __global__ void __launch_bounds__(256 * HALVES, 1) k_dcrnn_seq_tc(const TcParams
           if (c < CIN) xn[c] = __ldg(xb + (t + 1) * p.x_tstride + row * CIN + c);
       }
       // ---- round 1: diffuse [H | X_t] -----------------------------------------------------------------------
-      diffuse_tc<TC_NT>(U, gs, N, a_hi, a_lo, true, tid);
+      diffuse_tc<TC_NT>(U, gs, N, a_hi, a_lo, true, tid, 0, 2 * N);
       fence_proxy_async();
       tc_fence_before();
       __syncthreads();
@@ -378,7 +384,7 @@ __global__ void __launch_bounds__(256 * HALVES, 1) k_dcrnn_seq_tc(const TcParams
       __syncthreads();
       tc_fence_after();
       // ---- round 2: re-diffuse the H*R columns -----------------------------------------------------------------
-      diffuse_tc<TC_NT>(U, gs, N, a_hi, a_lo, false, tid);
+      diffuse_tc<TC_NT>(U, gs, N, a_hi, a_lo, false, tid, 0, 2 * N);
       fence_proxy_async();
       tc_fence_before();
       __syncthreads();
@@ -428,6 +434,7 @@ __global__ void __launch_bounds__(256 * HALVES, 1) k_dcrnn_seq_tc(const TcParams
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TC_TMEM_COLS));
 }
 
+
 inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
 
 bool tc_layout(const stmp_plan* plan, TcParams* p, int* smem_bytes) {
@@ -475,7 +482,7 @@ int dcrnn_tc_launch(const stmp_plan* plan, long long B, long long T, long long c
   static int halves = -1;
   if (halves < 0) {
     const char* v = getenv("STMP_DCRNN_TC_HALVES");
-    halves = (v && atoi(v) == 1) ? 1 : 2;   // default: 16 warps (two channel halves per row)
+    halves = (v && atoi(v) == 1) ? 1 : 2;   // 2 (default): 16 warps, two channel halves per row; 1: 8 warps
   }
   if (halves == 2) {
     STMP_CUDA_OK(cudaFuncSetAttribute(k_dcrnn_seq_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
