@@ -128,6 +128,20 @@ int stmp_dcrnn_seq_fwd(const stmp_plan* plan, int64_t B, int64_t T, int64_t cin,
 /* 1 if stmp_dcrnn_seq_fwd can take this configuration on the current device, else 0. */
 int stmp_dcrnn_seq_supported(const stmp_plan* plan, int64_t cin, int64_t cout, int64_t K);
 
+/* Generic fused graph-GRU recurrence on the tensor cores (tcgen05, fp16 hi/lo operand split = fp32-class accuracy):
+ *   pre_g = [H' | Op0 H' | Op1 H' | X | Op0 X | Op1 X] @ wcat_g^T + bcat_g      g in {z, r, h};  H' = H (z, r) or H*R (h)
+ *   Z = sigmoid(pre_z); R = sigmoid(pre_r); Ht = tanh(pre_h); H_t = Z*H + (1-Z)*Ht
+ * with the first `n_ops` (0..2) operators of `plan` (any flavor).  This one kernel serves DCRNN K=2 (DConv plan, 2 ops),
+ * GConvGRU K<=2 (gconv_gru.py:119-139; CHEB plan, 1 op) and TGCN / A3TGCN(2) (temporalgcn.py:82-102; GCN plan, 1 op:
+ * the GCNConv weight and the gate Linear are folded into wcat on the host side).  Cout = 32, cin <= 4, N <= 207.
+ *   wcat: [96][112] fp32, row = gate*32 + out channel, columns = H(32) | Op0 H(32) | Op1 H(32) | X(4) | Op0 X(4) | Op1 X(4) | 0(4)
+ *   bcat: [96];  h0: [B,N,32] (h0_bstride = N*32), one shared [N,32] (h0_bstride = 0) or NULL (zeros)
+ * x / win_start / strides / out / stash as stmp_dcrnn_seq_fwd.  STMP_EUNSUPPORTED outside the envelope. */
+int stmp_gru_seq_fwd(const stmp_plan* plan, int n_ops, int64_t B, int64_t T, int64_t cin, const float* x,
+                     const int64_t* win_start, int64_t x_bstride, int64_t x_tstride, const float* wcat,
+                     const float* bcat, const float* h0, int64_t h0_bstride, float* out, float* stash, void* stream);
+int stmp_gru_seq_supported(const stmp_plan* plan, int n_ops, int64_t cin, int64_t cout);
+
 /* ---- K5: gate epilogues for the tiled path -------------------------------------------------------
  * GRU (dcrnn.py:172-192, gconv_gru.py:119-139, temporalgcn.py:82-102), n = number of elements:
  *   stmp_gru_zr:   z = sigmoid(pz); r = sigmoid(pr); hr = h * r

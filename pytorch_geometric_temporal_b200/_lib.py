@@ -39,6 +39,8 @@ _SIGNATURES = {
     "stmp_dcrnn_seq_fwd": (c_int, [_P, c_int64, c_int64, c_int64, c_int64, c_int64, _P, _P, c_int64, c_int64,
                                    _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "stmp_dcrnn_seq_supported": (c_int, [_P, c_int64, c_int64, c_int64]),
+    "stmp_gru_seq_fwd": (c_int, [_P, c_int, c_int64, c_int64, c_int64, _P, _P, c_int64, c_int64, _P, _P, _P, c_int64, _P, _P, _P]),
+    "stmp_gru_seq_supported": (c_int, [_P, c_int, c_int64, c_int64]),
     "stmp_gru_zr": (c_int, [c_int64, _P, _P, _P, _P, _P, _P, _P]),
     "stmp_gru_out": (c_int, [c_int64, _P, _P, _P, _P, _P, _P]),
     "stmp_lstm_ifc": (c_int, [c_int64, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),

@@ -62,9 +62,10 @@ __device__ __forceinline__ float4 gather_row(const float* __restrict__ Sc, const
 template <int NT>
 __device__ __forceinline__ void stage_graph(const int* __restrict__ grp0, const int* __restrict__ grp1, const int2* __restrict__ gcv0,
                                             const int2* __restrict__ gcv1, int N, int pitch, int2* s_ce, int* s_gstart, int* s_order,
-                                            int tid, int split_row = 1 << 30) {
+                                            int tid, int split_row = 1 << 30, int n_ops = 2) {
+  const int NTASK = n_ops * N;
   int* s_len = s_order;  // scratch until the ranking pass writes it
-  for (int task = tid; task < 2 * N; task += NT) {
+  for (int task = tid; task < NTASK; task += NT) {
     const int op = task >= N ? 1 : 0, i = task - op * N;
     const int* rp = op ? grp1 : grp0;
     s_len[task] = (rp[i + 1] - rp[i] + 3) & ~3;
@@ -72,11 +73,11 @@ __device__ __forceinline__ void stage_graph(const int* __restrict__ grp0, const 
   __syncthreads();
   if (tid == 0) {
     int run = 0;
-    for (int task = 0; task < 2 * N; ++task) { s_gstart[task] = run; run += s_len[task]; }
-    s_gstart[2 * N] = run;
+    for (int task = 0; task < NTASK; ++task) { s_gstart[task] = run; run += s_len[task]; }
+    s_gstart[NTASK] = run;
   }
   __syncthreads();
-  for (int task = tid; task < 2 * N; task += NT) {
+  for (int task = tid; task < NTASK; task += NT) {
     const int op = task >= N ? 1 : 0, i = task - op * N;
     const int* rp = op ? grp1 : grp0;
     const int2* cv = op ? gcv1 : gcv0;
@@ -91,11 +92,11 @@ __device__ __forceinline__ void stage_graph(const int* __restrict__ grp0, const 
   __syncthreads();
   // order tasks: rows >= split_row first (the second MMA row tile of the tcgen05 kernel), then by descending
   // padded length (rank = number of tasks that sort before this one)
-  for (int task = tid; task < 2 * N; task += NT) {
+  for (int task = tid; task < NTASK; task += NT) {
     const int len = s_gstart[task + 1] - s_gstart[task];
     const int hi = ((task >= N ? task - N : task) >= split_row) ? 1 : 0;
     int rank = 0;
-    for (int o = 0; o < 2 * N; ++o) {
+    for (int o = 0; o < NTASK; ++o) {
       const int lo = s_gstart[o + 1] - s_gstart[o];
       const int ho = ((o >= N ? o - N : o) >= split_row) ? 1 : 0;
       rank += (ho > hi) || (ho == hi && ((lo > len) || (lo == len && o < task)));

@@ -30,6 +30,11 @@ int dcrnn_tc_launch(const stmp_plan* plan, long long B, long long T, long long c
                     long long x_bstride, long long x_tstride, const float* w_z, const float* w_r, const float* w_h, const float* b_z,
                     const float* b_r, const float* b_h, const float* h0, float* out, float* stash, cudaStream_t st);
 
+bool gru_tc_supported(const stmp_plan* plan, long long cin);
+int gru_tc_launch(const stmp_plan* plan, int n_ops, long long B, long long T, long long cin, const float* x, const long long* win_start,
+                  long long x_bstride, long long x_tstride, const float* wcat, const float* bcat, const float* h0, long long h0_bstride,
+                  float* out, float* stash, cudaStream_t st);
+
 namespace {
 
 constexpr int kMaxSmem = 232448;  // 227 KB opt-in limit per CTA on sm_100
@@ -465,4 +470,23 @@ extern "C" int stmp_dcrnn_seq_fwd(const stmp_plan* plan, int64_t B, int64_t T, i
   }
   if (cout == 16) return launch_rt<16>(L, grid, st, variant);
   return launch_rt<32>(L, grid, st, variant);
+}
+
+extern "C" int stmp_gru_seq_supported(const stmp_plan* plan, int n_ops, int64_t cin, int64_t cout) {
+  if (!plan || n_ops < 0 || n_ops > 2 || n_ops > plan->n_ops || cout != 32) return 0;
+  return gru_tc_supported(plan, cin) ? 1 : 0;
+}
+
+extern "C" int stmp_gru_seq_fwd(const stmp_plan* plan, int n_ops, int64_t B, int64_t T, int64_t cin, const float* x,
+                                const int64_t* win_start, int64_t x_bstride, int64_t x_tstride, const float* wcat,
+                                const float* bcat, const float* h0, int64_t h0_bstride, float* out, float* stash, void* stream) {
+  STMP_REQUIRE(plan != nullptr, STMP_EINVAL, "stmp_gru_seq_fwd: plan is NULL");
+  STMP_REQUIRE(n_ops >= 0 && n_ops <= 2 && n_ops <= plan->n_ops, STMP_EINVAL, "stmp_gru_seq_fwd: n_ops=%d not available in this plan", n_ops);
+  STMP_REQUIRE(B >= 0 && T >= 0, STMP_EINVAL, "stmp_gru_seq_fwd: negative B/T");
+  STMP_REQUIRE(x && wcat && bcat && out, STMP_EINVAL, "stmp_gru_seq_fwd: NULL tensor");
+  if (!gru_tc_supported(plan, cin))
+    return set_error(STMP_EUNSUPPORTED, "fused graph-GRU kernel supports N<=207, cin<=4, cout=32 (got N=%d cin=%lld)", plan->n, (long long)cin);
+  if (B == 0 || T == 0) return STMP_OK;
+  return gru_tc_launch(plan, n_ops, B, T, cin, x, reinterpret_cast<const long long*>(win_start), x_bstride, x_tstride, wcat, bcat, h0,
+                       h0_bstride, out, stash, (cudaStream_t)stream);
 }

@@ -49,6 +49,10 @@ struct TcParams {
   const float* w[3];
   const float* bias[3];
   const float* h0;
+  long long h0_bstride;   // elements between windows' H0 (0: every window starts from the same H0)
+  const float* wcat;      // optional prepacked fp32 weights [96][112] in the kernel's k order (else: DConv weights p.w[])
+  const float* bcat;      // with wcat: biases [96]
+  int n_ops;              // 2: DConv (P_o, P_i); 1: single operator (ChebConv K=2 / GCN); 0: no propagation
   float* out;
   float* stash;
   int off_A, off_B, off_U, off_gstart, off_order, off_ce, off_bias, off_bar;
@@ -242,7 +246,7 @@ __global__ void __launch_bounds__(256 * HALVES, 1) k_dcrnn_seq_tc(const TcParams
     for (int i = tid; i < (4 * TC_PANEL_A + 4 * TC_PANEL_B) / 16; i += TC_NT) z[i] = make_uint4(0, 0, 0, 0);
     for (int i = tid; i < N * TC_UP; i += TC_NT) U[i] = 0.f;
   }
-  stage_graph<TC_NT>(p.rowptr[0], p.rowptr[1], p.cv[0], p.cv[1], N, TC_UP, s_ce, s_gstart, s_order, tid);
+  stage_graph<TC_NT>(p.rowptr[0], p.rowptr[1], p.cv[0], p.cv[1], N, TC_UP, s_ce, s_gstart, s_order, tid, 1 << 30, p.n_ops);
   __syncthreads();
   // weights -> B operand (fp16 hi/lo, swizzled).  Row n = gate*32 + out channel; k order as the A panels.
   for (int idx = tid; idx < 96 * 112; idx += TC_NT) {
@@ -254,7 +258,9 @@ __global__ void __launch_bounds__(256 * HALVES, 1) k_dcrnn_seq_tc(const TcParams
     else if (kin < 32) { blk = 2; ch = CIN + kin; }
     else { const int q = kin - 32; blk = q >> 2; const int c = q & 3; ch = (blk < 3 && c < CIN) ? c : -1; }
     float v = 0.f;
-    if (ch >= 0) {
+    if (p.wcat) {
+      v = p.wcat[idx];
+    } else if (ch >= 0) {
       const float* wg = gte == 0 ? p.w[0] : (gte == 1 ? p.w[1] : p.w[2]);
       if (blk == 0) v = wg[((0 * 2 + 0) * C + ch) * 32 + o] + wg[((1 * 2 + 0) * C + ch) * 32 + o];
       else v = wg[(((blk - 1) * 2 + 1) * C + ch) * 32 + o];
@@ -268,7 +274,7 @@ __global__ void __launch_bounds__(256 * HALVES, 1) k_dcrnn_seq_tc(const TcParams
   for (int idx = tid; idx < 96; idx += TC_NT) {
     const int gte = idx >> 5;
     const float* bg = gte == 0 ? p.bias[0] : (gte == 1 ? p.bias[1] : p.bias[2]);
-    Bs[idx] = bg ? bg[idx & 31] : 0.f;
+    Bs[idx] = p.bcat ? p.bcat[idx] : (bg ? bg[idx & 31] : 0.f);
   }
   fence_proxy_async();
   tc_fence_before();
@@ -286,6 +292,7 @@ __global__ void __launch_bounds__(256 * HALVES, 1) k_dcrnn_seq_tc(const TcParams
   const uint32_t a_hi_s = smem_u32(a_hi), a_lo_s = smem_u32(a_lo), b_hi_s = smem_u32(b_hi), b_lo_s = smem_u32(b_lo);
   constexpr uint32_t ID64 = umma_idesc_f16(128, 64), ID32 = umma_idesc_f16(128, 32);
   uint32_t parity = 0;
+  const bool two_tiles = N > 128;
 
   // issue the 3 x 7 MMAs of one (tile, gemm) and commit them to `bar`          (one thread)
   auto issue = [&](int tl, int gm, uint64_t* bar) {
@@ -316,7 +323,7 @@ __global__ void __launch_bounds__(256 * HALVES, 1) k_dcrnn_seq_tc(const TcParams
     if (live) {
 #pragma unroll
       for (int c = 0; c < CW / 4; ++c) {
-        const float4 h = p.h0 ? __ldg(reinterpret_cast<const float4*>(p.h0 + (b * N + row) * 32 + ch0) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 h = p.h0 ? __ldg(reinterpret_cast<const float4*>(p.h0 + b * p.h0_bstride + row * 32 + ch0) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
         hreg[4 * c] = h.x; hreg[4 * c + 1] = h.y; hreg[4 * c + 2] = h.z; hreg[4 * c + 3] = h.w;
         st4(U + row * TC_UP + ch0 + 4 * c, h);
       }
@@ -340,14 +347,14 @@ __global__ void __launch_bounds__(256 * HALVES, 1) k_dcrnn_seq_tc(const TcParams
           if (c < CIN) xn[c] = __ldg(xb + (t + 1) * p.x_tstride + row * CIN + c);
       }
       // ---- round 1: diffuse [H | X_t] -----------------------------------------------------------------------
-      diffuse_tc<TC_NT>(U, gs, N, a_hi, a_lo, true, tid, 0, 2 * N);
+      diffuse_tc<TC_NT>(U, gs, N, a_hi, a_lo, true, tid, 0, p.n_ops * N);
       fence_proxy_async();
       tc_fence_before();
       __syncthreads();
       tc_fence_after();
-      if (tid == 0) { issue(0, 0, &bars[0]); issue(1, 0, &bars[1]); }
+      if (tid == 0) { issue(0, 0, &bars[0]); if (two_tiles) issue(1, 0, &bars[1]); }
       // ---- epilogue 1: z, r gates; H*R ------------------------------------------------------------------------
-      mbar_wait(&bars[tile], parity);
+      if (tile == 0 || two_tiles) mbar_wait(&bars[tile], parity);   // tile 1 has no rows when N <= 128
       tc_fence_after();
       float zreg[CW];
       const long long obase = (b * T + t) * (long long)N;
@@ -384,14 +391,14 @@ __global__ void __launch_bounds__(256 * HALVES, 1) k_dcrnn_seq_tc(const TcParams
       __syncthreads();
       tc_fence_after();
       // ---- round 2: re-diffuse the H*R columns -----------------------------------------------------------------
-      diffuse_tc<TC_NT>(U, gs, N, a_hi, a_lo, false, tid, 0, 2 * N);
+      diffuse_tc<TC_NT>(U, gs, N, a_hi, a_lo, false, tid, 0, p.n_ops * N);
       fence_proxy_async();
       tc_fence_before();
       __syncthreads();
       tc_fence_after();
-      if (tid == 0) { issue(0, 1, &bars[2]); issue(1, 1, &bars[3]); }
+      if (tid == 0) { issue(0, 1, &bars[2]); if (two_tiles) issue(1, 1, &bars[3]); }
       // ---- epilogue 2: candidate, H_t ----------------------------------------------------------------------------
-      mbar_wait(&bars[2 + tile], parity);
+      if (tile == 0 || two_tiles) mbar_wait(&bars[2 + tile], parity);
       tc_fence_after();
       {
         uint32_t vh[CW];
@@ -445,7 +452,8 @@ bool tc_layout(const stmp_plan* plan, TcParams* p, int* smem_bytes) {
   p->off_U = off; off += align_up(N * TC_UP * 4, 16);
   p->off_gstart = off; off += align_up((2 * N + 1) * 4, 16);
   p->off_order = off; off += align_up(2 * N * 4, 16);
-  p->off_ce = off; off += align_up((plan->fwd[0].nnz + plan->fwd[1].nnz + 6 * N + 4) * 8, 16);
+  const int nnz1 = plan->n_ops > 1 ? plan->fwd[1].nnz : 0;
+  p->off_ce = off; off += align_up((plan->fwd[0].nnz + nnz1 + 6 * N + 4) * 8, 16);
   p->off_bias = off; off += 96 * 4;
   p->off_bar = off; off += 64;
   *smem_bytes = off;
@@ -453,6 +461,15 @@ bool tc_layout(const stmp_plan* plan, TcParams* p, int* smem_bytes) {
 }
 
 }  // namespace
+
+bool gru_tc_supported(const stmp_plan* plan, long long cin) {
+  if (!plan || cin < 1 || cin > 4) return false;
+  if (plan->n > TC_AROWS - 1 || plan->n < 1) return false;
+  TcParams p;
+  int smem = 0;
+  p.N = plan->n;
+  return tc_layout(plan, &p, &smem);
+}
 
 bool dcrnn_tc_supported(const stmp_plan* plan, long long cin, long long cout, long long K) {
   if (!plan || plan->flavor != STMP_FLAVOR_DCONV || plan->n_ops != 2) return false;
@@ -464,17 +481,41 @@ bool dcrnn_tc_supported(const stmp_plan* plan, long long cin, long long cout, lo
   return tc_layout(plan, &p, &smem);
 }
 
+static int tc_launch_params(const stmp_plan* plan, TcParams& p, cudaStream_t st);
+
 int dcrnn_tc_launch(const stmp_plan* plan, long long B, long long T, long long cin, const float* x, const long long* win_start,
                     long long x_bstride, long long x_tstride, const float* w_z, const float* w_r, const float* w_h, const float* b_z,
                     const float* b_r, const float* b_h, const float* h0, float* out, float* stash, cudaStream_t st) {
   TcParams p;
-  int smem = 0;
   p.N = plan->n; p.CIN = (int)cin; p.T = (int)T; p.B = B;
-  if (!tc_layout(plan, &p, &smem)) return set_error(STMP_EUNSUPPORTED, "tcgen05 DCRNN kernel needs %d B of shared memory", smem);
-  for (int op = 0; op < 2; ++op) { p.rowptr[op] = plan->fwd[op].rowptr; p.cv[op] = plan->fwd[op].cv; }
   p.x = x; p.win_start = win_start; p.x_bstride = x_bstride; p.x_tstride = x_tstride;
   p.w[0] = w_z; p.w[1] = w_r; p.w[2] = w_h; p.bias[0] = b_z; p.bias[1] = b_r; p.bias[2] = b_h;
-  p.h0 = h0; p.out = out; p.stash = stash;
+  p.h0 = h0; p.h0_bstride = (long long)plan->n * 32; p.wcat = nullptr; p.bcat = nullptr; p.n_ops = 2;
+  p.out = out; p.stash = stash;
+  return tc_launch_params(plan, p, st);
+}
+
+// generic graph-GRU: prepacked weights, any plan flavor with >= n_ops operators
+int gru_tc_launch(const stmp_plan* plan, int n_ops, long long B, long long T, long long cin, const float* x, const long long* win_start,
+                  long long x_bstride, long long x_tstride, const float* wcat, const float* bcat, const float* h0, long long h0_bstride,
+                  float* out, float* stash, cudaStream_t st) {
+  TcParams p;
+  p.N = plan->n; p.CIN = (int)cin; p.T = (int)T; p.B = B;
+  p.x = x; p.win_start = win_start; p.x_bstride = x_bstride; p.x_tstride = x_tstride;
+  for (int i = 0; i < 3; ++i) { p.w[i] = nullptr; p.bias[i] = nullptr; }
+  p.h0 = h0; p.h0_bstride = h0_bstride; p.wcat = wcat; p.bcat = bcat; p.n_ops = n_ops;
+  p.out = out; p.stash = stash;
+  return tc_launch_params(plan, p, st);
+}
+
+static int tc_launch_params(const stmp_plan* plan, TcParams& p, cudaStream_t st) {
+  int smem = 0;
+  const long long B = p.B;
+  if (!tc_layout(plan, &p, &smem)) return set_error(STMP_EUNSUPPORTED, "tcgen05 graph-GRU kernel needs %d B of shared memory", smem);
+  for (int op = 0; op < 2; ++op) {
+    const int src = op < plan->n_ops ? op : 0;
+    p.rowptr[op] = plan->fwd[src].rowptr; p.cv[op] = plan->fwd[src].cv;
+  }
   int dev = 0, sms = 0;
   STMP_CUDA_OK(cudaGetDevice(&dev));
   STMP_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

@@ -4,6 +4,7 @@ state_dict keys `_attention (periods)`, `_base_tgcn.*`.  The reference loops ove
 :155), so all of them go through ONE batched SpMM + one set of GEMMs and the softmax-weighted sum."""
 import torch
 
+from ... import ops
 from .temporalgcn import TGCN, TGCN2
 from ...plan import _require_cuda
 
@@ -18,11 +19,23 @@ class _A3Base(torch.nn.Module):
         lead = Xp.shape[:-2]
         N, F = Xp.shape[-2:]
         plan = base._plan(edge_index, edge_weight, N)
+        probs = torch.nn.functional.softmax(self._attention, dim=0)
+        if base._fused_ok(plan, X, H) and not (torch.is_grad_enabled() and self._attention.requires_grad):
+            # all periods x batch rows = independent 1-step windows of ONE fused launch; H is shared by the periods
+            W, b = base._packed()
+            Xw = Xp.reshape(-1, 1, N, F)
+            if H is None:
+                Hn = ops.gru_seq_fwd(plan, 1, Xw, W, b)
+            elif X.dim() == 3:                                      # A3TGCN: a single (N,out) state for every period
+                Hn = ops.gru_seq_fwd(plan, 1, Xw, W, b, h0=H, h0_shared=True)
+            else:                                                   # A3TGCN2: (B,N,out) repeated over the periods
+                Hn = ops.gru_seq_fwd(plan, 1, Xw, W, b, h0=H.unsqueeze(0).expand(P, *H.shape).reshape(-1, N, base.out_channels))
+            Hn = Hn.reshape(*lead, N, base.out_channels)
+            return torch.tensordot(probs, Hn, dims=([0], [0]))
         G = base._gcn_all(plan, Xp.reshape(-1, N, F)).reshape(*lead, N, 3 * base.out_channels)
         if H is None:
             H = torch.zeros(*X.shape[:-2], base.out_channels, device=X.device, dtype=X.dtype)
         Hn = base._cell(G, H)                                   # H broadcasts over the period axis
-        probs = torch.nn.functional.softmax(self._attention, dim=0)
         return torch.tensordot(probs, Hn, dims=([0], [0]))      # sum_p probs[p] * H_p   (:153-155)
 
 

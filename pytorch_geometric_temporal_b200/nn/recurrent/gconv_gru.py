@@ -19,6 +19,7 @@ class GConvGRU(torch.nn.Module, ChebPlanMixin):
             setattr(self, f"conv_x_{g}", ChebParams(in_channels, out_channels, K, bias))
             setattr(self, f"conv_h_{g}", ChebParams(out_channels, out_channels, K, bias))
         self._init_plans()
+        self._pack = ops.PackCache()
 
     def _gate_weight(self, g, x_only=False, h_only=False):
         """Rows follow the basis [T_0 | T_1 | ...] of U=[X|H]: block k = [Wx_k^T ; Wh_k^T]."""
@@ -35,6 +36,33 @@ class GConvGRU(torch.nn.Module, ChebPlanMixin):
         cx, ch = getattr(self, f"conv_x_{g}"), getattr(self, f"conv_h_{g}")
         return None if cx.bias is None else cx.bias + ch.bias
 
+    def _packed(self):
+        """(wcat [96,112], bcat [96]) for stmp_gru_seq_fwd: columns H | L^H | - | X | L^X | - (one operator)."""
+        def build():
+            Ci, dev = self.in_channels, self.conv_x_z.lins[0].weight.device
+            W = torch.zeros(96, 112, device=dev)
+            b = torch.zeros(96, device=dev)
+            for gi, g in enumerate("zrh"):
+                cx, ch = getattr(self, f"conv_x_{g}"), getattr(self, f"conv_h_{g}")
+                r = slice(32 * gi, 32 * gi + 32)
+                W[r, 0:32] = ch.lins[0].weight
+                W[r, 96:96 + Ci] = cx.lins[0].weight
+                if self.K > 1:
+                    W[r, 32:64] = ch.lins[1].weight
+                    W[r, 100:100 + Ci] = cx.lins[1].weight
+                if cx.bias is not None:
+                    b[r] = cx.bias + ch.bias
+            return W, b
+        return self._pack.get(list(self.parameters()), build)
+
+    def _fused_ok(self, plan, X, H):
+        if self.K > 2 or self.out_channels != 32 or X.dim() != 2:
+            return False
+        if torch.is_grad_enabled() and (any(p.requires_grad for p in self.parameters()) or X.requires_grad
+                                        or (H is not None and H.requires_grad)):
+            return False
+        return ops.gru_seq_supported(plan, 1 if self.K > 1 else 0, self.in_channels, self.out_channels)
+
     def forward(self, X: torch.FloatTensor, edge_index: torch.LongTensor, edge_weight: torch.FloatTensor = None,
                 H: torch.FloatTensor = None, lambda_max: torch.Tensor = None) -> torch.FloatTensor:
         _require_cuda(X, "X")
@@ -42,6 +70,9 @@ class GConvGRU(torch.nn.Module, ChebPlanMixin):
         if H is None:
             H = torch.zeros(*X.shape[:-1], Co, device=X.device, dtype=X.dtype)
         plan = self._cheb_plan(edge_index, edge_weight, N, self.normalization, lambda_max)
+        if self._fused_ok(plan, X, H):   # one tcgen05 launch for the whole cell (stmp_gru_seq_fwd)
+            W, b = self._packed()
+            return ops.gru_seq_fwd(plan, 1 if K > 1 else 0, X.reshape(1, 1, N, Ci), W, b, h0=H.reshape(1, N, Co))[0, 0]
         TU = cheb_basis(plan, torch.cat([X, H], dim=-1), K)              # K x (N, Ci+Co)
         S = torch.cat(TU, dim=-1)
         pre = torch.matmul(S, torch.cat([self._gate_weight("z"), self._gate_weight("r")], dim=1))

@@ -28,6 +28,7 @@ class TGCN(torch.nn.Module):
             setattr(self, f"conv_{g}", GCNParams(in_channels, out_channels))
             setattr(self, f"linear_{g}", torch.nn.Linear(2 * out_channels, out_channels))
         self._plans = PlanCache()
+        self._pack = ops.PackCache()
 
     def _plan(self, edge_index, edge_weight, num_nodes):
         flags = (_lib.GCN_IMPROVED if self.improved else 0) | (0 if self.add_self_loops else _lib.GCN_NO_SELF_LOOPS)
@@ -49,12 +50,42 @@ class TGCN(torch.nn.Module):
         Ht = torch.tanh(lin(self.linear_h, Gh, H * R))
         return Z * H + (1 - Z) * Ht
 
+    def _packed(self):
+        """Fold GCNConv (lin, bias) and the gate Linear into the fused kernel's layout:
+        pre_g = H' @ L2^T + (A^X) @ (L1 W)^T + (L1 b + l),  L = linear_g.weight = [L1 | L2]."""
+        def build():
+            Ci, Co, dev = self.in_channels, self.out_channels, self.conv_z.lin.weight.device
+            W = torch.zeros(96, 112, device=dev)
+            b = torch.zeros(96, device=dev)
+            for gi, g in enumerate("zrh"):
+                conv, lin = getattr(self, f"conv_{g}"), getattr(self, f"linear_{g}")
+                L1, L2 = lin.weight[:, :Co], lin.weight[:, Co:]
+                r = slice(32 * gi, 32 * gi + 32)
+                W[r, 0:32] = L2
+                W[r, 100:100 + Ci] = L1 @ conv.lin.weight
+                b[r] = L1 @ conv.bias + lin.bias
+            return W, b
+        return self._pack.get(list(self.parameters()), build)
+
+    def _fused_ok(self, plan, X, H):
+        if self.out_channels != 32:
+            return False
+        if torch.is_grad_enabled() and (any(p.requires_grad for p in self.parameters()) or X.requires_grad
+                                        or (H is not None and H.requires_grad)):
+            return False
+        return ops.gru_seq_supported(plan, 1, self.in_channels, self.out_channels)
+
     def forward(self, X: torch.FloatTensor, edge_index: torch.LongTensor, edge_weight: torch.FloatTensor = None,
                 H: torch.FloatTensor = None) -> torch.FloatTensor:
         _require_cuda(X, "X")
         if H is None:
             H = torch.zeros(*X.shape[:-1], self.out_channels, device=X.device, dtype=X.dtype)
         plan = self._plan(edge_index, edge_weight, X.size(-2))
+        if self._fused_ok(plan, X, H):   # every (batch) row is an independent 1-step window of the fused kernel
+            W, b = self._packed()
+            N, Ci = X.shape[-2], X.shape[-1]
+            out = ops.gru_seq_fwd(plan, 1, X.reshape(-1, 1, N, Ci), W, b, h0=H.reshape(-1, N, self.out_channels))
+            return out.reshape(*X.shape[:-1], self.out_channels)
         return self._cell(self._gcn_all(plan, X), H)
 
 

@@ -117,6 +117,50 @@ def dcrnn_seq_fwd(plan: GraphPlan, x: torch.Tensor, wz, wr, wh, bz, br, bh, K: i
     return (out, st) if stash else out
 
 
+def gru_seq_supported(plan: GraphPlan, n_ops: int, cin: int, cout: int) -> bool:
+    return bool(_lib.lib().stmp_gru_seq_supported(plan.handle, n_ops, cin, cout))
+
+
+def gru_seq_fwd(plan: GraphPlan, n_ops: int, x: torch.Tensor, wcat: torch.Tensor, bcat: torch.Tensor, h0=None,
+                h0_shared: bool = False):
+    """Generic fused graph-GRU recurrence (stmp_gru_seq_fwd).  x (B,T,N,Cin) -> (B,T,N,32).
+    h0: (B,N,32), or (N,32)/(1,N,32) with h0_shared=True (every window starts from the same state), or None."""
+    x = _f32c(x, "X")
+    N = plan.num_nodes
+    if x.dim() != 4 or x.size(2) != N:
+        raise RuntimeError(f"X must be (B,T,{N},Cin), got {tuple(x.shape)}")
+    B, T, _, cin = x.shape
+    wcat, bcat = _f32c(wcat, "wcat"), _f32c(bcat, "bcat")
+    if wcat.shape != (96, 112) or bcat.numel() != 96:
+        raise RuntimeError("wcat must be (96,112) and bcat (96,)")
+    out = torch.empty((B, T, N, 32), dtype=torch.float32, device=x.device)
+    h0c, hs = None, 0
+    if h0 is not None:
+        h0c = _f32c(h0, "H")
+        hs = 0 if h0_shared else N * 32
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().stmp_gru_seq_fwd(plan.handle, n_ops, B, T, cin, _lib.ptr(x), None, T * N * cin, N * cin, _lib.ptr(wcat),
+                                         _lib.ptr(bcat), _lib.ptr(h0c), hs, _lib.ptr(out), None, _lib.stream_ptr())
+    _lib.check(rc)
+    return out
+
+
+class PackCache(object):
+    """Caches the packed (wcat, bcat) of a module until one of its parameters changes (host-side `_version`
+    check, no device sync), so inference pays the packing once."""
+
+    def __init__(self):
+        self._key, self._val = None, None
+
+    def get(self, params, build):
+        key = tuple((p.data_ptr(), p._version) for p in params)
+        if key != self._key:
+            with torch.no_grad():
+                self._val = build()
+            self._key = key
+        return self._val
+
+
 def gru_zr(pz, pr, h):
     pz, pr, h = _f32c(pz, "pz"), _f32c(pr, "pr"), _f32c(h, "h")
     z, r, hr = torch.empty_like(pz), torch.empty_like(pz), torch.empty_like(pz)
@@ -133,11 +177,6 @@ def gru_out(ph, z, h):
         _lib.check(_lib.lib().stmp_gru_out(ph.numel(), _lib.ptr(ph), _lib.ptr(z), _lib.ptr(h), None, _lib.ptr(hn),
                                            _lib.stream_ptr()))
     return hn
-
-
-def lstm_gates(pi, pf, pc, po_fn, c, wci, wcf, wco, bi, bf, bc, bo):
-    """Returns (h_new, c_new).  `po_fn` is unused here; see nn.recurrent.gconv_lstm for the two-phase use."""
-    raise NotImplementedError
 
 
 def lstm_ifc(pi, pf, pc, c, wci, wcf, bi, bf, bc):

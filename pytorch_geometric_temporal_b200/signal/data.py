@@ -3,6 +3,24 @@ as an attribute bag: signal/static_graph_temporal_signal.py:119-120; tests read 
 .edge_attr/.y).  Adds `.to(device)` / `.cuda()` so a snapshot can be moved in one call."""
 import torch
 
+# Static-graph tensors (edge_index / edge_attr) are the same host objects on every snapshot of a
+# StaticGraphTemporalSignal; moving each snapshot with `.to(device)` must not mint a new device copy per
+# snapshot (the layers key their cached plans on tensor identity).  Small memo: host tensor -> device copy.
+_GRAPH_KEYS = ("edge_index", "edge_attr")
+_DEVICE_MEMO = {}
+
+
+def _memo_to(t, device, non_blocking):
+    key = (id(t), t._version, str(device))
+    hit = _DEVICE_MEMO.get(key)
+    if hit is not None and hit[0] is t:
+        return hit[1]
+    if len(_DEVICE_MEMO) >= 16:
+        _DEVICE_MEMO.pop(next(iter(_DEVICE_MEMO)))
+    d = t.to(device, non_blocking=non_blocking)
+    _DEVICE_MEMO[key] = (t, d)
+    return d
+
 
 class Data(object):
     def __init__(self, x=None, edge_index=None, edge_attr=None, y=None, **kwargs):
@@ -23,7 +41,9 @@ class Data(object):
         out._keys = list(self._keys)
         for k in self._keys:
             v = getattr(self, k)
-            setattr(out, k, v.to(device, non_blocking=non_blocking) if torch.is_tensor(v) else v)
+            if torch.is_tensor(v):
+                v = _memo_to(v, device, non_blocking) if k in _GRAPH_KEYS else v.to(device, non_blocking=non_blocking)
+            setattr(out, k, v)
         return out
 
     def cuda(self, device=None, non_blocking=False):

@@ -163,3 +163,70 @@ def test_astgcn_backward_runs_and_matches_oracle_grad(golden_dir):
     m(c["X"].to(DEV), g["edge_index"].to(DEV)).square().sum().backward()
     for k, prm in m.named_parameters():
         _close(prm.grad, p[k].grad, rtol=2e-3, atol=2e-4)
+
+
+# ---- the generic fused graph-GRU kernel (stmp_gru_seq_fwd, tcgen05) behind GConvGRU / TGCN / A3TGCN -----------------
+def _metr():
+    ei, ew, _ = synthetic.metr_la_like(0, 16)
+    return torch.from_numpy(ei), torch.from_numpy(ew)
+
+
+@pytest.mark.parametrize("K", [1, 2])
+@pytest.mark.parametrize("norm", ["sym", "rw"])
+def test_gconv_gru_fused_tc_vs_oracle(K, norm):
+    ei, ew = _metr()
+    torch.manual_seed(K)
+    m = GConvGRU(4, 32, K, normalization=norm)
+    for p in m.parameters():   # non-zero biases
+        if p.dim() == 1:
+            torch.nn.init.uniform_(p, -0.5, 0.5)
+    X, H = torch.randn(207, 4), torch.randn(207, 32) * 0.5
+    lm = None if norm == "sym" else torch.tensor(2.4)
+    want = R.gconv_gru_cell(m.state_dict(), X, ei, ew, H, lm, norm)
+    mg = m.to(DEV)
+    n0 = _lib.launch_count()
+    with torch.no_grad():
+        got = mg(X.to(DEV), ei.to(DEV), ew.to(DEV), H.to(DEV), None if lm is None else lm.to(DEV))
+        got2 = mg(X.to(DEV), ei.to(DEV), ew.to(DEV), H.to(DEV), None if lm is None else lm.to(DEV))  # plan + pack cached
+    assert _lib.launch_count() - n0 < 40  # plan build once, then ONE fused launch per call
+    _close(got, want); _close(got2, want)
+    _close(mg(X.to(DEV), ei.to(DEV), ew.to(DEV), H.to(DEV), None if lm is None else lm.to(DEV)), want)  # tiled / autograd path
+
+
+@pytest.mark.parametrize("improved", [False, True])
+def test_tgcn_family_fused_tc_vs_oracle(improved):
+    ei, ew = _metr()
+    torch.manual_seed(3)
+    m = TGCN(2, 32, improved=improved)
+    for p in m.parameters():
+        if p.dim() == 1:
+            torch.nn.init.uniform_(p, -0.5, 0.5)
+    X, H = torch.randn(207, 2), torch.randn(207, 32) * 0.5
+    want = R.tgcn_cell(m.state_dict(), X, ei, ew, H, improved)
+    with torch.no_grad():
+        _close(m.to(DEV)(X.to(DEV), ei.to(DEV), ew.to(DEV), H.to(DEV)), want)
+        _close(m(X.to(DEV), ei.to(DEV), ew.to(DEV)), R.tgcn_cell(m.cpu().state_dict(), X, ei, ew, None, improved))
+    m2 = TGCN2(2, 32, 5, improved=improved)
+    Xb, Hb = torch.randn(5, 207, 2), torch.randn(5, 207, 32) * 0.5
+    want2 = R.tgcn_cell(m2.state_dict(), Xb, ei, ew, Hb, improved)
+    with torch.no_grad():
+        _close(m2.to(DEV)(Xb.to(DEV), ei.to(DEV), ew.to(DEV), Hb.to(DEV)), want2)
+
+
+def test_a3tgcn_fused_tc_vs_oracle():
+    ei, ew = _metr()
+    torch.manual_seed(5)
+    m = A3TGCN2(2, 32, 12, 4)
+    X, H = torch.randn(4, 207, 2, 12), torch.randn(4, 207, 32) * 0.3
+    want, wantH = R.a3tgcn(m.state_dict(), X, ei, ew), R.a3tgcn(m.state_dict(), X, ei, ew, H)
+    mg = m.to(DEV)
+    n0 = _lib.launch_count()
+    with torch.no_grad():
+        got, gotH = mg(X.to(DEV), ei.to(DEV), ew.to(DEV)), mg(X.to(DEV), ei.to(DEV), ew.to(DEV), H.to(DEV))
+    assert _lib.launch_count() - n0 < 40   # 12 periods x 4 rows in ONE launch per call (+ one-time plan build)
+    _close(got, want); _close(gotH, wantH)
+    m1 = A3TGCN(2, 32, 6)
+    X1, H1 = torch.randn(207, 2, 6), torch.randn(207, 32) * 0.3
+    want1 = R.a3tgcn(m1.state_dict(), X1, ei, ew, H1)
+    with torch.no_grad():
+        _close(m1.to(DEV)(X1.to(DEV), ei.to(DEV), ew.to(DEV), H1.to(DEV)), want1)

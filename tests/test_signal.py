@@ -104,3 +104,12 @@ def test_shard_indices_is_distributed_sampler(n, world, shuffle):
             s = DistributedSampler(ds, num_replicas=world, rank=rank, shuffle=shuffle, seed=7)
             s.set_epoch(epoch)
             assert list(s) == shard_indices(n, world, rank, shuffle, 7, epoch)
+
+
+def test_snapshot_to_device_reuses_static_graph_tensors():
+    """`.to(device)` on successive snapshots must hand the layers the SAME edge tensors (plan-cache identity)."""
+    ei, ew, feats, tg = _random_signal()
+    sig = StaticGraphTemporalSignal(ei, ew, feats, tg)
+    a, b = sig[0].to("cpu"), sig[1].to("cpu")
+    assert a.edge_index is b.edge_index and a.edge_attr is b.edge_attr
+    assert a.x is not b.x and torch.equal(a.edge_index, torch.LongTensor(ei))
