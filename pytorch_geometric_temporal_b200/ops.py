@@ -105,6 +105,8 @@ def dcrnn_seq_fwd(plan: GraphPlan, x: torch.Tensor, wz, wr, wh, bz, br, bh, K: i
         raise RuntimeError(f"DConv weight expects {wz.size(2)} input channels, got Cin+Cout={cin + cout}")
     out = torch.empty((B, T, N, cout), dtype=torch.float32, device=x.device)
     st = torch.empty((B, T, 3, N, cout), dtype=torch.float32, device=x.device) if stash else None
+    if B == 0 or T == 0:   # nothing to launch (empty tensors have NULL data pointers)
+        return (out, st) if stash else out
     h0c = None if h0 is None else _f32c(h0, "H")
     args = [_f32c(w.detach(), "weight") for w in (wz, wr, wh)]
     bs = [None if b is None else _f32c(b.detach(), "bias") for b in (bz, br, bh)]
@@ -134,6 +136,8 @@ def gru_seq_fwd(plan: GraphPlan, n_ops: int, x: torch.Tensor, wcat: torch.Tensor
     if wcat.shape != (96, 112) or bcat.numel() != 96:
         raise RuntimeError("wcat must be (96,112) and bcat (96,)")
     out = torch.empty((B, T, N, 32), dtype=torch.float32, device=x.device)
+    if B == 0 or T == 0:
+        return out
     h0c, hs = None, 0
     if h0 is not None:
         h0c = _f32c(h0, "H")
