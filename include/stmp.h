@@ -160,6 +160,26 @@ int stmp_lstm_ifc(int64_t rows, int64_t cout, const float* pi, const float* pf, 
 int stmp_lstm_oh(int64_t rows, int64_t cout, const float* po, const float* cnew, const float* wco,
                  const float* bo, float* o, float* hnew, void* stream);
 
+/* ---- K4: dense node-feature x weight contraction on the tensor cores (tcgen05), fp32 in / fp32 out ------------------
+ * C[M,N] = A[M,K] @ W[K,N] + bias.  Replaces `torch.matmul(Tx_k, weight[..][k])` / ChebConv `lins[k](Tx_k)` / GCNConv
+ * `lin(x)` (dcrnn.py:81-105; PyG) for the large-graph (tiled) path.  fp32-class accuracy: operands are split into fp16
+ * hi/lo halves and multiplied in three tcgen05.mma passes with an fp32 TMEM accumulator.
+ *   stmp_gemm_packed_elems(K,N): number of fp16 elements of the packed weight buffer
+ *   stmp_gemm_prepack: W [K,N] row-major (row stride ldw) -> packed (hi/lo, K-major, K padded to 64); once per weight update
+ *   stmp_gemm_f32: A row-major (row stride lda), C row-major (ldc); needs N <= 256, N % 32 == 0, K % 4 == 0, 16-byte aligned
+ *                  rows; otherwise STMP_EUNSUPPORTED (callers use cuBLAS)
+ *   stmp_gemm_lstm_f32: same contraction with N = 4*cout (column blocks i|f|c|o) fused with the peephole-LSTM gate epilogue
+ *                  of GConvLSTM (gconv_lstm.py:168-202): conv_bias [4*cout] (ChebConv biases), cell C_{t-1} [M,cout],
+ *                  peepholes w_c{i,f,o} [cout], gate biases b_{i,f,c,o} [cout] -> h_out, c_out [M,cout]; cout in {32, 64}. */
+int64_t stmp_gemm_packed_elems(int64_t K, int64_t N);
+int stmp_gemm_prepack(const float* W, int64_t ldw, int64_t K, int64_t N, void* packed, void* stream);
+int stmp_gemm_f32(const float* A, int64_t lda, int64_t M, int64_t K, int64_t N, const void* packed, const float* bias,
+                  float* C, int64_t ldc, void* stream);
+int stmp_gemm_lstm_f32(const float* A, int64_t lda, int64_t M, int64_t K, int64_t cout, const void* packed,
+                       const float* conv_bias, const float* cell, const float* wci, const float* wcf, const float* wco,
+                       const float* bi, const float* bf, const float* bc, const float* bo, float* h_out, float* c_out,
+                       void* stream);
+
 /* ---- K8: index-batching window gather -----------------------------------------------------------
  * x[b] = series[start[b] : start[b]+h], y[b] = series[start[b]+h : start[b]+2h]   (index_dataset.py:49-57
  * + DataLoader default collate), series [T_total, row_elems] resident on the device.  y may be NULL. */

@@ -45,6 +45,10 @@ _SIGNATURES = {
     "stmp_gru_out": (c_int, [c_int64, _P, _P, _P, _P, _P, _P]),
     "stmp_lstm_ifc": (c_int, [c_int64, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "stmp_lstm_oh": (c_int, [c_int64, c_int64, _P, _P, _P, _P, _P, _P, _P]),
+    "stmp_gemm_packed_elems": (c_int64, [c_int64, c_int64]),
+    "stmp_gemm_prepack": (c_int, [_P, c_int64, c_int64, c_int64, _P, _P]),
+    "stmp_gemm_f32": (c_int, [_P, c_int64, c_int64, c_int64, c_int64, _P, _P, _P, c_int64, _P]),
+    "stmp_gemm_lstm_f32": (c_int, [_P, c_int64, c_int64, c_int64, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "stmp_window_gather": (c_int, [_P, c_int64, c_int64, _P, c_int64, c_int64, _P, _P, _P]),
     "stmp_last_error": (c_char_p, []),
     "stmp_version": (c_char_p, []),

@@ -6,7 +6,7 @@ reference = 8(K-1) propagations; here T_k([X|H]) is computed once (K-1 SpMMs on 
 GEMM produces all four gate pre-activations."""
 import torch
 
-from ... import ops
+from ... import _lib, ops
 from ...plan import _require_cuda
 from ._cheb import ChebParams, ChebPlanMixin, cheb_basis, glorot_
 
@@ -29,6 +29,7 @@ class GConvLSTM(torch.nn.Module, ChebPlanMixin):
         for g in "ifco":
             torch.nn.init.zeros_(getattr(self, f"b_{g}"))
         self._init_plans()
+        self._pack = ops.PackCache()
 
     def _weight(self):
         cols = []
@@ -51,13 +52,33 @@ class GConvLSTM(torch.nn.Module, ChebPlanMixin):
         if C is None:
             C = torch.zeros(*X.shape[:-1], Co, device=X.device, dtype=X.dtype)
         plan = self._cheb_plan(edge_index, edge_weight, N, self.normalization, lambda_max)
+        needs_grad = torch.is_grad_enabled() and (any(p.requires_grad for p in self.parameters()) or X.requires_grad
+                                                  or H.requires_grad or C.requires_grad)
+        Cw = self.in_channels + Co
+        if not needs_grad and Co in (32, 64) and (self.K * Cw) % 4 == 0 and Cw % 4 == 0:
+            # large-graph inference: T_k written in place into S = [T_0|T_1|..] by the SpMM kernel, then ONE tcgen05
+            # launch does S @ W and the whole peephole-LSTM gate chain in its epilogue (stmp_gemm_lstm_f32)
+            S = torch.empty(*X.shape[:-1], self.K * Cw, device=X.device, dtype=torch.float32)
+            S[..., :self.in_channels] = X
+            S[..., self.in_channels:Cw] = H
+            for k in range(1, self.K):
+                if k == 1:
+                    ops.spmm_cols(plan, 0, S, 0, Cw, Cw)
+                else:
+                    ops.spmm_cols(plan, 0, S, (k - 1) * Cw, k * Cw, Cw, alpha=2.0, z_col=(k - 2) * Cw, beta=-1.0)
+            packed, cb = self._pack.get(list(self.parameters()), lambda: (ops.gemm_prepack(self._weight()), self._conv_bias()))
+            try:
+                return ops.gemm_lstm(S, packed, self.K * Cw, Co, cb, C.contiguous(), self.w_c_i, self.w_c_f, self.w_c_o,
+                                     self.b_i, self.b_f, self.b_c, self.b_o)
+            except _lib.StmpUnsupported:
+                pass
         S = torch.cat(cheb_basis(plan, torch.cat([X, H], dim=-1), self.K), dim=-1)
         pre = torch.matmul(S, self._weight())
         cb = self._conv_bias()
         if cb is not None:
             pre = pre + cb
         pi, pf, pc, po = (pre[..., j * Co:(j + 1) * Co] for j in range(4))
-        grad = torch.is_grad_enabled() and (pre.requires_grad or H.requires_grad or C.requires_grad)
+        grad = needs_grad
         if grad:
             I = torch.sigmoid(pi + self.w_c_i * C + self.b_i)
             Fg = torch.sigmoid(pf + self.w_c_f * C + self.b_f)

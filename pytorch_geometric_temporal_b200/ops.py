@@ -1,4 +1,5 @@
 """Autograd-aware wrappers over the C ABI (stmp_spmm, fused DCRNN sequence, gate epilogues)."""
+import ctypes
 from typing import Optional
 
 import torch
@@ -147,6 +148,60 @@ def gru_seq_fwd(plan: GraphPlan, n_ops: int, x: torch.Tensor, wcat: torch.Tensor
                                          _lib.ptr(bcat), _lib.ptr(h0c), hs, _lib.ptr(out), None, _lib.stream_ptr())
     _lib.check(rc)
     return out
+
+
+def spmm_cols(plan: GraphPlan, op: int, buf: torch.Tensor, src_col: int, dst_col: int, width: int, alpha: float = 1.0,
+              z_col: Optional[int] = None, beta: float = 0.0):
+    """In-place column-block product inside one basis buffer `buf` (..., N, LD):
+    buf[..., dst_col:dst_col+width] = alpha * A_op buf[..., src_col:+width] + beta * buf[..., z_col:+width].
+    Lets T_k be written straight into its slot of S = [T_0 | T_1 | ...] (no torch.cat of large tensors)."""
+    _require_cuda(buf, "buf")
+    b3 = buf if buf.dim() == 3 else buf.unsqueeze(0)
+    B, N, LD = b3.shape
+    if not b3.is_contiguous() or N != plan.num_nodes:
+        raise RuntimeError("basis buffer must be contiguous (..., N, LD)")
+    base, es = b3.data_ptr(), 4
+    pz = None if z_col is None else ctypes.c_void_p(base + z_col * es)
+    with torch.cuda.device(buf.device):
+        rc = _lib.lib().stmp_spmm(plan.handle, op, 0, B, width, ctypes.c_void_p(base + src_col * es), LD, N * LD,
+                                  ctypes.c_void_p(base + dst_col * es), LD, N * LD, alpha, pz, LD, N * LD, beta, None,
+                                  _lib.stream_ptr())
+    _lib.check(rc)
+
+
+def gemm_prepack(W: torch.Tensor) -> torch.Tensor:
+    """Split a (K,N) fp32 weight into the packed fp16 hi/lo buffer of stmp_gemm_f32 (once per weight update)."""
+    W = _f32c(W, "W")
+    K, N = W.shape
+    packed = torch.empty(int(_lib.lib().stmp_gemm_packed_elems(K, N)), dtype=torch.float16, device=W.device)
+    with torch.cuda.device(W.device):
+        _lib.check(_lib.lib().stmp_gemm_prepack(_lib.ptr(W), N, K, N, _lib.ptr(packed), _lib.stream_ptr()))
+    return packed
+
+
+def gemm(A: torch.Tensor, packed: torch.Tensor, K: int, N: int, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """C = A @ W + bias on tcgen05 with the fp16 hi/lo operand split (fp32-class accuracy).  A (..., K) contiguous."""
+    A = _f32c(A, "A")
+    M = A.numel() // K
+    C = torch.empty(*A.shape[:-1], N, dtype=torch.float32, device=A.device)
+    b = None if bias is None else _f32c(bias.detach(), "bias")
+    with torch.cuda.device(A.device):
+        _lib.check(_lib.lib().stmp_gemm_f32(_lib.ptr(A), K, M, K, N, _lib.ptr(packed), _lib.ptr(b), _lib.ptr(C), N, _lib.stream_ptr()))
+    return C
+
+
+def gemm_lstm(A: torch.Tensor, packed: torch.Tensor, K: int, cout: int, conv_bias, cell, wci, wcf, wco, bi, bf, bc, bo):
+    """(H', C') = peephole-LSTM gates of (A @ W + conv_bias), fused in the GEMM epilogue (stmp_gemm_lstm_f32)."""
+    A, cell = _f32c(A, "A"), _f32c(cell, "C")
+    M = A.numel() // K
+    h = torch.empty_like(cell)
+    c = torch.empty_like(cell)
+    v = [None if t is None else _f32c(t.detach().reshape(-1), "param") for t in (conv_bias, wci, wcf, wco, bi, bf, bc, bo)]
+    with torch.cuda.device(A.device):
+        _lib.check(_lib.lib().stmp_gemm_lstm_f32(_lib.ptr(A), K, M, K, cout, _lib.ptr(packed), _lib.ptr(v[0]), _lib.ptr(cell),
+                                                 _lib.ptr(v[1]), _lib.ptr(v[2]), _lib.ptr(v[3]), _lib.ptr(v[4]), _lib.ptr(v[5]),
+                                                 _lib.ptr(v[6]), _lib.ptr(v[7]), _lib.ptr(h), _lib.ptr(c), _lib.stream_ptr()))
+    return h, c
 
 
 class PackCache(object):

@@ -197,3 +197,28 @@ def test_window_gather_bit_exact():
     series3 = torch.randn(40, 7, 3)  # row not a multiple of 4 floats -> scalar path
     x, y = ops.window_gather(series3.to(DEV), starts[:3].to(DEV), 4)
     assert torch.equal(x[2].cpu(), series3[17:21]) and torch.equal(y[1].cpu(), series3[9:13])
+
+
+# ---- K4: tcgen05 split-fp16 GEMM (stmp_gemm_f32) and its fused LSTM epilogue ------------------------------------------
+@pytest.mark.parametrize("M,K,N", [(1, 4, 32), (127, 36, 64), (128, 64, 96), (1000, 384, 256), (20000, 132, 128)])
+def test_gemm_tc_matches_fp64(M, K, N):
+    g = torch.Generator().manual_seed(M + K + N)
+    A = torch.randn(M, K, generator=g) * 2
+    W = (torch.rand(K, N, generator=g) - 0.5) * 0.4
+    bias = torch.randn(N, generator=g)
+    want64 = A.double() @ W.double() + bias.double()
+    packed = ops.gemm_prepack(W.to(DEV))
+    got = ops.gemm(A.to(DEV), packed, K, N, bias.to(DEV)).cpu()
+    ref32 = A @ W + bias                      # the CPU fp32 result's own error vs fp64 is the yardstick
+    err, err32 = (got.double() - want64).abs().max().item(), (ref32.double() - want64).abs().max().item()
+    assert err < 4 * err32 + 1e-6, (err, err32)
+    assert torch.allclose(got, ref32, rtol=1e-4, atol=1e-5)
+    got_nb = ops.gemm(A.to(DEV), packed, K, N).cpu()
+    assert torch.allclose(got_nb, A @ W, rtol=1e-4, atol=1e-5)
+
+
+def test_gemm_tc_rejects_unsupported_shapes():
+    W = torch.randn(10, 40, device=DEV)            # N % 32 != 0
+    packed = ops.gemm_prepack(W)
+    with pytest.raises(_lib.StmpUnsupported):
+        ops.gemm(torch.randn(5, 10, device=DEV), packed, 10, 40)
