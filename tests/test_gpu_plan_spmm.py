@@ -211,10 +211,10 @@ def test_gemm_tc_matches_fp64(M, K, N):
     got = ops.gemm(A.to(DEV), packed, K, N, bias.to(DEV)).cpu()
     ref32 = A @ W + bias                      # the CPU fp32 result's own error vs fp64 is the yardstick
     err, err32 = (got.double() - want64).abs().max().item(), (ref32.double() - want64).abs().max().item()
-    assert err < 4 * err32 + 1e-6, (err, err32)
-    assert torch.allclose(got, ref32, rtol=1e-4, atol=1e-5)
+    assert err < 4 * err32 + 1e-6, (err, err32)         # fp32-class accuracy: within a small factor of fp32's own error
+    assert torch.allclose(got, ref32, rtol=1e-4, atol=1e-4)
     got_nb = ops.gemm(A.to(DEV), packed, K, N).cpu()
-    assert torch.allclose(got_nb, A @ W, rtol=1e-4, atol=1e-5)
+    assert torch.allclose(got_nb, A @ W, rtol=1e-4, atol=1e-4)
 
 
 def test_gemm_tc_rejects_unsupported_shapes():

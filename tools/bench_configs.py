@@ -124,6 +124,15 @@ def main():
         cms = cpu_time(cpu5, budget=8) * 6 * 8  # 2 of 12 steps, 1 of 8 windows, scaled
         out.append({"config": "cfg5 GConvLSTM(64,64,K=3), 10k nodes / 100k edges, 8 windows x 12 steps per GPU, forward", "launch": how,
                     "ours_ms": ms, "ours_snapshots_per_s": 8 / ms * 1e3, "cpu_oracle_ms_scaled": cms, "cpu_snapshots_per_s": 8 / cms * 1e3})
+        # K4 probe: the tcgen05 split-fp16 GEMM alone at the cfg5 size, vs cuBLAS fp32 (torch.matmul)
+        from pytorch_geometric_temporal_b200 import ops
+        A = torch.randn(80000, 384, device=DEV); W = torch.randn(384, 256, device=DEV) * 0.1
+        packed = ops.gemm_prepack(W)
+        ms_tc = gpu_time(lambda: ops.gemm(A, packed, 384, 256), iters=20)
+        ms_cb = gpu_time(lambda: torch.matmul(A, W), iters=20)
+        byt = 80000 * 384 * 4 + 80000 * 256 * 4
+        out.append({"config": "K4 probe: C[80000,256] = A[80000,384] @ W, fp32 in/out", "tcgen05_split_fp16_ms": ms_tc, "cublas_fp32_ms": ms_cb,
+                    "algorithmic_bytes": byt, "achieved_gbs": byt / ms_tc / 1e6, "tflops_fp32_equiv": 2 * 80000 * 384 * 256 / ms_tc / 1e9})
     for o in out:
         print(json.dumps(o))
 
