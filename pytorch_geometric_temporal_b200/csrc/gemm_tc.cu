@@ -89,23 +89,47 @@ __global__ void __launch_bounds__(GM_NT, 1) k_gemm_split(const GemmParams p) {
       tc_fence_after();
     }
     const int k0 = kb * GM_BK;
-    // A: 128 x 64 fp32 -> hi/lo fp16, swizzled.  16 lanes cover one row's 256 B contiguously.
-#pragma unroll 4
-    for (int idx = tid; idx < GM_BM * 16; idx += GM_NT) {
-      const int r = idx >> 4, c4 = idx & 15;
-      const long long row = m0 + r;
-      const int k = k0 + 4 * c4;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (row < p.M && k < p.K) v = __ldg(reinterpret_cast<const float4*>(p.A + row * p.lda + k));   // K % 4 == 0
-      store_split4(a_hi, a_lo, r, 4 * c4, v);
+    // A: 128 x 64 fp32 -> hi/lo fp16, swizzled.  16 lanes cover one row's 256 B contiguously; all 8 loads of a
+    // thread are issued before the first conversion (the kernel is bound by HBM latency, not by math).
+    {
+      float4 v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int idx = tid + j * GM_NT;
+        const int r = idx >> 4, c4 = idx & 15;
+        const long long row = m0 + r;
+        const int k = k0 + 4 * c4;
+        v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row < p.M && k < p.K) v[j] = __ldg(reinterpret_cast<const float4*>(p.A + row * p.lda + k));   // K % 4 == 0
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int idx = tid + j * GM_NT;
+        store_split4(a_hi, a_lo, idx >> 4, 4 * (idx & 15), v[j]);
+      }
     }
-    // B: N x 64 fp16 (already split) -> swizzled
-    for (int idx = tid; idx < N * 8; idx += GM_NT) {
-      const int n = idx >> 3, c = idx & 7;
-      const long long g = (long long)n * p.Kpad + k0 + 8 * c;
-      const int off = n * 128 + ((c ^ (n & 7)) << 4);
-      *reinterpret_cast<uint4*>(b_hi + off) = __ldg(reinterpret_cast<const uint4*>(p.w_hi + g));
-      *reinterpret_cast<uint4*>(b_lo + off) = __ldg(reinterpret_cast<const uint4*>(p.w_lo + g));
+    // B: N x 64 fp16 (already split, L2-resident) -> swizzled; 4 x (hi, lo) 128-bit loads in flight per thread
+    for (int base = 0; base < N * 8; base += 4 * GM_NT) {
+      uint4 h[4], l[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int idx = base + tid + j * GM_NT;
+        if (idx < N * 8) {
+          const long long g = (long long)(idx >> 3) * p.Kpad + k0 + 8 * (idx & 7);
+          h[j] = __ldg(reinterpret_cast<const uint4*>(p.w_hi + g));
+          l[j] = __ldg(reinterpret_cast<const uint4*>(p.w_lo + g));
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int idx = base + tid + j * GM_NT;
+        if (idx < N * 8) {
+          const int n = idx >> 3, c = idx & 7;
+          const int off = n * 128 + ((c ^ (n & 7)) << 4);
+          *reinterpret_cast<uint4*>(b_hi + off) = h[j];
+          *reinterpret_cast<uint4*>(b_lo + off) = l[j];
+        }
+      }
     }
     fence_proxy_async();
     tc_fence_before();
