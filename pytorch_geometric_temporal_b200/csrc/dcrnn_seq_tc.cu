@@ -294,17 +294,14 @@ __global__ void __launch_bounds__(256 * HALVES, 1) k_dcrnn_seq_tc(const TcParams
       // ---- epilogue 1: z, r gates; H*R ------------------------------------------------------------------------
       if (tile == 0 || two_tiles) mbar_wait(&bars[tile], parity);   // tile 1 has no rows when N <= 128
       tc_fence_after();
-      float zreg[CW];
       const long long obase = (b * T + t) * (long long)N;
       {
-        uint32_t vz[CW], vr[CW];
-        tmem_ld<CW>(trow + 64 * tile + ch0, vz);
+        uint32_t vr[CW];
         tmem_ld<CW>(trow + 64 * tile + 32 + ch0, vr);
         tmem_ld_wait();
         float hr[CW];
 #pragma unroll
         for (int c = 0; c < CW; ++c) {
-          zreg[c] = sigmoid_fast(__uint_as_float(vz[c]) + Bs[ch0 + c]);
           const float r = sigmoid_fast(__uint_as_float(vr[c]) + Bs[32 + ch0 + c]);
           hr[c] = hreg[c] * r;
           vr[c] = __float_as_uint(r);
@@ -317,7 +314,6 @@ __global__ void __launch_bounds__(256 * HALVES, 1) k_dcrnn_seq_tc(const TcParams
             float* sp = p.stash + ((obase * 3) + row) * 32 + ch0;
 #pragma unroll
             for (int c = 0; c < CW / 4; ++c) {
-              st4(sp + 4 * c, make_float4(zreg[4 * c], zreg[4 * c + 1], zreg[4 * c + 2], zreg[4 * c + 3]));
               st4(sp + (long long)N * 32 + 4 * c, make_float4(__uint_as_float(vr[4 * c]), __uint_as_float(vr[4 * c + 1]),
                                                               __uint_as_float(vr[4 * c + 2]), __uint_as_float(vr[4 * c + 3])));
             }
@@ -339,12 +335,16 @@ __global__ void __launch_bounds__(256 * HALVES, 1) k_dcrnn_seq_tc(const TcParams
       if (tile == 0 || two_tiles) mbar_wait(&bars[2 + tile], parity);
       tc_fence_after();
       {
-        uint32_t vh[CW];
+        // Z is recomputed from its accumulator, which stays in TMEM until the next step's GEMM 1: cheaper than keeping
+        // CW registers alive (and spilling) across the second diffusion round
+        uint32_t vh[CW], vz[CW];
         tmem_ld<CW>(trow + 128 + 32 * tile + ch0, vh);
+        tmem_ld<CW>(trow + 64 * tile + ch0, vz);
         tmem_ld_wait();
-        float ht[CW];
+        float ht[CW], zreg[CW];
 #pragma unroll
         for (int c = 0; c < CW; ++c) {
+          zreg[c] = sigmoid_fast(__uint_as_float(vz[c]) + Bs[ch0 + c]);
           ht[c] = tanh_fast(__uint_as_float(vh[c]) + Bs[64 + ch0 + c]);
           hreg[c] = zreg[c] * hreg[c] + (1.0f - zreg[c]) * ht[c];   // dcrnn.py:190-192
         }
@@ -358,9 +358,12 @@ __global__ void __launch_bounds__(256 * HALVES, 1) k_dcrnn_seq_tc(const TcParams
           }
           store_split_row<CW>(a_hi, a_lo, row, half, hreg);
           if (p.stash) {
-            float* sp = p.stash + ((obase * 3) + 2 * (long long)N + row) * 32 + ch0;
+            float* sp = p.stash + ((obase * 3) + row) * 32 + ch0;
 #pragma unroll
-            for (int c = 0; c < CW / 4; ++c) st4(sp + 4 * c, make_float4(ht[4 * c], ht[4 * c + 1], ht[4 * c + 2], ht[4 * c + 3]));
+            for (int c = 0; c < CW / 4; ++c) {
+              st4(sp + 4 * c, make_float4(zreg[4 * c], zreg[4 * c + 1], zreg[4 * c + 2], zreg[4 * c + 3]));
+              st4(sp + 2 * (long long)N * 32 + 4 * c, make_float4(ht[4 * c], ht[4 * c + 1], ht[4 * c + 2], ht[4 * c + 3]));
+            }
           }
           if (half == 0 && t + 1 < T) {
             const float4 xv = make_float4(xn[0], xn[1], xn[2], xn[3]);
