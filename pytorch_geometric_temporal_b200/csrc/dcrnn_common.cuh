@@ -26,8 +26,8 @@ __device__ __forceinline__ void fma4(float4& acc, float w, const float4& x) {
 }
 
 // Shared-memory form of the two operators, built once per CTA from the plan's CSR:
-//   * every (row, op) task's edge list is padded to a multiple of 4 with (self, 0.0f) entries, so the
-//     gather loop has no tail predication;
+//   * every (row, op) task's edge list is padded to a multiple of `pad` (4, or 2 = groups of 4 + one 2-edge tail)
+//     with (self, 0.0f) entries, so the gather loop has no per-edge predication;
 //   * the column index is pre-multiplied by LD (element offset of the source row in S);
 //   * tasks are ordered by descending group count, so the quarter-warps of a warp (consecutive slots)
 //     walk rows of equal length -- no divergence inside a warp pass.
@@ -38,9 +38,11 @@ struct GraphSmem {
 };
 
 // sum over the padded edge list of one task for the float4 at S[src*LD + coff .. +3]
+// (edge lists padded to a multiple of 4, or of 2 with a 2-edge tail group)
 __device__ __forceinline__ float4 gather_row(const float* __restrict__ Sc, const int2* __restrict__ ce, int beg, int end) {
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int k = beg; k < end; k += 4) {
+  int k = beg;
+  for (; k + 4 <= end; k += 4) {
     const int4 e01 = *reinterpret_cast<const int4*>(ce + k);      // two edges per 128-bit load
     const int4 e23 = *reinterpret_cast<const int4*>(ce + k + 2);
     const float4 x0 = ld4(Sc + e01.x);
@@ -52,6 +54,13 @@ __device__ __forceinline__ float4 gather_row(const float* __restrict__ Sc, const
     fma4(acc, __int_as_float(e23.y), x2);
     fma4(acc, __int_as_float(e23.w), x3);
   }
+  if (k < end) {   // 2-edge tail (pad == 2)
+    const int4 e01 = *reinterpret_cast<const int4*>(ce + k);
+    const float4 x0 = ld4(Sc + e01.x);
+    const float4 x1 = ld4(Sc + e01.z);
+    fma4(acc, __int_as_float(e01.y), x0);
+    fma4(acc, __int_as_float(e01.w), x1);
+  }
   return acc;
 }
 
@@ -62,13 +71,13 @@ __device__ __forceinline__ float4 gather_row(const float* __restrict__ Sc, const
 template <int NT>
 __device__ __forceinline__ void stage_graph(const int* __restrict__ grp0, const int* __restrict__ grp1, const int2* __restrict__ gcv0,
                                             const int2* __restrict__ gcv1, int N, int pitch, int2* s_ce, int* s_gstart, int* s_order,
-                                            int tid, int split_row = 1 << 30, int n_ops = 2) {
+                                            int tid, int split_row = 1 << 30, int n_ops = 2, int pad = 4) {
   const int NTASK = n_ops * N;
   int* s_len = s_order;  // scratch until the ranking pass writes it
   for (int task = tid; task < NTASK; task += NT) {
     const int op = task >= N ? 1 : 0, i = task - op * N;
     const int* rp = op ? grp1 : grp0;
-    s_len[task] = (rp[i + 1] - rp[i] + 3) & ~3;
+    s_len[task] = (rp[i + 1] - rp[i] + pad - 1) & ~(pad - 1);
   }
   __syncthreads();
   if (tid == 0) {

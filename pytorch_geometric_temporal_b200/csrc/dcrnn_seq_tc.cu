@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(256 * HALVES, 1) k_dcrnn_seq_tc(const TcParams
     for (int i = tid; i < (4 * TC_PANEL_A + 4 * TC_PANEL_B) / 16; i += TC_NT) z[i] = make_uint4(0, 0, 0, 0);
     for (int i = tid; i < N * TC_UP; i += TC_NT) U[i] = 0.f;
   }
-  stage_graph<TC_NT>(p.rowptr[0], p.rowptr[1], p.cv[0], p.cv[1], N, TC_UP, s_ce, s_gstart, s_order, tid, 1 << 30, p.n_ops);
+  stage_graph<TC_NT>(p.rowptr[0], p.rowptr[1], p.cv[0], p.cv[1], N, TC_UP, s_ce, s_gstart, s_order, tid, 1 << 30, p.n_ops, 2);
   __syncthreads();
   // weights -> B operand (fp16 hi/lo, swizzled).  Row n = gate*32 + out channel; k order as the A panels.
   for (int idx = tid; idx < 96 * 112; idx += TC_NT) {
