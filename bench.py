@@ -158,7 +158,7 @@ def run_reference(args):
         "e2e": {"value": r["value"], "unit": "snapshots/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -401,12 +401,35 @@ def run_ours(args):
                 "d2h_bytes_per_step": 4, "api": "signal.DevicePrefetcher(host batches) -> BatchedDCRNN.forward(X, edge_index, edge_weight) -> scalar metric read every step"},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "spmm": spmm, "train": train, "cpu_baseline": cpu,
     }
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner to
+    stdout at communicator creation), so fd 1 is pointed at stderr for the whole run and the JSON line is written to
+    the saved descriptor."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
