@@ -124,7 +124,7 @@ int stmp_dcrnn_seq_fwd(const stmp_plan* plan, int64_t B, int64_t T, int64_t cin,
                        const float* x, const int64_t* win_start, int64_t x_bstride, int64_t x_tstride,
                        const float* w_z, const float* w_r, const float* w_h, const float* b_z,
                        const float* b_r, const float* b_h, const float* h0, float* out, float* stash,
-                       void* stream);
+                       const void* wimage, void* stream);
 /* 1 if stmp_dcrnn_seq_fwd can take this configuration on the current device, else 0. */
 int stmp_dcrnn_seq_supported(const stmp_plan* plan, int64_t cin, int64_t cout, int64_t K);
 
@@ -139,7 +139,16 @@ int stmp_dcrnn_seq_supported(const stmp_plan* plan, int64_t cin, int64_t cout, i
  * x / win_start / strides / out / stash as stmp_dcrnn_seq_fwd.  STMP_EUNSUPPORTED outside the envelope. */
 int stmp_gru_seq_fwd(const stmp_plan* plan, int n_ops, int64_t B, int64_t T, int64_t cin, const float* x,
                      const int64_t* win_start, int64_t x_bstride, int64_t x_tstride, const float* wcat,
-                     const float* bcat, const float* h0, int64_t h0_bstride, float* out, float* stash, void* stream);
+                     const float* bcat, const float* h0, int64_t h0_bstride, float* out, float* stash,
+                     const void* wimage, void* stream);
+/* Optional weight image for the tcgen05 kernel: the B operand (fp16 hi/lo halves, SWIZZLE_128B, + biases) exactly as the kernel
+ * holds it in shared memory, so every CTA fetches it with one TMA bulk copy instead of converting the fp32 weights itself.
+ * Build it once per weight update into a device buffer of stmp_gru_weight_image_bytes() bytes and pass it as `wimage`
+ * (NULL => the kernel converts in place).  The plan carries the analogous graph image. */
+int64_t stmp_gru_weight_image_bytes(void);
+int stmp_dcrnn_pack_weights(int64_t cin, int64_t cout, int64_t K, const float* w_z, const float* w_r, const float* w_h,
+                            const float* b_z, const float* b_r, const float* b_h, void* image, void* stream);
+int stmp_gru_pack_weights(const float* wcat, const float* bcat, void* image, void* stream);
 int stmp_gru_seq_supported(const stmp_plan* plan, int n_ops, int64_t cin, int64_t cout);
 
 /* ---- K5: gate epilogues for the tiled path -------------------------------------------------------
@@ -185,6 +194,9 @@ int stmp_gemm_lstm_f32(const float* A, int64_t lda, int64_t M, int64_t K, int64_
  * + DataLoader default collate), series [T_total, row_elems] resident on the device.  y may be NULL. */
 int stmp_window_gather(const float* series, int64_t t_total, int64_t row_elems, const int64_t* start,
                        int64_t B, int64_t horizon, float* x, float* y, void* stream);
+
+/* Run-time switches for tests: "dcrnn_tc" = 1 (tcgen05 kernel, default) / 0 (FFMA kernel) behind stmp_dcrnn_seq_fwd. */
+int stmp_set_option(const char* name, int value);
 
 /* ---- misc ---------------------------------------------------------------------------------------- */
 const char* stmp_last_error(void);

@@ -37,9 +37,12 @@ _SIGNATURES = {
                           _P, c_int64, c_int64, c_float, _P, _P]),
     "stmp_spmm_att_grad": (c_int, [_P, c_int, c_int64, c_int64, _P, c_int64, c_int64, _P, c_int64, c_int64, _P, _P]),
     "stmp_dcrnn_seq_fwd": (c_int, [_P, c_int64, c_int64, c_int64, c_int64, c_int64, _P, _P, c_int64, c_int64,
-                                   _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+                                   _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "stmp_dcrnn_seq_supported": (c_int, [_P, c_int64, c_int64, c_int64]),
-    "stmp_gru_seq_fwd": (c_int, [_P, c_int, c_int64, c_int64, c_int64, _P, _P, c_int64, c_int64, _P, _P, _P, c_int64, _P, _P, _P]),
+    "stmp_gru_seq_fwd": (c_int, [_P, c_int, c_int64, c_int64, c_int64, _P, _P, c_int64, c_int64, _P, _P, _P, c_int64, _P, _P, _P, _P]),
+    "stmp_gru_weight_image_bytes": (c_int64, []),
+    "stmp_dcrnn_pack_weights": (c_int, [c_int64, c_int64, c_int64, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "stmp_gru_pack_weights": (c_int, [_P, _P, _P, _P]),
     "stmp_gru_seq_supported": (c_int, [_P, c_int, c_int64, c_int64]),
     "stmp_gru_zr": (c_int, [c_int64, _P, _P, _P, _P, _P, _P, _P]),
     "stmp_gru_out": (c_int, [c_int64, _P, _P, _P, _P, _P, _P]),
@@ -50,6 +53,7 @@ _SIGNATURES = {
     "stmp_gemm_f32": (c_int, [_P, c_int64, c_int64, c_int64, c_int64, _P, _P, _P, c_int64, _P]),
     "stmp_gemm_lstm_f32": (c_int, [_P, c_int64, c_int64, c_int64, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "stmp_window_gather": (c_int, [_P, c_int64, c_int64, _P, c_int64, c_int64, _P, _P, _P]),
+    "stmp_set_option": (c_int, [c_char_p, c_int]),
     "stmp_last_error": (c_char_p, []),
     "stmp_version": (c_char_p, []),
     "stmp_launch_count": (c_int64, []),
@@ -94,6 +98,10 @@ def check(rc: int):
     if rc == STMP_ENOMEM:
         raise MemoryError(msg)
     raise StmpError(msg)  # ESHAPE / EGRAPH / ECUDA -> RuntimeError, like torch shape errors
+
+
+def set_option(name: str, value: int):
+    check(lib().stmp_set_option(name.encode(), int(value)))
 
 
 def launch_count() -> int:

@@ -62,6 +62,11 @@ struct stmp_plan {
   stmp::Csr fwd[2];  // by destination
   stmp::Csr bwd[2];  // by source (transposed product)
   int device = 0;
+  // Shared-memory image of the first n_ops operators for the fused tcgen05 kernel (gstart | order | padded edge
+  // entries, exactly as the kernel lays them out), built once at plan creation when the graph fits (N <= 207):
+  // the kernel then fetches it with ONE TMA bulk copy instead of re-staging the CSR in every CTA.
+  void* gimg[3] = {nullptr, nullptr, nullptr};   // index = n_ops (1, 2)
+  int gimg_bytes[3] = {0, 0, 0};
 };
 
 namespace stmp {

@@ -19,6 +19,7 @@
 //    with LD/4 odd => conflict-free LDS.128; B is a warp-uniform broadcast.  The gate epilogue
 //    (sigmoid/tanh/Hadamard/convex combine) runs on the accumulators in registers.
 #include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 #include "dcrnn_common.cuh"
@@ -28,12 +29,18 @@ namespace stmp {
 bool dcrnn_tc_supported(const stmp_plan* plan, long long cin, long long cout, long long K);
 int dcrnn_tc_launch(const stmp_plan* plan, long long B, long long T, long long cin, const float* x, const long long* win_start,
                     long long x_bstride, long long x_tstride, const float* w_z, const float* w_r, const float* w_h, const float* b_z,
-                    const float* b_r, const float* b_h, const float* h0, float* out, float* stash, cudaStream_t st);
+                    const float* b_r, const float* b_h, const float* h0, float* out, float* stash, const void* wimage,
+                    cudaStream_t st);
+int tc_pack_weight_image(const float* wcat, const float* bcat, const float* w0, const float* w1, const float* w2, const float* b0,
+                         const float* b1, const float* b2, int cin, void* image, cudaStream_t st);
+int tc_weight_image_bytes();
 
 bool gru_tc_supported(const stmp_plan* plan, long long cin);
 int gru_tc_launch(const stmp_plan* plan, int n_ops, long long B, long long T, long long cin, const float* x, const long long* win_start,
                   long long x_bstride, long long x_tstride, const float* wcat, const float* bcat, const float* h0, long long h0_bstride,
-                  float* out, float* stash, cudaStream_t st);
+                  float* out, float* stash, const void* wimage, cudaStream_t st);
+
+int g_use_tc = -1;   // -1: read STMP_DCRNN_TC on first use
 
 namespace {
 
@@ -417,7 +424,7 @@ extern "C" int stmp_dcrnn_seq_fwd(const stmp_plan* plan, int64_t B, int64_t T, i
                                   const float* x, const int64_t* win_start, int64_t x_bstride, int64_t x_tstride,
                                   const float* w_z, const float* w_r, const float* w_h, const float* b_z,
                                   const float* b_r, const float* b_h, const float* h0, float* out, float* stash,
-                                  void* stream) {
+                                  const void* wimage, void* stream) {
   STMP_REQUIRE(plan != nullptr, STMP_EINVAL, "stmp_dcrnn_seq_fwd: plan is NULL");
   STMP_REQUIRE(plan->flavor == STMP_FLAVOR_DCONV, STMP_EINVAL, "stmp_dcrnn_seq_fwd: plan is not a DConv plan");
   STMP_REQUIRE(B >= 0 && T >= 0, STMP_EINVAL, "stmp_dcrnn_seq_fwd: negative B/T");
@@ -427,15 +434,14 @@ extern "C" int stmp_dcrnn_seq_fwd(const stmp_plan* plan, int64_t B, int64_t T, i
     return set_error(STMP_EUNSUPPORTED, "fused DCRNN kernel supports N<=256 (cout 32), cin<=4, cout in {16,32}, K<=4 (got N=%d cin=%lld cout=%lld K=%lld)",
                      plan->n, (long long)cin, (long long)cout, (long long)K);
   if (B == 0 || T == 0) return STMP_OK;
-  {  // tensor-core variant unless disabled (STMP_DCRNN_TC=0) or the configuration is outside its envelope
-    static int use_tc = -1;
-    if (use_tc < 0) {
+  {  // tensor-core variant unless disabled (STMP_DCRNN_TC=0 / stmp_set_option) or outside its envelope
+    if (g_use_tc < 0) {
       const char* v = getenv("STMP_DCRNN_TC");
-      use_tc = v ? atoi(v) : 1;
+      g_use_tc = v ? atoi(v) : 1;
     }
-    if (use_tc && dcrnn_tc_supported(plan, cin, cout, K))
+    if (g_use_tc && dcrnn_tc_supported(plan, cin, cout, K))
       return dcrnn_tc_launch(plan, B, T, cin, x, reinterpret_cast<const long long*>(win_start), x_bstride, x_tstride, w_z, w_r, w_h,
-                             b_z, b_r, b_h, h0, out, stash, (cudaStream_t)stream);
+                             b_z, b_r, b_h, h0, out, stash, wimage, (cudaStream_t)stream);
   }
   STMP_REQUIRE(T * (long long)plan->n * cin < (1ll << 24), STMP_ESHAPE, "window too long for the shared-memory X buffer");
   Layout L;
@@ -479,7 +485,8 @@ extern "C" int stmp_gru_seq_supported(const stmp_plan* plan, int n_ops, int64_t 
 
 extern "C" int stmp_gru_seq_fwd(const stmp_plan* plan, int n_ops, int64_t B, int64_t T, int64_t cin, const float* x,
                                 const int64_t* win_start, int64_t x_bstride, int64_t x_tstride, const float* wcat,
-                                const float* bcat, const float* h0, int64_t h0_bstride, float* out, float* stash, void* stream) {
+                                const float* bcat, const float* h0, int64_t h0_bstride, float* out, float* stash,
+                                const void* wimage, void* stream) {
   STMP_REQUIRE(plan != nullptr, STMP_EINVAL, "stmp_gru_seq_fwd: plan is NULL");
   STMP_REQUIRE(n_ops >= 0 && n_ops <= 2 && n_ops <= plan->n_ops, STMP_EINVAL, "stmp_gru_seq_fwd: n_ops=%d not available in this plan", n_ops);
   STMP_REQUIRE(B >= 0 && T >= 0, STMP_EINVAL, "stmp_gru_seq_fwd: negative B/T");
@@ -488,5 +495,28 @@ extern "C" int stmp_gru_seq_fwd(const stmp_plan* plan, int n_ops, int64_t B, int
     return set_error(STMP_EUNSUPPORTED, "fused graph-GRU kernel supports N<=207, cin<=4, cout=32 (got N=%d cin=%lld)", plan->n, (long long)cin);
   if (B == 0 || T == 0) return STMP_OK;
   return gru_tc_launch(plan, n_ops, B, T, cin, x, reinterpret_cast<const long long*>(win_start), x_bstride, x_tstride, wcat, bcat, h0,
-                       h0_bstride, out, stash, (cudaStream_t)stream);
+                       h0_bstride, out, stash, wimage, (cudaStream_t)stream);
+}
+
+/* Test hook: select the kernel family behind stmp_dcrnn_seq_fwd at run time ("dcrnn_tc": 1 tcgen05 / 0 FFMA), so the two
+ * independent implementations can be cross-checked against each other at full benchmark size. */
+extern "C" int stmp_set_option(const char* name, int value) {
+  STMP_REQUIRE(name != nullptr, STMP_EINVAL, "stmp_set_option: NULL name");
+  if (strcmp(name, "dcrnn_tc") == 0) { g_use_tc = value ? 1 : 0; return STMP_OK; }
+  return set_error(STMP_EINVAL, "stmp_set_option: unknown option '%s'", name);
+}
+
+extern "C" int64_t stmp_gru_weight_image_bytes(void) { return tc_weight_image_bytes(); }
+
+extern "C" int stmp_dcrnn_pack_weights(int64_t cin, int64_t cout, int64_t K, const float* w_z, const float* w_r, const float* w_h,
+                                       const float* b_z, const float* b_r, const float* b_h, void* image, void* stream) {
+  STMP_REQUIRE(w_z && w_r && w_h && image, STMP_EINVAL, "stmp_dcrnn_pack_weights: NULL pointer");
+  if (cout != 32 || K != 2 || cin < 1 || cin > 4)
+    return set_error(STMP_EUNSUPPORTED, "weight images exist for the tcgen05 kernel only (cout=32, K=2, cin<=4)");
+  return tc_pack_weight_image(nullptr, nullptr, w_z, w_r, w_h, b_z, b_r, b_h, (int)cin, image, (cudaStream_t)stream);
+}
+
+extern "C" int stmp_gru_pack_weights(const float* wcat, const float* bcat, void* image, void* stream) {
+  STMP_REQUIRE(wcat && bcat && image, STMP_EINVAL, "stmp_gru_pack_weights: NULL pointer");
+  return tc_pack_weight_image(wcat, bcat, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 4, image, (cudaStream_t)stream);
 }

@@ -54,6 +54,9 @@ struct TcParams {
   const float* wcat;      // optional prepacked fp32 weights [96][112] in the kernel's k order (else: DConv weights p.w[])
   const float* bcat;      // with wcat: biases [96]
   int n_ops;              // 2: DConv (P_o, P_i); 1: single operator (ChebConv K=2 / GCN); 0: no propagation
+  const void* gimg;       // plan's prebuilt shared-memory graph image (TMA bulk source) or null
+  int gimg_bytes;
+  const void* wimage;     // prebuilt B-operand image (fp16 hi/lo, swizzled, + biases) or null
   float* out;
   float* stash;
   int off_A, off_B, off_U, off_gstart, off_order, off_ce, off_bias, off_bar;
@@ -117,6 +120,44 @@ __device__ __forceinline__ void store_split_row(unsigned char* a_hi, unsigned ch
   }
 }
 
+constexpr int TC_WIMAGE_BYTES = 4 * TC_PANEL_B + 96 * 4;   // B hi (2 panels) | B lo (2 panels) | 96 biases
+
+// fp32 weight of output row n (gate*32 + channel) at k position kk (kernel k order, 0..111)
+__device__ __forceinline__ float tc_weight_value(const float* wcat, const float* w0, const float* w1, const float* w2, int CIN, int n,
+                                                 int kk) {
+  if (wcat) return wcat[n * 112 + kk];
+  const int C = 32 + CIN;
+  const int gte = n >> 5, o = n & 31;
+  const int panel = kk >= 64 ? 1 : 0, kin = kk - 64 * panel;
+  int blk, ch;  // blk 0: U, 1: P_o, 2: P_i ; ch = reference channel index or -1
+  if (panel == 0) { blk = kin < 32 ? 0 : 1; ch = CIN + (kin & 31); }
+  else if (kin < 32) { blk = 2; ch = CIN + kin; }
+  else { const int qq = kin - 32; blk = qq >> 2; const int c = qq & 3; ch = (blk < 3 && c < CIN) ? c : -1; }
+  if (ch < 0) return 0.f;
+  const float* wg = gte == 0 ? w0 : (gte == 1 ? w1 : w2);
+  if (blk == 0) return wg[((0 * 2 + 0) * C + ch) * 32 + o] + wg[((1 * 2 + 0) * C + ch) * 32 + o];
+  return wg[(((blk - 1) * 2 + 1) * C + ch) * 32 + o];
+}
+
+// Builds the B-operand image once per weight update (stmp_*_pack_weights); the fused kernel then TMA-copies it.
+__global__ void k_pack_weight_image(const float* wcat, const float* bcat, const float* w0, const float* w1, const float* w2,
+                                    const float* b0, const float* b1, const float* b2, int CIN, unsigned char* image) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < 96 * 128) {
+    const int n = idx >> 7, kk = idx & 127;
+    const float v = kk < 112 ? tc_weight_value(wcat, w0, w1, w2, CIN, n, kk) : 0.f;
+    const __half h = __float2half_rn(v);
+    const __half l = __float2half_rn(v - __half2float(h));
+    const int off = (kk >> 6) * TC_PANEL_B + sw128(n, kk & 63);
+    *reinterpret_cast<__half*>(image + off) = h;
+    *reinterpret_cast<__half*>(image + 2 * TC_PANEL_B + off) = l;
+  } else if (idx < 96 * 128 + 96) {
+    const int j = idx - 96 * 128, gte = j >> 5;
+    const float* bg = gte == 0 ? b0 : (gte == 1 ? b1 : b2);
+    reinterpret_cast<float*>(image + 4 * TC_PANEL_B)[j] = bcat ? bcat[j] : (bg ? bg[j & 31] : 0.f);
+  }
+}
+
 // fast, accurate-enough gates (abs err ~2e-7): ex2.approx + rcp.approx
 __device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float tanh_fast(float x) { return 2.0f * __fdividef(1.0f, 1.0f + __expf(-2.0f * x)) - 1.0f; }
@@ -154,8 +195,6 @@ __global__ void __launch_bounds__(256 * HALVES, 1) k_dcrnn_seq_tc(const TcParams
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int N = p.N, CIN = p.CIN, T = p.T;
-  const int C = 32 + CIN;
-
   unsigned char* a_hi = smem + p.off_A;
   unsigned char* a_lo = a_hi + 2 * TC_PANEL_A;
   unsigned char* b_hi = smem + p.off_B;
@@ -166,7 +205,7 @@ __global__ void __launch_bounds__(256 * HALVES, 1) k_dcrnn_seq_tc(const TcParams
   int2* s_ce = reinterpret_cast<int2*>(smem + p.off_ce);
   float* Bs = reinterpret_cast<float*>(smem + p.off_bias);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.off_bar);   // [4]: gemm1 tile0/1, gemm2 tile0/1
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
 
   if (blockIdx.x >= p.B) return;
 
@@ -175,45 +214,46 @@ __global__ void __launch_bounds__(256 * HALVES, 1) k_dcrnn_seq_tc(const TcParams
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TC_TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
+  // bars[0..3]: MMA completion (gemm1 tile0/1, gemm2 tile0/1); bars[4]: prologue TMA copies
   if (tid == 0) {
-    for (int i = 0; i < 4; ++i) mbar_init(&bars[i], 1);
+    for (int i = 0; i < 5; ++i) mbar_init(&bars[i], 1);
     fence_mbar_init();
+    const uint32_t tx = (p.gimg ? (uint32_t)p.gimg_bytes : 0u) + (p.wimage ? (uint32_t)TC_WIMAGE_BYTES : 0u);
+    if (tx) {   // graph image and weight image arrive by TMA bulk copies while the CTA zeroes its panels
+      mbar_arrive_expect_tx(&bars[4], tx);
+      if (p.gimg) tma_bulk_g2s(smem + p.off_gstart, p.gimg, (uint32_t)p.gimg_bytes, &bars[4]);
+      if (p.wimage) {
+        tma_bulk_g2s(b_hi, p.wimage, 4u * TC_PANEL_B, &bars[4]);
+        tma_bulk_g2s(Bs, reinterpret_cast<const unsigned char*>(p.wimage) + 4 * TC_PANEL_B, 96u * 4u, &bars[4]);
+      }
+    }
   }
-  {  // zero A (pad columns / rows must be finite) and B
+  {  // zero A (pad columns / rows must be finite); B too unless the TMA image overwrites all of it
     uint4* z = reinterpret_cast<uint4*>(a_hi);
-    for (int i = tid; i < (4 * TC_PANEL_A + 4 * TC_PANEL_B) / 16; i += TC_NT) z[i] = make_uint4(0, 0, 0, 0);
+    const int nz = (4 * TC_PANEL_A + (p.wimage ? 0 : 4 * TC_PANEL_B)) / 16;
+    for (int i = tid; i < nz; i += TC_NT) z[i] = make_uint4(0, 0, 0, 0);
     for (int i = tid; i < N * TC_UP; i += TC_NT) U[i] = 0.f;
   }
-  stage_graph<TC_NT>(p.rowptr[0], p.rowptr[1], p.cv[0], p.cv[1], N, TC_UP, s_ce, s_gstart, s_order, tid, 1 << 30, p.n_ops, 2);
+  if (!p.gimg) stage_graph<TC_NT>(p.rowptr[0], p.rowptr[1], p.cv[0], p.cv[1], N, TC_UP, s_ce, s_gstart, s_order, tid, 1 << 30, p.n_ops, 2);
   __syncthreads();
-  // weights -> B operand (fp16 hi/lo, swizzled).  Row n = gate*32 + out channel; k order as the A panels.
-  for (int idx = tid; idx < 96 * 112; idx += TC_NT) {
-    const int n = idx / 112, kk = idx - n * 112;
-    const int gte = n >> 5, o = n & 31;
-    const int panel = kk >= 64 ? 1 : 0, kin = kk - 64 * panel;
-    int blk, ch;  // blk 0: U, 1: P_o, 2: P_i ; ch = reference channel index or -1
-    if (panel == 0) { blk = kin < 32 ? 0 : 1; ch = CIN + (kin & 31); }
-    else if (kin < 32) { blk = 2; ch = CIN + kin; }
-    else { const int q = kin - 32; blk = q >> 2; const int c = q & 3; ch = (blk < 3 && c < CIN) ? c : -1; }
-    float v = 0.f;
-    if (p.wcat) {
-      v = p.wcat[idx];
-    } else if (ch >= 0) {
-      const float* wg = gte == 0 ? p.w[0] : (gte == 1 ? p.w[1] : p.w[2]);
-      if (blk == 0) v = wg[((0 * 2 + 0) * C + ch) * 32 + o] + wg[((1 * 2 + 0) * C + ch) * 32 + o];
-      else v = wg[(((blk - 1) * 2 + 1) * C + ch) * 32 + o];
+  if (!p.wimage) {
+    // weights -> B operand (fp16 hi/lo, swizzled).  Row n = gate*32 + out channel; k order as the A panels.
+    for (int idx = tid; idx < 96 * 112; idx += TC_NT) {
+      const int n = idx / 112, kk = idx - n * 112;
+      const float v = tc_weight_value(p.wcat, p.w[0], p.w[1], p.w[2], CIN, n, kk);
+      const __half h = __float2half_rn(v);
+      const __half l = __float2half_rn(v - __half2float(h));
+      const int off = (kk >> 6) * TC_PANEL_B + sw128(n, kk & 63);
+      *reinterpret_cast<__half*>(b_hi + off) = h;
+      *reinterpret_cast<__half*>(b_lo + off) = l;
     }
-    const __half h = __float2half_rn(v);
-    const __half l = __float2half_rn(v - __half2float(h));
-    const int off = panel * TC_PANEL_B + sw128(n, kin);
-    *reinterpret_cast<__half*>(b_hi + off) = h;
-    *reinterpret_cast<__half*>(b_lo + off) = l;
+    for (int idx = tid; idx < 96; idx += TC_NT) {
+      const int gte = idx >> 5;
+      const float* bg = gte == 0 ? p.bias[0] : (gte == 1 ? p.bias[1] : p.bias[2]);
+      Bs[idx] = p.bcat ? p.bcat[idx] : (bg ? bg[idx & 31] : 0.f);
+    }
   }
-  for (int idx = tid; idx < 96; idx += TC_NT) {
-    const int gte = idx >> 5;
-    const float* bg = gte == 0 ? p.bias[0] : (gte == 1 ? p.bias[1] : p.bias[2]);
-    Bs[idx] = p.bcat ? p.bcat[idx] : (bg ? bg[idx & 31] : 0.f);
-  }
+  if (p.gimg || p.wimage) mbar_wait(&bars[4], 0);
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
@@ -426,26 +466,27 @@ static int tc_launch_params(const stmp_plan* plan, TcParams& p, cudaStream_t st)
 
 int dcrnn_tc_launch(const stmp_plan* plan, long long B, long long T, long long cin, const float* x, const long long* win_start,
                     long long x_bstride, long long x_tstride, const float* w_z, const float* w_r, const float* w_h, const float* b_z,
-                    const float* b_r, const float* b_h, const float* h0, float* out, float* stash, cudaStream_t st) {
+                    const float* b_r, const float* b_h, const float* h0, float* out, float* stash, const void* wimage,
+                    cudaStream_t st) {
   TcParams p;
   p.N = plan->n; p.CIN = (int)cin; p.T = (int)T; p.B = B;
   p.x = x; p.win_start = win_start; p.x_bstride = x_bstride; p.x_tstride = x_tstride;
   p.w[0] = w_z; p.w[1] = w_r; p.w[2] = w_h; p.bias[0] = b_z; p.bias[1] = b_r; p.bias[2] = b_h;
   p.h0 = h0; p.h0_bstride = (long long)plan->n * 32; p.wcat = nullptr; p.bcat = nullptr; p.n_ops = 2;
-  p.out = out; p.stash = stash;
+  p.out = out; p.stash = stash; p.wimage = wimage;
   return tc_launch_params(plan, p, st);
 }
 
 // generic graph-GRU: prepacked weights, any plan flavor with >= n_ops operators
 int gru_tc_launch(const stmp_plan* plan, int n_ops, long long B, long long T, long long cin, const float* x, const long long* win_start,
                   long long x_bstride, long long x_tstride, const float* wcat, const float* bcat, const float* h0, long long h0_bstride,
-                  float* out, float* stash, cudaStream_t st) {
+                  float* out, float* stash, const void* wimage, cudaStream_t st) {
   TcParams p;
   p.N = plan->n; p.CIN = (int)cin; p.T = (int)T; p.B = B;
   p.x = x; p.win_start = win_start; p.x_bstride = x_bstride; p.x_tstride = x_tstride;
   for (int i = 0; i < 3; ++i) { p.w[i] = nullptr; p.bias[i] = nullptr; }
   p.h0 = h0; p.h0_bstride = h0_bstride; p.wcat = wcat; p.bcat = bcat; p.n_ops = n_ops;
-  p.out = out; p.stash = stash;
+  p.out = out; p.stash = stash; p.wimage = wimage;
   return tc_launch_params(plan, p, st);
 }
 
@@ -457,6 +498,9 @@ static int tc_launch_params(const stmp_plan* plan, TcParams& p, cudaStream_t st)
     const int src = op < plan->n_ops ? op : 0;
     p.rowptr[op] = plan->fwd[src].rowptr; p.cv[op] = plan->fwd[src].cv;
   }
+  p.gimg = (p.n_ops >= 1 && p.n_ops <= 2) ? plan->gimg[p.n_ops] : nullptr;
+  p.gimg_bytes = p.gimg ? plan->gimg_bytes[p.n_ops] : 0;
+  if (p.n_ops == 0) { p.gimg = nullptr; p.gimg_bytes = 0; }
   int dev = 0, sms = 0;
   STMP_CUDA_OK(cudaGetDevice(&dev));
   STMP_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -476,5 +520,14 @@ static int tc_launch_params(const stmp_plan* plan, TcParams& p, cudaStream_t st)
   STMP_LAUNCH_OK("k_dcrnn_seq_tc");
   return STMP_OK;
 }
+
+int tc_pack_weight_image(const float* wcat, const float* bcat, const float* w0, const float* w1, const float* w2, const float* b0,
+                         const float* b1, const float* b2, int cin, void* image, cudaStream_t st) {
+  const int total = 96 * 128 + 96;
+  k_pack_weight_image<<<(total + 255) / 256, 256, 0, st>>>(wcat, bcat, w0, w1, w2, b0, b1, b2, cin, reinterpret_cast<unsigned char*>(image));
+  STMP_LAUNCH_OK("k_pack_weight_image");
+  return STMP_OK;
+}
+int tc_weight_image_bytes() { return TC_WIMAGE_BYTES; }
 
 }  // namespace stmp

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "dcrnn_common.cuh"
 
 namespace stmp {
 
@@ -553,6 +554,47 @@ int build_gcn(Builder& b, stmp_plan* p, int n, int e, const int* row, const int*
   return 0;
 }
 
+// ---- shared-memory graph image for the fused tcgen05 kernel (see stmp_plan::gimg) -----------------------------------
+constexpr int kImgPitch = 36, kImgPad = 2, kImgMaxN = 207;
+
+__host__ __device__ inline int img_align16(int v) { return (v + 15) & ~15; }
+
+// One CTA stages the operators exactly like the kernel would (stage_graph) but into global memory.
+// header[0] = number of padded edge entries.
+__global__ void __launch_bounds__(512) k_build_graph_image(const int* rp0, const int* rp1, const int2* cv0, const int2* cv1, int N,
+                                                           int n_ops, unsigned char* image, int* header) {
+  int* gstart = reinterpret_cast<int*>(image);
+  int* order = reinterpret_cast<int*>(image + img_align16((2 * N + 1) * 4));
+  int2* ce = reinterpret_cast<int2*>(image + img_align16((2 * N + 1) * 4) + img_align16(2 * N * 4));
+  stage_graph<512>(rp0, rp1, cv0, cv1, N, kImgPitch, ce, gstart, order, threadIdx.x, 1 << 30, n_ops, kImgPad);
+  __syncthreads();
+  if (threadIdx.x == 0) header[0] = gstart[n_ops * N];
+}
+
+int build_graph_images(Builder& b, stmp_plan* p) {
+  if (p->n > kImgMaxN) return 0;
+  const int N = p->n;
+  int* d_hdr = b.talloc<int>(4);
+  if (!d_hdr) return b.rc;
+  for (int n_ops = 1; n_ops <= p->n_ops; ++n_ops) {
+    int nnz = 0;
+    for (int op = 0; op < n_ops; ++op) nnz += p->fwd[op].nnz;
+    const int cap = img_align16((2 * N + 1) * 4) + img_align16(2 * N * 4) + (nnz + 2 * N * (kImgPad - 1) + 4) * 8;
+    STMP_CUDA_OK(cudaMalloc(&p->gimg[n_ops], (size_t)cap));
+    STMP_CUDA_OK(cudaMemsetAsync(p->gimg[n_ops], 0, (size_t)cap, b.st));
+    const Csr& c1 = p->fwd[n_ops > 1 ? 1 : 0];
+    k_build_graph_image<<<1, 512, 0, b.st>>>(p->fwd[0].rowptr, c1.rowptr, p->fwd[0].cv, c1.cv, N, n_ops,
+                                             reinterpret_cast<unsigned char*>(p->gimg[n_ops]), d_hdr + n_ops);
+    STMP_LAUNCH_OK("k_build_graph_image");
+  }
+  int h[4] = {0, 0, 0, 0};
+  STMP_CUDA_OK(cudaMemcpyAsync(h, d_hdr, sizeof(h), cudaMemcpyDeviceToHost, b.st));
+  STMP_CUDA_OK(cudaStreamSynchronize(b.st));
+  for (int n_ops = 1; n_ops <= p->n_ops; ++n_ops)
+    p->gimg_bytes[n_ops] = img_align16(img_align16((2 * N + 1) * 4) + img_align16(2 * N * 4) + h[n_ops] * 8);
+  return 0;
+}
+
 void free_csr(Csr& c) {
   if (c.rowptr) cudaFree(c.rowptr);
   if (c.cv) cudaFree(c.cv);
@@ -622,6 +664,8 @@ extern "C" int stmp_plan_create(int flavor, int64_t num_nodes, int64_t num_edges
       p->fwd[op].max_row_nnz = h.max_row[op * 2];
       p->bwd[op].max_row_nnz = h.max_row[op * 2 + 1];
     }
+    rc = build_graph_images(b, p);
+    if (rc) break;
   } while (0);
   if (rc) {
     stmp_plan_destroy(p);
@@ -637,6 +681,8 @@ extern "C" void stmp_plan_destroy(stmp_plan* p) {
     free_csr(p->fwd[i]);
     free_csr(p->bwd[i]);
   }
+  for (int i = 0; i < 3; ++i)
+    if (p->gimg[i]) cudaFree(p->gimg[i]);
   delete p;
 }
 

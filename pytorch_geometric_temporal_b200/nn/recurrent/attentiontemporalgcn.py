@@ -22,14 +22,14 @@ class _A3Base(torch.nn.Module):
         probs = torch.nn.functional.softmax(self._attention, dim=0)
         if base._fused_ok(plan, X, H) and not (torch.is_grad_enabled() and self._attention.requires_grad):
             # all periods x batch rows = independent 1-step windows of ONE fused launch; H is shared by the periods
-            W, b = base._packed()
+            W, b, img = base._packed()
             Xw = Xp.reshape(-1, 1, N, F)
             if H is None:
-                Hn = ops.gru_seq_fwd(plan, 1, Xw, W, b)
+                Hn = ops.gru_seq_fwd(plan, 1, Xw, W, b, wimage=img)
             elif X.dim() == 3:                                      # A3TGCN: a single (N,out) state for every period
-                Hn = ops.gru_seq_fwd(plan, 1, Xw, W, b, h0=H, h0_shared=True)
+                Hn = ops.gru_seq_fwd(plan, 1, Xw, W, b, h0=H, h0_shared=True, wimage=img)
             else:                                                   # A3TGCN2: (B,N,out) repeated over the periods
-                Hn = ops.gru_seq_fwd(plan, 1, Xw, W, b, h0=H.unsqueeze(0).expand(P, *H.shape).reshape(-1, N, base.out_channels))
+                Hn = ops.gru_seq_fwd(plan, 1, Xw, W, b, h0=H.unsqueeze(0).expand(P, *H.shape).reshape(-1, N, base.out_channels), wimage=img)
             Hn = Hn.reshape(*lead, N, base.out_channels)
             return torch.tensordot(probs, Hn, dims=([0], [0]))
         G = base._gcn_all(plan, Xp.reshape(-1, N, F)).reshape(*lead, N, 3 * base.out_channels)

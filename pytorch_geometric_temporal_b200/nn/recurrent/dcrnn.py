@@ -104,6 +104,7 @@ class DCRNN(torch.nn.Module):
         self.conv_x_r = self._conv_cls(C, out_channels, K, bias)
         self.conv_x_h = self._conv_cls(C, out_channels, K, bias)
         self._plans = PlanCache()
+        self._wimg = ops.PackCache()
 
     # ---- helpers -----------------------------------------------------------------------------------
     def _plan(self, edge_index, edge_weight, num_nodes):
@@ -118,6 +119,11 @@ class DCRNN(torch.nn.Module):
     def _params(self):
         return (self.conv_x_z.weight, self.conv_x_r.weight, self.conv_x_h.weight,
                 self.conv_x_z.bias, self.conv_x_r.bias, self.conv_x_h.bias)
+
+    def _weight_image(self):
+        """B-operand image for the tcgen05 kernel, rebuilt only when a parameter changes."""
+        return self._wimg.get(list(self.parameters()),
+                              lambda: ops.dcrnn_weight_image(*self._params(), self.in_channels, self.K))
 
     def _tiled_step(self, plan, X, H):
         """One GRU step on (N,*) or (B,N,*) tensors; z and r share the diffusion of [X|H]."""
@@ -144,7 +150,8 @@ class DCRNN(torch.nn.Module):
         plan = self._plan(edge_index, edge_weight, N)
         if not self._needs_grad(X, H) and ops.dcrnn_seq_supported(plan, self.in_channels, self.out_channels, self.K):
             h0 = None if H is None else H.reshape(1, N, self.out_channels)
-            out = ops.dcrnn_seq_fwd(plan, X.reshape(1, 1, N, self.in_channels), *self._params(), self.K, h0=h0)
+            out = ops.dcrnn_seq_fwd(plan, X.reshape(1, 1, N, self.in_channels), *self._params(), self.K, h0=h0,
+                                    wimage=self._weight_image())
             return out[0, 0]
         if H is None:
             H = torch.zeros(N, self.out_channels, device=X.device, dtype=X.dtype)
@@ -165,7 +172,7 @@ class BatchedDCRNN(DCRNN):
         plan = self._plan(edge_index, edge_weight, N)
         if not self._needs_grad(X) and ops.dcrnn_seq_supported(plan, self.in_channels, self.out_channels, self.K):
             try:
-                return ops.dcrnn_seq_fwd(plan, X, *self._params(), self.K)
+                return ops.dcrnn_seq_fwd(plan, X, *self._params(), self.K, wimage=self._weight_image())
             except _lib.StmpUnsupported:
                 pass
         H = torch.zeros(B, N, self.out_channels, device=X.device, dtype=X.dtype)
@@ -181,6 +188,7 @@ class BatchedDCRNN(DCRNN):
         _require_cuda(series, "series")
         plan = self._plan(edge_index, edge_weight, series.size(1))
         if not self._needs_grad(series) and ops.dcrnn_seq_supported(plan, self.in_channels, self.out_channels, self.K):
-            return ops.dcrnn_seq_fwd(plan, series, *self._params(), self.K, win_start=win_start, horizon=horizon)
+            return ops.dcrnn_seq_fwd(plan, series, *self._params(), self.K, win_start=win_start, horizon=horizon,
+                                     wimage=self._weight_image())
         X = ops.window_gather(series, win_start, horizon, with_target=False)
         return self.forward(X, edge_index, edge_weight)

@@ -52,7 +52,7 @@ class GConvGRU(torch.nn.Module, ChebPlanMixin):
                     W[r, 100:100 + Ci] = cx.lins[1].weight
                 if cx.bias is not None:
                     b[r] = cx.bias + ch.bias
-            return W, b
+            return W, b, ops.gru_weight_image(W, b)
         return self._pack.get(list(self.parameters()), build)
 
     def _fused_ok(self, plan, X, H):
@@ -71,8 +71,8 @@ class GConvGRU(torch.nn.Module, ChebPlanMixin):
             H = torch.zeros(*X.shape[:-1], Co, device=X.device, dtype=X.dtype)
         plan = self._cheb_plan(edge_index, edge_weight, N, self.normalization, lambda_max)
         if self._fused_ok(plan, X, H):   # one tcgen05 launch for the whole cell (stmp_gru_seq_fwd)
-            W, b = self._packed()
-            return ops.gru_seq_fwd(plan, 1 if K > 1 else 0, X.reshape(1, 1, N, Ci), W, b, h0=H.reshape(1, N, Co))[0, 0]
+            W, b, img = self._packed()
+            return ops.gru_seq_fwd(plan, 1 if K > 1 else 0, X.reshape(1, 1, N, Ci), W, b, h0=H.reshape(1, N, Co), wimage=img)[0, 0]
         TU = cheb_basis(plan, torch.cat([X, H], dim=-1), K)              # K x (N, Ci+Co)
         S = torch.cat(TU, dim=-1)
         pre = torch.matmul(S, torch.cat([self._gate_weight("z"), self._gate_weight("r")], dim=1))

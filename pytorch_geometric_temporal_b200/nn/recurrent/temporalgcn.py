@@ -64,7 +64,7 @@ class TGCN(torch.nn.Module):
                 W[r, 0:32] = L2
                 W[r, 100:100 + Ci] = L1 @ conv.lin.weight
                 b[r] = L1 @ conv.bias + lin.bias
-            return W, b
+            return W, b, ops.gru_weight_image(W, b)
         return self._pack.get(list(self.parameters()), build)
 
     def _fused_ok(self, plan, X, H):
@@ -82,9 +82,9 @@ class TGCN(torch.nn.Module):
             H = torch.zeros(*X.shape[:-1], self.out_channels, device=X.device, dtype=X.dtype)
         plan = self._plan(edge_index, edge_weight, X.size(-2))
         if self._fused_ok(plan, X, H):   # every (batch) row is an independent 1-step window of the fused kernel
-            W, b = self._packed()
+            W, b, img = self._packed()
             N, Ci = X.shape[-2], X.shape[-1]
-            out = ops.gru_seq_fwd(plan, 1, X.reshape(-1, 1, N, Ci), W, b, h0=H.reshape(-1, N, self.out_channels))
+            out = ops.gru_seq_fwd(plan, 1, X.reshape(-1, 1, N, Ci), W, b, h0=H.reshape(-1, N, self.out_channels), wimage=img)
             return out.reshape(*X.shape[:-1], self.out_channels)
         return self._cell(self._gcn_all(plan, X), H)
 

@@ -82,7 +82,8 @@ def dcrnn_seq_supported(plan: GraphPlan, cin: int, cout: int, K: int) -> bool:
 
 
 def dcrnn_seq_fwd(plan: GraphPlan, x: torch.Tensor, wz, wr, wh, bz, br, bh, K: int, h0=None,
-                  win_start: Optional[torch.Tensor] = None, horizon: Optional[int] = None, stash: bool = False):
+                  win_start: Optional[torch.Tensor] = None, horizon: Optional[int] = None, stash: bool = False,
+                  wimage: Optional[torch.Tensor] = None):
     """Fused DCRNN recurrence.  x: (B,T,N,Cin) windows, or -- with win_start (int64 [B]) and horizon --
     the resident series (T_total,N,Cin) from which window b = series[win_start[b]:win_start[b]+horizon]
     is read in-kernel (index-batching).  Returns out (B,T,N,Cout) [, stash (B,T,3,N,Cout)]."""
@@ -115,7 +116,7 @@ def dcrnn_seq_fwd(plan: GraphPlan, x: torch.Tensor, wz, wr, wh, bz, br, bh, K: i
         rc = _lib.lib().stmp_dcrnn_seq_fwd(plan.handle, B, T, cin, cout, K, _lib.ptr(x), _lib.ptr(ws), bstride, tstride,
                                            _lib.ptr(args[0]), _lib.ptr(args[1]), _lib.ptr(args[2]), _lib.ptr(bs[0]),
                                            _lib.ptr(bs[1]), _lib.ptr(bs[2]), _lib.ptr(h0c), _lib.ptr(out), _lib.ptr(st),
-                                           _lib.stream_ptr())
+                                           _lib.ptr(wimage), _lib.stream_ptr())
     _lib.check(rc)
     return (out, st) if stash else out
 
@@ -125,7 +126,7 @@ def gru_seq_supported(plan: GraphPlan, n_ops: int, cin: int, cout: int) -> bool:
 
 
 def gru_seq_fwd(plan: GraphPlan, n_ops: int, x: torch.Tensor, wcat: torch.Tensor, bcat: torch.Tensor, h0=None,
-                h0_shared: bool = False):
+                h0_shared: bool = False, wimage: Optional[torch.Tensor] = None):
     """Generic fused graph-GRU recurrence (stmp_gru_seq_fwd).  x (B,T,N,Cin) -> (B,T,N,32).
     h0: (B,N,32), or (N,32)/(1,N,32) with h0_shared=True (every window starts from the same state), or None."""
     x = _f32c(x, "X")
@@ -145,7 +146,7 @@ def gru_seq_fwd(plan: GraphPlan, n_ops: int, x: torch.Tensor, wcat: torch.Tensor
         hs = 0 if h0_shared else N * 32
     with torch.cuda.device(x.device):
         rc = _lib.lib().stmp_gru_seq_fwd(plan.handle, n_ops, B, T, cin, _lib.ptr(x), None, T * N * cin, N * cin, _lib.ptr(wcat),
-                                         _lib.ptr(bcat), _lib.ptr(h0c), hs, _lib.ptr(out), None, _lib.stream_ptr())
+                                         _lib.ptr(bcat), _lib.ptr(h0c), hs, _lib.ptr(out), None, _lib.ptr(wimage), _lib.stream_ptr())
     _lib.check(rc)
     return out
 
@@ -202,6 +203,28 @@ def gemm_lstm(A: torch.Tensor, packed: torch.Tensor, K: int, cout: int, conv_bia
                                                  _lib.ptr(v[1]), _lib.ptr(v[2]), _lib.ptr(v[3]), _lib.ptr(v[4]), _lib.ptr(v[5]),
                                                  _lib.ptr(v[6]), _lib.ptr(v[7]), _lib.ptr(h), _lib.ptr(c), _lib.stream_ptr()))
     return h, c
+
+
+def dcrnn_weight_image(wz, wr, wh, bz, br, bh, cin: int, K: int) -> Optional[torch.Tensor]:
+    """B-operand image of the tcgen05 kernel for DConv weights (None when the configuration has no tensor kernel)."""
+    cout = wz.size(-1)
+    if cout != 32 or K != 2 or not (1 <= cin <= 4):
+        return None
+    img = torch.empty(int(_lib.lib().stmp_gru_weight_image_bytes()), dtype=torch.uint8, device=wz.device)
+    args = [_f32c(w.detach(), "weight") for w in (wz, wr, wh)]
+    bs = [None if b is None else _f32c(b.detach(), "bias") for b in (bz, br, bh)]
+    with torch.cuda.device(wz.device):
+        _lib.check(_lib.lib().stmp_dcrnn_pack_weights(cin, cout, K, _lib.ptr(args[0]), _lib.ptr(args[1]), _lib.ptr(args[2]),
+                                                      _lib.ptr(bs[0]), _lib.ptr(bs[1]), _lib.ptr(bs[2]), _lib.ptr(img), _lib.stream_ptr()))
+    return img
+
+
+def gru_weight_image(wcat: torch.Tensor, bcat: torch.Tensor) -> torch.Tensor:
+    img = torch.empty(int(_lib.lib().stmp_gru_weight_image_bytes()), dtype=torch.uint8, device=wcat.device)
+    with torch.cuda.device(wcat.device):
+        _lib.check(_lib.lib().stmp_gru_pack_weights(_lib.ptr(_f32c(wcat, "wcat")), _lib.ptr(_f32c(bcat, "bcat")), _lib.ptr(img),
+                                                    _lib.stream_ptr()))
+    return img
 
 
 class PackCache(object):
