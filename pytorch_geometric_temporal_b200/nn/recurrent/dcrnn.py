@@ -39,6 +39,107 @@ def _stack_weight(weight: torch.Tensor) -> torch.Tensor:
     return torch.cat(parts, dim=0)
 
 
+def _basis_raw(plan, U: torch.Tensor, K: int):
+    """no-autograd version of `_basis` (used inside the hand-written backward)."""
+    blocks = [U]
+    To = Ti = None
+    for k in range(1, K):
+        if k == 1:
+            To, Ti = ops.spmm_raw(plan, 0, U), ops.spmm_raw(plan, 1, U)
+        else:
+            To = ops.spmm_raw(plan, 0, To, alpha=2.0, z=U, beta=-1.0)
+            Ti = ops.spmm_raw(plan, 1, Ti, alpha=2.0, z=U, beta=-1.0)
+        blocks += [To, Ti]
+    return blocks
+
+
+def _basis_adjoint(plan, dS: torch.Tensor, C: int, K: int) -> torch.Tensor:
+    """Adjoint of U -> [U | P_o U | P_i U | 2 P_o T_1o - U | ...]: returns dU for dS (..., (2K-1)*C)."""
+    d = [dS[..., j * C:(j + 1) * C].contiguous() for j in range(2 * K - 1)]
+    d0 = d[0]
+    for k in range(K - 1, 1, -1):                      # T_k = 2 P T_{k-1} - U
+        for o in (0, 1):
+            dk = d[1 + 2 * (k - 1) + o]
+            d[1 + 2 * (k - 2) + o] = ops.spmm_raw(plan, o, dk, transposed=True, alpha=2.0, z=d[1 + 2 * (k - 2) + o], beta=1.0)
+            d0 = d0 - dk
+    if K > 1:                                          # T_1 = P U
+        d0 = ops.spmm_raw(plan, 0, d[1], transposed=True, z=d0, beta=1.0)
+        d0 = ops.spmm_raw(plan, 1, d[2], transposed=True, z=d0, beta=1.0)
+    return d0
+
+
+def _unstack_weight_grad(dWs: torch.Tensor, K: int, C: int) -> torch.Tensor:
+    """((2K-1)*C, O) gradient of `_stack_weight(W)` -> gradient of W (2,K,C,O)."""
+    O = dWs.size(1)
+    g = dWs.new_zeros(2, K, C, O)
+    g[0, 0] = dWs[:C]
+    g[1, 0] = dWs[:C]
+    for k in range(1, K):
+        g[0, k] = dWs[(1 + 2 * (k - 1)) * C:(2 + 2 * (k - 1)) * C]
+        g[1, k] = dWs[(2 + 2 * (k - 1)) * C:(3 + 2 * (k - 1)) * C]
+    return g
+
+
+class _DcrnnSeqFn(torch.autograd.Function):
+    """Training path of the recurrence: forward = ONE fused launch that also stashes (Z, R, H~) per step; backward =
+    hand-written reverse-time loop over the stash (transposed SpMM for the diffusion adjoints, cuBLAS for the
+    contractions).  Replaces autograd's replay of the ~1500-launch tiled graph."""
+
+    @staticmethod
+    def forward(ctx, X, H0, wz, wr, wh, bz, br, bh, plan, K, wimage):
+        out, stash = ops.dcrnn_seq_fwd(plan, X, wz, wr, wh, bz, br, bh, K, h0=H0, stash=True, wimage=wimage)
+        ctx.plan, ctx.K, ctx.has_bias, ctx.has_h0 = plan, K, bz is not None, H0 is not None
+        ctx.save_for_backward(X, H0, wz, wr, wh, out, stash)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        X, H0, wz, wr, wh, out, stash = ctx.saved_tensors
+        plan, K = ctx.plan, ctx.K
+        B, T, N, Ci = X.shape
+        Co = wz.size(-1)
+        C = Ci + Co
+        Wzs, Wrs, Whs = _stack_weight(wz), _stack_weight(wr), _stack_weight(wh)
+        Wzr = torch.cat([Wzs, Wrs], dim=1)
+        dWzr = torch.zeros_like(Wzr)
+        dWh = torch.zeros_like(Whs)
+        dbzr = gout.new_zeros(2 * Co)
+        dbh = gout.new_zeros(Co)
+        dX = torch.zeros_like(X) if ctx.needs_input_grad[0] else None
+        dH = gout.new_zeros(B, N, Co)
+        gout = gout.contiguous()
+        for t in range(T - 1, -1, -1):
+            Hp = out[:, t - 1] if t > 0 else (H0 if H0 is not None else gout.new_zeros(B, N, Co))
+            Z, R, Ht = stash[:, t, 0], stash[:, t, 1], stash[:, t, 2]
+            Xt = X[:, t]
+            g = gout[:, t] + dH
+            dZ = g * (Hp - Ht)
+            dph = g * (1 - Z) * (1 - Ht * Ht)
+            dHp = g * Z
+            # candidate: ph = basis([X | H*R]) @ Whs + bh
+            S2 = torch.cat(_basis_raw(plan, torch.cat([Xt, Hp * R], dim=-1), K), dim=-1)
+            dWh += torch.matmul(S2.reshape(-1, S2.size(-1)).t(), dph.reshape(-1, Co))
+            dbh += dph.sum(dim=(0, 1))
+            dU2 = _basis_adjoint(plan, torch.matmul(dph, Whs.t()), C, K)
+            dHR = dU2[..., Ci:]
+            dpzr = torch.cat([dZ * Z * (1 - Z), dHR * Hp * R * (1 - R)], dim=-1)
+            dHp = dHp + dHR * R
+            # z, r: [pz | pr] = basis([X | H]) @ [Wzs | Wrs] + [bz | br]
+            S1 = torch.cat(_basis_raw(plan, torch.cat([Xt, Hp], dim=-1), K), dim=-1)
+            dWzr += torch.matmul(S1.reshape(-1, S1.size(-1)).t(), dpzr.reshape(-1, 2 * Co))
+            dbzr += dpzr.sum(dim=(0, 1))
+            dU1 = _basis_adjoint(plan, torch.matmul(dpzr, Wzr.t()), C, K)
+            dH = dHp + dU1[..., Ci:]
+            if dX is not None:
+                dX[:, t] = dU2[..., :Ci] + dU1[..., :Ci]
+        gz = _unstack_weight_grad(dWzr[:, :Co], K, C)
+        gr = _unstack_weight_grad(dWzr[:, Co:], K, C)
+        gh = _unstack_weight_grad(dWh, K, C)
+        gb = (dbzr[:Co], dbzr[Co:], dbh) if ctx.has_bias else (None, None, None)
+        gH0 = dH if (ctx.has_h0 and ctx.needs_input_grad[1]) else None
+        return dX, gH0, gz, gr, gh, gb[0], gb[1], gb[2], None, None, None
+
+
 class DConv(torch.nn.Module):
     r"""Diffusion convolution (reference: dcrnn.py:7-111).  Messages use only the degree norms, never
     edge_weight (:39-40); norm_in is indexed by `row` and paired positionally with the re-sorted
@@ -92,6 +193,7 @@ class DCRNN(torch.nn.Module):
 
     _conv_cls = DConv
     _batched_semantics = False
+    _fused_training = True   # training forward = fused kernel + stash, backward = hand-written reverse-time loop
 
     def __init__(self, in_channels: int, out_channels: int, K: int, bias: bool = True):
         super().__init__()
@@ -153,6 +255,9 @@ class DCRNN(torch.nn.Module):
             out = ops.dcrnn_seq_fwd(plan, X.reshape(1, 1, N, self.in_channels), *self._params(), self.K, h0=h0,
                                     wimage=self._weight_image())
             return out[0, 0]
+        if self._fused_training and ops.dcrnn_seq_supported(plan, self.in_channels, self.out_channels, self.K):
+            h0 = None if H is None else H.reshape(1, N, self.out_channels)
+            return _DcrnnSeqFn.apply(X.reshape(1, 1, N, self.in_channels), h0, *self._params(), plan, self.K, self._weight_image())[0, 0]
         if H is None:
             H = torch.zeros(N, self.out_channels, device=X.device, dtype=X.dtype)
         return self._tiled_step(plan, X, H)
@@ -173,6 +278,11 @@ class BatchedDCRNN(DCRNN):
         if not self._needs_grad(X) and ops.dcrnn_seq_supported(plan, self.in_channels, self.out_channels, self.K):
             try:
                 return ops.dcrnn_seq_fwd(plan, X, *self._params(), self.K, wimage=self._weight_image())
+            except _lib.StmpUnsupported:
+                pass
+        if self._fused_training and ops.dcrnn_seq_supported(plan, self.in_channels, self.out_channels, self.K):
+            try:
+                return _DcrnnSeqFn.apply(X, None, *self._params(), plan, self.K, self._weight_image())
             except _lib.StmpUnsupported:
                 pass
         H = torch.zeros(B, N, self.out_channels, device=X.device, dtype=X.dtype)

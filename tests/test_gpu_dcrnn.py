@@ -188,3 +188,29 @@ def test_full_bench_size_two_independent_kernels_agree():
     want = R.batched_dcrnn(m.state_dict(), X, ei_t, ew_t)
     _close(out_tc[pick], want)
     _close(out_ff[pick], want)
+
+
+def test_training_path_fused_forward_manual_backward_matches_autograd():
+    """Training = fused forward (+ stash) and the hand-written reverse-time backward; gradients must match autograd
+    through the tiled path (same module, `_fused_training` off) on the cfg2 shape."""
+    ei, ew, series = synthetic.metr_la_like(0, 64)
+    ei_t, ew_t = torch.from_numpy(ei).to(DEV), torch.from_numpy(ew).to(DEV)
+    X = torch.from_numpy(series[:36]).reshape(3, 12, 207, 2).to(DEV)
+    torch.manual_seed(0)
+    a = BatchedDCRNN(2, 32, 2).to(DEV)
+    b = BatchedDCRNN(2, 32, 2).to(DEV)
+    b.load_state_dict(a.state_dict())
+    b._fused_training = False
+    w = torch.linspace(-1, 1, 3 * 12 * 207 * 32, device=DEV).view(3, 12, 207, 32)
+    Xa, Xb = X.clone().requires_grad_(True), X.clone().requires_grad_(True)
+    n0 = _lib.launch_count()
+    oa = a(Xa, ei_t, ew_t)
+    fused_fwd_launches = _lib.launch_count() - n0
+    ob = b(Xb, ei_t, ew_t)
+    assert fused_fwd_launches < 80 < _lib.launch_count() - n0 - fused_fwd_launches   # 1 fused launch (+ plan) vs the tiled graph
+    _close(oa, ob.detach().cpu())
+    (oa * w).sum().backward()
+    (ob * w).sum().backward()
+    _close(Xa.grad, Xb.grad.cpu(), 1e-3, 1e-5)
+    for (k, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
+        _close(pa.grad, pb.grad.cpu(), 1e-3, 2e-4)
