@@ -101,37 +101,38 @@ class _DcrnnSeqFn(torch.autograd.Function):
         C = Ci + Co
         Wzs, Wrs, Whs = _stack_weight(wz), _stack_weight(wr), _stack_weight(wh)
         Wzr = torch.cat([Wzs, Wrs], dim=1)
-        dWzr = torch.zeros_like(Wzr)
-        dWh = torch.zeros_like(Whs)
-        dbzr = gout.new_zeros(2 * Co)
-        dbh = gout.new_zeros(Co)
-        dX = torch.zeros_like(X) if ctx.needs_input_grad[0] else None
-        dH = gout.new_zeros(B, N, Co)
         gout = gout.contiguous()
+        Z, R, Ht = stash[:, :, 0], stash[:, :, 1], stash[:, :, 2]
+        first = H0.unsqueeze(1) if H0 is not None else out.new_zeros(B, 1, N, Co)
+        Hp_all = torch.cat([first, out[:, :-1]], dim=1)                                   # H_{t-1} for every t
+        # everything that does not depend on the reverse recurrence is done ONCE for all (b, t):
+        # the two bases (4 batched SpMMs instead of 4 per step) and, after the loop, the weight-gradient contractions
+        S1_all = torch.cat(_basis_raw(plan, torch.cat([X, Hp_all], dim=-1).reshape(B * T, N, C), K), dim=-1)
+        S2_all = torch.cat(_basis_raw(plan, torch.cat([X, Hp_all * R], dim=-1).reshape(B * T, N, C), K), dim=-1)
+        dph_all = torch.empty(B, T, N, Co, device=X.device, dtype=X.dtype)
+        dpzr_all = torch.empty(B, T, N, 2 * Co, device=X.device, dtype=X.dtype)
+        dX = torch.zeros_like(X) if ctx.needs_input_grad[0] else None
+        one_m_z, dt = 1 - Z, 1 - Ht * Ht
+        gz_fac, gr_fac = Z * one_m_z, Hp_all * R * (1 - R)
+        dH = gout.new_zeros(B, N, Co)
+        WhsT, WzrT = Whs.t().contiguous(), Wzr.t().contiguous()
         for t in range(T - 1, -1, -1):
-            Hp = out[:, t - 1] if t > 0 else (H0 if H0 is not None else gout.new_zeros(B, N, Co))
-            Z, R, Ht = stash[:, t, 0], stash[:, t, 1], stash[:, t, 2]
-            Xt = X[:, t]
             g = gout[:, t] + dH
-            dZ = g * (Hp - Ht)
-            dph = g * (1 - Z) * (1 - Ht * Ht)
-            dHp = g * Z
-            # candidate: ph = basis([X | H*R]) @ Whs + bh
-            S2 = torch.cat(_basis_raw(plan, torch.cat([Xt, Hp * R], dim=-1), K), dim=-1)
-            dWh += torch.matmul(S2.reshape(-1, S2.size(-1)).t(), dph.reshape(-1, Co))
-            dbh += dph.sum(dim=(0, 1))
-            dU2 = _basis_adjoint(plan, torch.matmul(dph, Whs.t()), C, K)
+            dph = g * one_m_z[:, t] * dt[:, t]
+            dph_all[:, t] = dph
+            dU2 = _basis_adjoint(plan, torch.matmul(dph, WhsT), C, K)
             dHR = dU2[..., Ci:]
-            dpzr = torch.cat([dZ * Z * (1 - Z), dHR * Hp * R * (1 - R)], dim=-1)
-            dHp = dHp + dHR * R
-            # z, r: [pz | pr] = basis([X | H]) @ [Wzs | Wrs] + [bz | br]
-            S1 = torch.cat(_basis_raw(plan, torch.cat([Xt, Hp], dim=-1), K), dim=-1)
-            dWzr += torch.matmul(S1.reshape(-1, S1.size(-1)).t(), dpzr.reshape(-1, 2 * Co))
-            dbzr += dpzr.sum(dim=(0, 1))
-            dU1 = _basis_adjoint(plan, torch.matmul(dpzr, Wzr.t()), C, K)
-            dH = dHp + dU1[..., Ci:]
+            dpzr = torch.cat([g * (Hp_all[:, t] - Ht[:, t]) * gz_fac[:, t], dHR * gr_fac[:, t]], dim=-1)
+            dpzr_all[:, t] = dpzr
+            dU1 = _basis_adjoint(plan, torch.matmul(dpzr, WzrT), C, K)
+            dH = g * Z[:, t] + dHR * R[:, t] + dU1[..., Ci:]
             if dX is not None:
                 dX[:, t] = dU2[..., :Ci] + dU1[..., :Ci]
+        nbC = S1_all.size(-1)
+        dWh = torch.matmul(S2_all.reshape(-1, nbC).t(), dph_all.reshape(-1, Co))
+        dWzr = torch.matmul(S1_all.reshape(-1, nbC).t(), dpzr_all.reshape(-1, 2 * Co))
+        dbh = dph_all.sum(dim=(0, 1, 2))
+        dbzr = dpzr_all.sum(dim=(0, 1, 2))
         gz = _unstack_weight_grad(dWzr[:, :Co], K, C)
         gr = _unstack_weight_grad(dWzr[:, Co:], K, C)
         gh = _unstack_weight_grad(dWh, K, C)
