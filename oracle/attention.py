@@ -94,3 +94,69 @@ def astgcn(p, X, edge_index, nb_block, normalization, time_strides, lambda_max=N
                          time_strides if i == 0 else 1, lambda_max)
     X = F.conv2d(X.permute(0, 3, 1, 2), p["_final_conv.weight"], p["_final_conv.bias"])
     return X[:, :, :, -1].permute(0, 2, 1)
+
+
+# ----------------------------------------------------------------------------------------------
+# STConv / MSTGCN                 nn/attention/stgcn.py, nn/attention/mstgcn.py
+# ----------------------------------------------------------------------------------------------
+def temporal_conv(p, X):
+    """TemporalConv.forward (stgcn.py:28-47): gated 1xk convolution over time; X (B,T,N,C) -> (B,T-k+1,N,C')."""
+    Xp = X.permute(0, 3, 2, 1)
+    P = F.conv2d(Xp, p["conv_1.weight"], p["conv_1.bias"])
+    Q = torch.sigmoid(F.conv2d(Xp, p["conv_2.weight"], p["conv_2.bias"]))
+    H = F.relu(P * Q + F.conv2d(Xp, p["conv_3.weight"], p["conv_3.bias"]))
+    return H.permute(0, 3, 2, 1)
+
+
+def stconv(p, X, edge_index, edge_weight=None, normalization="sym", training=True, eps=1e-5):
+    """STConv.forward (stgcn.py:131-160): TemporalConv -> ChebConv on every (b,t) slice -> ReLU -> TemporalConv ->
+    BatchNorm2d over the node axis (training mode = batch statistics, the module default)."""
+    from . import recurrent as R
+    T0 = temporal_conv(_sub(p, "_temporal_conv1."), X)
+    pc = _sub(p, "_graph_conv.")
+    K = len([k for k in pc if k.startswith("lins.")])
+    en = pyg.cheb_norm(edge_index, T0.size(-2), edge_weight, normalization, None, X.dtype)
+    T = torch.zeros_like(T0)
+    for b in range(T0.size(0)):
+        for t in range(T0.size(1)):
+            T[b][t] = R.cheb_conv(pc, T0[b][t], en, K)
+    T = temporal_conv(_sub(p, "_temporal_conv2."), F.relu(T))
+    T = T.permute(0, 2, 1, 3)
+    T = F.batch_norm(T, None if training else p["_batch_norm.running_mean"], None if training else p["_batch_norm.running_var"],
+                     p["_batch_norm.weight"], p["_batch_norm.bias"], training, 0.1, eps)
+    return T.permute(0, 2, 1, 3)
+
+
+def mstgcn_block(p, X, edge_index, time_strides, lambda_max=None):
+    """MSTGCNBlock.forward (mstgcn.py:60-122), static edge_index: the (F,B,N,T) -> (N,F,T*B) RESHAPE (:84-88) is a
+    reinterpretation, not a transpose -- it is the spec; ChebConv(normalization=None) with scipy lambda_max."""
+    from . import recurrent as R
+    B, N, Fi, T = X.shape
+    lam = lambda ei: lambda_max if lambda_max is not None else \
+        pyg.LaplacianLambdaMax()(pyg.Data(edge_index=ei, edge_attr=None, num_nodes=N)).lambda_max
+    pc = _sub(p, "_cheb_conv.")
+    K = len([k for k in pc if k.startswith("lins.")])
+    Ft = p["_time_conv.weight"].size(0)
+    if not isinstance(edge_index, list):
+        Xt = X.permute(2, 0, 1, 3).reshape(N, Fi, T * B).permute(2, 0, 1)
+        en = pyg.cheb_norm(edge_index, N, None, None, lam(edge_index), X.dtype)
+        Xt = F.relu(R.cheb_conv(pc, Xt, en, K))
+        Xt = Xt.permute(1, 2, 0).reshape(N, Ft, B, T).permute(2, 0, 1, 3)
+    else:                                         # per-timestep graphs (:96-115): a genuine per-slice convolution --
+        hats = []                                 # NOT the same function as the tensor path above
+        for t in range(T):
+            en = pyg.cheb_norm(edge_index[t], N, None, None, lam(edge_index[t]), X.dtype)
+            hats.append(R.cheb_conv(pc, X[:, :, :, t], en, K).unsqueeze(-1))
+        Xt = F.relu(torch.cat(hats, dim=-1))
+    Xt = F.conv2d(Xt.permute(0, 2, 1, 3), p["_time_conv.weight"], p["_time_conv.bias"], stride=(1, time_strides), padding=(0, 1))
+    Xr = F.conv2d(X.permute(0, 2, 1, 3), p["_residual_conv.weight"], p["_residual_conv.bias"], stride=(1, time_strides))
+    Y = F.layer_norm(F.relu(Xr + Xt).permute(0, 3, 2, 1), (Ft,), p["_layer_norm.weight"], p["_layer_norm.bias"])
+    return Y.permute(0, 2, 3, 1)
+
+
+def mstgcn(p, X, edge_index, nb_block, time_strides, lambda_max=None):
+    """MSTGCN.forward (mstgcn.py:181-200)."""
+    for i in range(nb_block):
+        X = mstgcn_block(_sub(p, f"_blocklist.{i}."), X, edge_index, time_strides if i == 0 else 1, lambda_max)
+    X = F.conv2d(X.permute(0, 3, 1, 2), p["_final_conv.weight"], p["_final_conv.bias"])
+    return X[:, :, :, -1].permute(0, 2, 1)

@@ -106,7 +106,9 @@ def batched_dcrnn(p, X: Tensor, edge_index: Tensor, edge_weight: Tensor) -> Tens
 def cheb_conv(p, x, ei_norm, K: int):
     """PyG ChebConv given the already-normalised (edge_index', w_hat) pair; params 'lins.k.weight', 'bias'."""
     ei, w = ei_norm
-    lin = lambda k, t: torch.nn.functional.linear(t, p[f"lins.{k}.weight"])
+    # .contiguous(): with a strided (permuted) input, ATen's CPU linear takes a different summation path for a
+    # detached weight than for the reference's nn.Parameter (1 ulp apart); the Parameter path equals the contiguous one.
+    lin = lambda k, t: torch.nn.functional.linear(t.contiguous(), p[f"lins.{k}.weight"])
     T0, T1 = x, x
     out = lin(0, T0)
     if K > 1:
@@ -154,6 +156,24 @@ def gconv_lstm_cell(p, X, edge_index, edge_weight=None, H=None, C=None, lambda_m
     T = torch.tanh(c("conv_x_c", X) + c("conv_h_c", H) + p["b_c"])
     C = Fg * C + I * T
     O = torch.sigmoid(c("conv_x_o", X) + c("conv_h_o", H) + p["w_c_o"] * C + p["b_o"])
+    return O * torch.tanh(C), C
+
+
+def gc_lstm_cell(p, X, edge_index, edge_weight=None, H=None, C=None, lambda_max=None, normalization="sym"):
+    """GCLSTM.forward (gc_lstm.py:152-205): dense `X @ W_g`, ChebConv only on H, no peepholes; O does not see C."""
+    K = _cheb_K(p, "conv_i")
+    out = p["W_i"].size(1)
+    if H is None:
+        H = torch.zeros(X.shape[0], out)
+    if C is None:
+        C = torch.zeros(X.shape[0], out)
+    en = pyg.cheb_norm(edge_index, X.size(-2), edge_weight, normalization, lambda_max, X.dtype)
+    c = lambda g: cheb_conv(_sub(p, f"conv_{g}."), H, en, K)
+    I = torch.sigmoid(torch.matmul(X, p["W_i"]) + c("i") + p["b_i"])
+    Fg = torch.sigmoid(torch.matmul(X, p["W_f"]) + c("f") + p["b_f"])
+    T = torch.tanh(torch.matmul(X, p["W_c"]) + c("c") + p["b_c"])
+    C = Fg * C + I * T
+    O = torch.sigmoid(torch.matmul(X, p["W_o"]) + c("o") + p["b_o"])
     return O * torch.tanh(C), C
 
 

@@ -81,3 +81,30 @@ def cheb_basis(plan, U: torch.Tensor, K: int):
     for _ in range(2, K):
         T.append(ops.spmm(plan, 0, T[-1], alpha=2.0, z=T[-2], beta=-1.0))
     return T
+
+
+class ChebConv(ChebParams, ChebPlanMixin):
+    """PyG ChebConv as a layer (ctor sites stgcn.py:108-114, mstgcn.py:33): `forward(x, edge_index, edge_weight=None,
+    batch=None, lambda_max=None)`, x (N,F) or (B,N,F) -- every leading batch row shares the cached operator, so the
+    reference's Python loops over (b, t) slices (stgcn.py:151-153) become the batch axis of one SpMM launch per hop,
+    followed by one GEMM over the stacked basis."""
+
+    def __init__(self, in_channels: int, out_channels: int, K: int, normalization="sym", bias: bool = True, **kwargs):
+        super().__init__(in_channels, out_channels, K, bias)
+        assert normalization in (None, "sym", "rw"), "Invalid normalization"
+        self.normalization = normalization
+        self._init_plans()
+
+    def forward(self, x, edge_index, edge_weight=None, batch=None, lambda_max=None):
+        if batch is not None:
+            raise ValueError("multi-graph `batch` vectors are not supported; pass (B,N,F) instead")
+        if self.K > 1:
+            plan = self._cheb_plan(edge_index, edge_weight, x.size(-2), self.normalization, lambda_max)
+            S = torch.cat(cheb_basis(plan, x, self.K), dim=-1)
+        else:
+            S = x                                                        # K=1: no propagation at all
+        out = torch.matmul(S, self.stacked())
+        return out if self.bias is None else out + self.bias
+
+    def __repr__(self):
+        return f"{self.__class__.__name__}({self.in_channels}, {self.out_channels}, K={self.K}, normalization={self.normalization})"

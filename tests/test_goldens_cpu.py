@@ -56,3 +56,31 @@ def test_astgcn_goldens(golden_dir):
         got = A.astgcn(c["state"], c["X"], g["edge_index"], g["ctor"]["nb_block"], c["normalization"],
                        g["ctor"]["time_strides"], c["lambda_max"])
         assert torch.allclose(got, c["out"], rtol=1e-6, atol=1e-6)
+
+
+def test_gc_lstm_goldens(golden_dir):
+    g = _load(golden_dir, "gc_lstm_small")
+    for c in g["cases"].values():
+        h, cc = R.gc_lstm_cell(c["state"], c["X"], g["edge_index"], g["edge_weight"], c["H"], c["C"], c["lambda_max"], c["normalization"])
+        assert torch.equal(h, c["outH"]) and torch.equal(cc, c["outC"])
+        if "outH0" in c:
+            h, cc = R.gc_lstm_cell(c["state"], c["X"], g["edge_index"], lambda_max=c["lambda_max"], normalization=c["normalization"])
+            assert torch.equal(h, c["outH0"]) and torch.equal(cc, c["outC0"])
+
+
+def test_stconv_goldens(golden_dir):
+    g = _load(golden_dir, "stconv_small")
+    for c in g["cases"].values():
+        got = A.stconv(c["state"], c["X"], g["edge_index"], g["edge_weight"], c["normalization"], training=True)
+        assert torch.equal(got, c["out_train"])                # batch statistics do not depend on the running buffers
+        assert torch.equal(A.stconv(c["state"], c["X"], g["edge_index"], g["edge_weight"], c["normalization"], training=False), c["out_eval"])
+        assert torch.equal(A.stconv(c["state"], c["X"], g["edge_index"], None, c["normalization"], training=False), c["out_eval_noew"])
+
+
+def test_mstgcn_goldens(golden_dir):
+    g = _load(golden_dir, "mstgcn_small")
+    for c in g["cases"].values():
+        got = A.mstgcn(c["state"], c["X"], g["edge_index"], g["ctor"]["nb_block"], c["time_strides"], g["lambda_max"])
+        assert torch.allclose(got, c["out"], rtol=1e-6, atol=1e-6)      # ARPACK start vector: lambda_max moves in the last bits
+        got = A.mstgcn(c["state"], c["X"], [g["edge_index"]] * 6, g["ctor"]["nb_block"], c["time_strides"], g["lambda_max"])
+        assert torch.allclose(got, c["out_list"], rtol=1e-6, atol=1e-6)  # list path: a different function (no reshape scramble)

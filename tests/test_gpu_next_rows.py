@@ -1,0 +1,135 @@
+"""GPU parity of the SURVEY 8f rank-1 modules (GCLSTM, STConv, MSTGCN) through the public modules -> C ABI, against
+goldens generated from the unmodified reference (tests/golden/make_goldens_next.py).  Strict fp32: rtol 1e-4 / atol
+1e-5 on outputs, 1e-3 / 1e-5 on gradients (same bars as the round-1 cells)."""
+import os
+
+import pytest
+import torch
+
+from oracle import recurrent as R
+from pytorch_geometric_temporal_b200 import _lib
+from pytorch_geometric_temporal_b200.dataset import synthetic
+from pytorch_geometric_temporal_b200.nn.attention import MSTGCN, STConv
+from pytorch_geometric_temporal_b200.nn.recurrent import GCLSTM, ChebConv
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _load(golden_dir, name):
+    return torch.load(os.path.join(golden_dir, name + ".pt"), weights_only=False)
+
+
+def _close(got, want, rtol=1e-4, atol=1e-5):
+    got = got.detach().cpu()
+    assert got.shape == want.shape
+    assert torch.allclose(got, want, rtol=rtol, atol=atol), f"max abs err {(got - want).abs().max():.3e}"
+
+
+def _loss(outs):
+    return sum((o * torch.linspace(-1, 1, o.numel(), device=o.device).view_as(o)).sum() for o in outs)
+
+
+def _check_grads(m, want, rtol=1e-3, atol=1e-5):
+    for k, p in m.named_parameters():
+        _close(p.grad, want[k], rtol, atol)
+
+
+def test_gc_lstm_goldens(golden_dir):
+    g = _load(golden_dir, "gc_lstm_small")
+    ei, ew = g["edge_index"].to(DEV), g["edge_weight"].to(DEV)
+    for name, c in g["cases"].items():
+        cin, cout = c.get("cin", 4), c.get("cout", 16)
+        m = GCLSTM(cin, cout, c["K"], normalization=c["normalization"]).to(DEV)
+        m.load_state_dict(c["state"])
+        lm = None if c["lambda_max"] is None else c["lambda_max"].to(DEV)
+        x, h, cc = c["X"].to(DEV), c["H"].to(DEV), c["C"].to(DEV)
+        n0 = _lib.launch_count()
+        with torch.no_grad():
+            ho, co = m(x, ei, ew, h, cc, lm)                      # in-place basis + fused gate kernels / tcgen05 epilogue
+            _close(ho, c["outH"]); _close(co, c["outC"])
+            if "outH0" in c:
+                ho, co = m(x, ei, lambda_max=lm)
+                _close(ho, c["outH0"]); _close(co, c["outC0"])
+        assert _lib.launch_count() > n0
+        if "grads" in c:
+            xg, hg, cg = (t.clone().requires_grad_(True) for t in (x, h, cc))
+            ho, co = m(xg, ei, ew, hg, cg, lm)                    # autograd path
+            _close(ho, c["outH"]); _close(co, c["outC"])
+            _loss([ho, co]).backward()
+            _check_grads(m, c["grads"])
+            _close(xg.grad, c["gX"], 1e-3, 1e-5); _close(hg.grad, c["gH"], 1e-3, 1e-5); _close(cg.grad, c["gC"], 1e-3, 1e-5)
+
+
+def test_gc_lstm_recurrence_matches_oracle_over_steps():
+    """size-independent property: T chained cell calls stay on the oracle's trajectory (H, C fed back)."""
+    ei, ew, series = synthetic.metr_la_like(seed=1, t_total=8)
+    ei, ew = torch.from_numpy(ei), torch.from_numpy(ew)
+    torch.manual_seed(0)
+    m = GCLSTM(2, 32, 3)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    mg = m.to(DEV)
+    eig, ewg = ei.to(DEV), ew.to(DEV)
+    Hc = Cc = Hg = Cg = None
+    for t in range(6):
+        x = torch.from_numpy(series[t])
+        Hc, Cc = R.gc_lstm_cell(sd, x, ei, ew, Hc, Cc)
+        with torch.no_grad():
+            Hg, Cg = mg(x.to(DEV), eig, ewg, Hg, Cg)
+        _close(Hg, Hc); _close(Cg, Cc)
+
+
+def test_stconv_goldens(golden_dir):
+    g = _load(golden_dir, "stconv_small")
+    ei, ew = g["edge_index"].to(DEV), g["edge_weight"].to(DEV)
+    for name, c in g["cases"].items():
+        m = STConv(K=c["K"], normalization=c["normalization"], **g["ctor"]).to(DEV)
+        m.load_state_dict(c["state"])
+        X = c["X"].to(DEV)
+        m.eval()
+        n0 = _lib.launch_count()
+        with torch.no_grad():
+            _close(m(X, ei, ew), c["out_eval"])
+            _close(m(X, ei), c["out_eval_noew"])
+        # (B, T') slices ride the batch axis: (K-1) SpMM launches per forward, not B*T'*(K-1)
+        assert _lib.launch_count() - n0 <= 2 * max(c["K"] - 1, 0) + 40       # + plan builds of the two graphs
+        m.train()
+        Xg = X.clone().requires_grad_(True)
+        out = m(Xg, ei, ew)                                     # training-mode BatchNorm: batch statistics
+        _close(out, c["out_train"])
+        _loss([out]).backward()
+        # BatchNorm divides by a batch std: gradients carry its conditioning, same bar as ASTGCN end-to-end
+        _check_grads(m, c["grads"], 2e-3, 2e-5)
+        _close(Xg.grad, c["gX"], 2e-3, 2e-5)
+
+
+def test_stconv_batched_equals_per_slice_chebconv():
+    """the folded (B*T') batch must equal the reference's per-slice loop bit for bit (same kernel, same row order)."""
+    ei, ew, _ = synthetic.metr_la_like(seed=2, t_total=4)
+    ei, ew = torch.from_numpy(ei).to(DEV), torch.from_numpy(ew).to(DEV)
+    torch.manual_seed(0)
+    conv = ChebConv(8, 8, 3).to(DEV)
+    x = torch.randn(3, 5, 207, 8, device=DEV)
+    with torch.no_grad():
+        whole = conv(x.reshape(15, 207, 8), ei, ew).reshape(3, 5, 207, 8)
+        for b in range(3):
+            for t in range(5):
+                assert torch.allclose(conv(x[b, t], ei, ew), whole[b, t], rtol=1e-6, atol=1e-6)
+
+
+def test_mstgcn_goldens(golden_dir):
+    g = _load(golden_dir, "mstgcn_small")
+    ei = g["edge_index"].to(DEV)
+    for name, c in g["cases"].items():
+        m = MSTGCN(time_strides=c["time_strides"], **g["ctor"]).to(DEV)
+        m.load_state_dict(c["state"])
+        X = c["X"].to(DEV)
+        with torch.no_grad():
+            _close(m(X, ei), c["out"], 2e-4, 2e-5)               # two blocks of LayerNorm on GEMM rounding (= ASTGCN bar)
+            _close(m(X, [ei] * 6), c["out_list"], 2e-4, 2e-5)    # per-timestep edge_index list path
+        Xg = X.clone().requires_grad_(True)
+        out = m(Xg, ei)
+        _close(out, c["out"], 2e-4, 2e-5)
+        _loss([out]).backward()
+        _check_grads(m, c["grads"], 2e-3, 2e-5)
+        _close(Xg.grad, c["gX"], 2e-3, 2e-5)

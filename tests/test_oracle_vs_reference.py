@@ -82,3 +82,44 @@ def test_astgcn(norm):
         want = ref(Xa, eiu)
         got = A.astgcn(ref.state_dict(), Xa, eiu, 2, norm, 2, lm)
     assert torch.allclose(want, got, rtol=1e-6, atol=1e-6)  # diag-scale vs dense matmul: 1 ulp
+
+
+# ---- GCLSTM, STConv, MSTGCN ---------------------------------------------------------------
+@pytest.mark.parametrize("K", [1, 2, 3])
+@pytest.mark.parametrize("norm", ["sym", "rw", None])
+def test_gc_lstm(K, norm):
+    ei, ew = _graph()
+    lm = None if norm == "sym" else torch.tensor(2.3)
+    X, H, C = torch.randn(12, 4), torch.randn(12, 8), torch.randn(12, 8)
+    with torch.no_grad():
+        ref = refload.load("nn.recurrent.gc_lstm").GCLSTM(4, 8, K, normalization=norm)
+        a, b = ref(X, ei, ew, H, C, lm), R.gc_lstm_cell(ref.state_dict(), X, ei, ew, H, C, lm, norm)
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+        a, b = ref(X, ei, lambda_max=lm), R.gc_lstm_cell(ref.state_dict(), X, ei, lambda_max=lm, normalization=norm)
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+
+
+@pytest.mark.parametrize("K", [1, 2, 3])
+def test_stconv(K):
+    ei, ew = _graph()
+    ref = refload.load("nn.attention.stgcn").STConv(12, 3, 8, 6, 3, K)
+    X = torch.randn(2, 9, 12, 3)
+    with torch.no_grad():
+        want = ref(X, ei, ew)                                   # module default: training-mode BatchNorm
+        assert torch.equal(want, A.stconv(ref.state_dict(), X, ei, ew))
+        ref.eval()
+        assert torch.equal(ref(X, ei, ew), A.stconv(ref.state_dict(), X, ei, ew, training=False))
+        assert torch.equal(ref._temporal_conv1(X), A.temporal_conv({k[len("_temporal_conv1."):]: v for k, v in ref.state_dict().items()
+                                                                     if k.startswith("_temporal_conv1.")}, X))
+
+
+@pytest.mark.parametrize("strides", [1, 2])
+def test_mstgcn(strides):
+    ei, _ = _graph()
+    und = sorted({(a, b) for a, b in ei.t().tolist() if a != b} | {(b, a) for a, b in ei.t().tolist() if a != b})
+    eiu = torch.tensor(und).t().contiguous()
+    ref = refload.load("nn.attention.mstgcn").MSTGCN(2, 2, 3, 8, 8, strides, 4, 6)
+    X = torch.randn(3, 12, 2, 6)
+    with torch.no_grad():
+        assert torch.allclose(ref(X, eiu), A.mstgcn(ref.state_dict(), X, eiu, 2, strides), rtol=1e-6, atol=1e-6)  # ARPACK seed
+        assert torch.allclose(ref(X, [eiu] * 6), A.mstgcn(ref.state_dict(), X, [eiu] * 6, 2, strides), rtol=1e-6, atol=1e-6)
