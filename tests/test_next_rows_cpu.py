@@ -1,0 +1,129 @@
+"""Host-side tests of the SURVEY 8f rank 2/3 rows: StaticGraphTemporalSignalBatch (mirrors test/batch_test.py:120-134,
+:181-190) and the offline METR-LA / PEMS-BAY loaders (mirrors test/index_test.py:18-66 on synthetic archives; where
+/root/reference is present the unmodified reference loaders are run on the same files and must agree bit for bit)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import refload
+from pytorch_geometric_temporal_b200.dataset import METRLADatasetLoader, PemsBayDatasetLoader, dense_to_sparse
+from pytorch_geometric_temporal_b200.signal import StaticGraphTemporalSignalBatch, temporal_signal_split
+
+
+def _archive(tmp, n, f, t, prefix=""):
+    rng = np.random.default_rng(7)
+    A = (rng.random((n, n)) < 0.2) * rng.random((n, n)).astype(np.float32)
+    np.fill_diagonal(A, 1.0)
+    np.save(os.path.join(tmp, prefix + "adj_mat.npy"), A.astype(np.float32))
+    np.save(os.path.join(tmp, prefix + "node_values.npy"), (rng.normal(size=(t, n, f)) * 10 + 50))   # float64, like the archive
+    return A
+
+
+def test_static_graph_temporal_signal_batch_none_and_typing():
+    ds = StaticGraphTemporalSignalBatch(None, None, [None, None], [None, None], None)
+    n = 0
+    for snap in ds:
+        assert snap.edge_index is None and snap.edge_attr is None and snap.x is None and snap.y is None and snap.batch is None
+        n += 1
+    assert n == 2
+    ds = StaticGraphTemporalSignalBatch(None, None, [np.array([1])], [np.array([2])], None)
+    for snap in ds:
+        assert snap.x.shape == (1,) and snap.y.shape == (1,) and snap.batch is None
+
+
+def test_static_graph_temporal_signal_batch_iteration_and_split():
+    rng = np.random.default_rng(0)
+    # two graphs of 5 and 7 nodes, block-diagonal edge list
+    e1, e2 = rng.integers(0, 5, (2, 12)), rng.integers(0, 7, (2, 20)) + 5
+    ei = np.concatenate([e1, e2], axis=1)
+    ew = rng.random(ei.shape[1])
+    batches = np.array([0] * 5 + [1] * 7)
+    feats = [rng.random((12, 3)) for _ in range(10)]
+    targs = [rng.random((12,)) for _ in range(10)]
+    extra = [rng.integers(0, 4, (12,)) for _ in range(10)]
+    ds = StaticGraphTemporalSignalBatch(ei, ew, feats, targs, batches, marks=extra)
+    for epoch in range(2):
+        seen = 0
+        for t, snap in enumerate(ds):
+            assert snap.x.shape == (12, 3) and snap.x.dtype == torch.float32
+            assert snap.edge_index.dtype == torch.int64 and torch.equal(snap.edge_index, torch.from_numpy(ei))
+            assert torch.equal(snap.batch, torch.from_numpy(batches)) and snap.batch.dtype == torch.int64
+            assert torch.equal(snap.marks, torch.from_numpy(extra[t]))
+            assert "batch" in snap.keys()
+            seen += 1
+        assert seen == 10
+    a, b = ds[0], ds[1]
+    assert a.edge_index is b.edge_index and a.batch is b.batch        # static tensors are shared, not re-wrapped
+    tr, te = temporal_signal_split(ds, 0.8)
+    assert isinstance(tr, StaticGraphTemporalSignalBatch) and tr.snapshot_count == 8 and te.snapshot_count == 2
+    assert torch.equal(te[0].batch, torch.from_numpy(batches))
+    assert isinstance(ds[2:5], StaticGraphTemporalSignalBatch) and len(ds[2:5].features) == 3
+
+
+def test_dense_to_sparse_row_major():
+    A = torch.tensor([[0.0, 2.0, 0.0], [3.0, 0.0, 0.0], [0.0, 4.0, 5.0]])
+    ei, w = dense_to_sparse(A)
+    assert ei.tolist() == [[0, 1, 2, 2], [1, 0, 1, 2]] and w.tolist() == [2.0, 3.0, 4.0, 5.0]
+
+
+@pytest.mark.parametrize("cls,prefix,lags", [(METRLADatasetLoader, "", 6), (PemsBayDatasetLoader, "pems_", 4)])
+def test_index_batching_equals_snapshot_iterator(tmp_path, cls, prefix, lags):
+    """test/index_test.py:18-66 on a synthetic archive: windows served by index batching are the snapshots, bit for bit."""
+    tmp = str(tmp_path)
+    A = _archive(tmp, 9, 2, 60, prefix)
+    dataset = cls(raw_data_dir=tmp).get_dataset(num_timesteps_in=lags, num_timesteps_out=lags)
+    train, val, test, edges, weights, means, stds = cls(raw_data_dir=tmp, index=True).get_index_dataset(batch_size=1, shuffle=False, lags=lags)
+    n_windows = 60 - (2 * lags - 1)
+    assert len(train.dataset) == round(n_windows * 0.7) and len(test.dataset) == round(n_windows * 0.2)
+    assert len(train.dataset) + len(val.dataset) + len(test.dataset) == n_windows
+    assert edges.shape == (2, int((A != 0).sum())) and means.shape == (2,) and stds.shape == (2,)
+    for epoch in range(2):
+        k = 0
+        for snap, (x, y) in zip(dataset, train):
+            x = torch.squeeze(x).permute(1, 2, 0)
+            y = torch.squeeze(y)[..., 0].permute(1, 0) if cls is METRLADatasetLoader else torch.squeeze(y).permute(1, 2, 0)
+            assert torch.equal(snap.x, x) and torch.equal(snap.y, y)
+            assert torch.equal(snap.edge_index, edges) and torch.equal(snap.edge_attr, weights)
+            k += 1
+        assert k == len(train.dataset)
+
+
+def test_offline_loader_errors(tmp_path):
+    with pytest.raises(FileNotFoundError):
+        METRLADatasetLoader(raw_data_dir=str(tmp_path))
+    _archive(str(tmp_path), 5, 2, 40)
+    with pytest.raises(ValueError):
+        METRLADatasetLoader(raw_data_dir=str(tmp_path)).get_index_dataset()
+
+
+@pytest.mark.skipif(not refload.available(), reason="/root/reference not present")
+@pytest.mark.parametrize("mod,name,prefix", [("dataset.metr_la", "METRLADatasetLoader", ""), ("dataset.pems_bay", "PemsBayDatasetLoader", "pems_")])
+def test_offline_loaders_match_reference(tmp_path, mod, name, prefix):
+    tmp = str(tmp_path)
+    _archive(tmp, 9, 2, 60, prefix)
+    open(os.path.join(tmp, "METR-LA.zip" if prefix == "" else "PEMS-BAY.zip"), "wb").close()      # the reference checks the zip exists
+    # the reference loader does `from ..signal import StaticGraphTemporalSignal`; its signal/__init__ pulls every iterator
+    # (PyG Batch/HeteroData), so expose just that one unmodified class on the path-only parent package refload registers
+    import sys
+    sig = refload.load("signal.static_graph_temporal_signal")
+    sys.modules["torch_geometric_temporal.signal"].StaticGraphTemporalSignal = sig.StaticGraphTemporalSignal
+    ref_cls = getattr(refload.load(mod), name)
+    ours_cls = METRLADatasetLoader if prefix == "" else PemsBayDatasetLoader
+    want, got = ref_cls(raw_data_dir=tmp).get_dataset(6, 6), ours_cls(raw_data_dir=tmp).get_dataset(6, 6)
+    assert want.snapshot_count == got.snapshot_count
+    for a, b in zip(want, got):
+        assert torch.equal(a.x, b.x) and torch.equal(a.y, b.y) and torch.equal(a.edge_index, b.edge_index) and torch.equal(a.edge_attr, b.edge_attr)
+    w = ref_cls(raw_data_dir=tmp, index=True).get_index_dataset(lags=6, batch_size=4)
+    g = ours_cls(raw_data_dir=tmp, index=True).get_index_dataset(lags=6, batch_size=4)
+    for i in range(3):
+        for (xa, ya), (xb, yb) in zip(w[i], g[i]):
+            assert torch.equal(xa, xb) and torch.equal(ya, yb)
+    for i in range(3, 7):
+        assert torch.equal(w[i], g[i])
+    # DistributedSampler shards
+    w = ref_cls(raw_data_dir=tmp, index=True).get_index_dataset(lags=6, batch_size=4, shuffle=True, world_size=2, ddp_rank=1)
+    g = ours_cls(raw_data_dir=tmp, index=True).get_index_dataset(lags=6, batch_size=4, shuffle=True, world_size=2, ddp_rank=1)
+    for (xa, ya), (xb, yb) in zip(w[0], g[0]):
+        assert torch.equal(xa, xb) and torch.equal(ya, yb)
