@@ -87,12 +87,13 @@ def test_stconv_goldens(golden_dir):
         m.load_state_dict(c["state"])
         X = c["X"].to(DEV)
         m.eval()
-        n0 = _lib.launch_count()
         with torch.no_grad():
             _close(m(X, ei, ew), c["out_eval"])
             _close(m(X, ei), c["out_eval_noew"])
+            n0 = _lib.launch_count()
+            m(X, ei, ew)                                         # plan cached by now
         # (B, T') slices ride the batch axis: (K-1) SpMM launches per forward, not B*T'*(K-1)
-        assert _lib.launch_count() - n0 <= 2 * max(c["K"] - 1, 0) + 40       # + plan builds of the two graphs
+        assert _lib.launch_count() - n0 == c["K"] - 1
         m.train()
         Xg = X.clone().requires_grad_(True)
         out = m(Xg, ei, ew)                                     # training-mode BatchNorm: batch statistics
