@@ -169,6 +169,24 @@ int stmp_lstm_ifc(int64_t rows, int64_t cout, const float* pi, const float* pf, 
 int stmp_lstm_oh(int64_t rows, int64_t cout, const float* po, const float* cnew, const float* wco,
                  const float* bo, float* o, float* hnew, void* stream);
 
+/* GRU reverse-time gate derivatives: the pointwise part of the hand-written backward of the DCRNN sequence (what
+ * autograd records for dcrnn.py:172-192, once per step).  Tensors are (B, N, cout) with a batch stride in elements
+ * (slices of gout (B,T,N,cout) and of the forward stash (B,T,3,N,cout)); du2/du1 are (B, N, du_ld) buffers whose
+ * first cin+cout columns hold dL/d[X | H*R] and dL/d[X | H_{t-1}] of the step being closed.
+ *   stmp_gru_bwd_carry: close step t+1 (all of g_prev.. or none): dH = g_prev*Z + dU2[...,cin:]*R + dU1[...,cin:],
+ *                       dX_{t+1} = dU2[...,:cin] + dU1[...,:cin] (dx nullable), dh_out = dH (nullable);
+ *                       open step t (gout.. or none): g = gout_t + dH, dph = g (1-Z_t)(1-Ht_t^2).
+ *   stmp_gru_bwd_zr:    dpzr[..., :cout] = g (H_{t-1} - Ht) Z (1-Z);  dpzr[..., cout:] = dU2[...,cin:] H_{t-1} R (1-R);
+ *                       hprev NULL = zeros (first step without H0).
+ */
+int stmp_gru_bwd_carry(int64_t B, int64_t N, int64_t cin, int64_t cout, int64_t du_ld, const float* g_prev,
+                       const float* z_prev, const float* r_prev, const float* du2, const float* du1, float* dx,
+                       int64_t dx_bstride, const float* gout, int64_t gout_bstride, const float* z, const float* ht,
+                       int64_t stash_bstride, float* g, float* dph, float* dh_out, void* stream);
+int stmp_gru_bwd_zr(int64_t B, int64_t N, int64_t cin, int64_t cout, int64_t du_ld, const float* g, const float* hprev,
+                    int64_t hprev_bstride, const float* z, const float* r, const float* ht, int64_t stash_bstride,
+                    const float* du2, float* dpzr, void* stream);
+
 /* ---- K4: dense node-feature x weight contraction on the tensor cores (tcgen05), fp32 in / fp32 out ------------------
  * C[M,N] = A[M,K] @ W[K,N] + bias.  Replaces `torch.matmul(Tx_k, weight[..][k])` / ChebConv `lins[k](Tx_k)` / GCNConv
  * `lin(x)` (dcrnn.py:81-105; PyG) for the large-graph (tiled) path.  fp32-class accuracy: operands are split into fp16

@@ -78,6 +78,59 @@ __global__ void __launch_bounds__(kT) k_window_gather(const V* __restrict__ seri
   }
 }
 
+
+// ---- reverse-time GRU gate derivatives (hand-written backward of the DCRNN sequence, dcrnn.py:172-192) -------------
+// One thread per (b, n, c), c < Co.  `close` finishes step t+1 (dH_t+1 -> dH_t, dX_{t+1}), `open` starts step t
+// (g_t = dL/dH_t, d pre-activation of the candidate); both halves are optional so one kernel serves the first step,
+// the steady state and the final flush.
+struct GruBwdCarry {
+  long long total; int N, Ci, Co; long long du_ld;
+  const float* g_prev; const float* z_prev; const float* r_prev; const float* du2; const float* du1;
+  float* dx; long long dx_bs;
+  const float* gout; long long gout_bs; const float* z; const float* ht; long long stash_bs;
+  float* g; float* dph; float* dh_out;
+};
+__global__ void __launch_bounds__(kT) k_gru_bwd_carry(GruBwdCarry p) {
+  const int Co = p.Co, Ci = p.Ci;
+  const long long per = (long long)p.N * Co;
+  for (long long i = blockIdx.x * (long long)kT + threadIdx.x; i < p.total; i += (long long)gridDim.x * kT) {
+    const long long b = i / per, rem = i - b * per;
+    const int n = (int)(rem / Co), c = (int)(rem - (long long)n * Co);
+    float dh = 0.f;
+    if (p.g_prev) {
+      const long long row = (b * p.N + n) * p.du_ld;
+      const float dhr = p.du2[row + Ci + c];
+      dh = p.g_prev[i] * p.z_prev[b * p.stash_bs + rem] + dhr * p.r_prev[b * p.stash_bs + rem] + p.du1[row + Ci + c];
+      if (p.dx)
+        for (int ci = c; ci < Ci; ci += Co) p.dx[b * p.dx_bs + (long long)n * Ci + ci] = p.du2[row + ci] + p.du1[row + ci];
+    }
+    if (p.dh_out) p.dh_out[i] = dh;
+    if (p.gout) {
+      const float g = p.gout[b * p.gout_bs + rem] + dh;
+      const float z = p.z[b * p.stash_bs + rem], ht = p.ht[b * p.stash_bs + rem];
+      p.g[i] = g;
+      p.dph[i] = g * (1.f - z) * (1.f - ht * ht);
+    }
+  }
+}
+// d pre-activations of the update and reset gates at step t:  dpz = g (H_{t-1} - Ht) Z (1-Z),  dpr = dHR H_{t-1} R (1-R)
+__global__ void __launch_bounds__(kT) k_gru_bwd_zr(long long total, int N, int Ci, int Co, long long du_ld, const float* __restrict__ g,
+                                                   const float* __restrict__ hprev, long long hprev_bs, const float* __restrict__ z,
+                                                   const float* __restrict__ r, const float* __restrict__ ht, long long stash_bs,
+                                                   const float* __restrict__ du2, float* __restrict__ dpzr) {
+  const long long per = (long long)N * Co;
+  for (long long i = blockIdx.x * (long long)kT + threadIdx.x; i < total; i += (long long)gridDim.x * kT) {
+    const long long b = i / per, rem = i - b * per;
+    const int n = (int)(rem / Co), c = (int)(rem - (long long)n * Co);
+    const float hp = hprev ? hprev[b * hprev_bs + rem] : 0.f;
+    const float zv = z[b * stash_bs + rem], rv = r[b * stash_bs + rem], hv = ht[b * stash_bs + rem];
+    const float dhr = du2[(b * N + n) * du_ld + Ci + c];
+    float* o = dpzr + (b * N + n) * 2 * Co;
+    o[c] = g[i] * (hp - hv) * zv * (1.f - zv);
+    o[Co + c] = dhr * hp * rv * (1.f - rv);
+  }
+}
+
 }  // namespace
 }  // namespace stmp
 
@@ -135,5 +188,34 @@ extern "C" int stmp_window_gather(const float* series, int64_t t_total, int64_t 
                                                                               (int)horizon, x, y);
   }
   STMP_LAUNCH_OK("k_window_gather");
+  return STMP_OK;
+}
+
+extern "C" int stmp_gru_bwd_carry(int64_t B, int64_t N, int64_t cin, int64_t cout, int64_t du_ld, const float* g_prev,
+                                  const float* z_prev, const float* r_prev, const float* du2, const float* du1, float* dx,
+                                  int64_t dx_bstride, const float* gout, int64_t gout_bstride, const float* z, const float* ht,
+                                  int64_t stash_bstride, float* g, float* dph, float* dh_out, void* stream) {
+  STMP_REQUIRE(B >= 0 && N > 0 && cin >= 0 && cout > 0 && du_ld >= cin + cout, STMP_EINVAL, "stmp_gru_bwd_carry: bad sizes");
+  STMP_REQUIRE(!g_prev || (z_prev && r_prev && du2 && du1), STMP_EINVAL, "stmp_gru_bwd_carry: incomplete `close` operands");
+  STMP_REQUIRE(!gout || (z && ht && g && dph), STMP_EINVAL, "stmp_gru_bwd_carry: incomplete `open` operands");
+  STMP_REQUIRE(g_prev || gout, STMP_EINVAL, "stmp_gru_bwd_carry: nothing to do");
+  if (B == 0) return STMP_OK;
+  GruBwdCarry p;
+  p.total = B * N * cout; p.N = (int)N; p.Ci = (int)cin; p.Co = (int)cout; p.du_ld = du_ld;
+  p.g_prev = g_prev; p.z_prev = z_prev; p.r_prev = r_prev; p.du2 = du2; p.du1 = du1; p.dx = dx; p.dx_bs = dx_bstride;
+  p.gout = gout; p.gout_bs = gout_bstride; p.z = z; p.ht = ht; p.stash_bs = stash_bstride; p.g = g; p.dph = dph; p.dh_out = dh_out;
+  k_gru_bwd_carry<<<grid_for(p.total), kT, 0, (cudaStream_t)stream>>>(p);
+  STMP_LAUNCH_OK("k_gru_bwd_carry");
+  return STMP_OK;
+}
+extern "C" int stmp_gru_bwd_zr(int64_t B, int64_t N, int64_t cin, int64_t cout, int64_t du_ld, const float* g, const float* hprev,
+                               int64_t hprev_bstride, const float* z, const float* r, const float* ht, int64_t stash_bstride,
+                               const float* du2, float* dpzr, void* stream) {
+  STMP_REQUIRE(B >= 0 && N > 0 && cin >= 0 && cout > 0 && du_ld >= cin + cout && g && z && r && ht && du2 && dpzr, STMP_EINVAL,
+               "stmp_gru_bwd_zr: bad argument");
+  if (B == 0) return STMP_OK;
+  k_gru_bwd_zr<<<grid_for(B * N * cout), kT, 0, (cudaStream_t)stream>>>(B * N * cout, (int)N, (int)cin, (int)cout, du_ld, g, hprev,
+                                                                         hprev_bstride, z, r, ht, stash_bstride, du2, dpzr);
+  STMP_LAUNCH_OK("k_gru_bwd_zr");
   return STMP_OK;
 }

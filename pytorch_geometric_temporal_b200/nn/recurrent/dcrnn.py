@@ -94,50 +94,89 @@ class _DcrnnSeqFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gout):
+        """Reverse-time loop with 8 launches per step: [carry] -> GEMM -> 2 transposed SpMMs (in-place adjoint) -> [zr] ->
+        GEMM -> 2 transposed SpMMs.  Everything that does not depend on the dH recurrence is hoisted out: both bases of
+        every step are built with 4 batched SpMMs straight into their column blocks, and the weight gradients are two
+        large GEMMs over all (t, b, n) rows after the loop."""
         X, H0, wz, wr, wh, out, stash = ctx.saved_tensors
         plan, K = ctx.plan, ctx.K
         B, T, N, Ci = X.shape
         Co = wz.size(-1)
         C = Ci + Co
-        Wzs, Wrs, Whs = _stack_weight(wz), _stack_weight(wr), _stack_weight(wh)
-        Wzr = torch.cat([Wzs, Wrs], dim=1)
-        gout = gout.contiguous()
-        Z, R, Ht = stash[:, :, 0], stash[:, :, 1], stash[:, :, 2]
-        first = H0.unsqueeze(1) if H0 is not None else out.new_zeros(B, 1, N, Co)
-        Hp_all = torch.cat([first, out[:, :-1]], dim=1)                                   # H_{t-1} for every t
-        # everything that does not depend on the reverse recurrence is done ONCE for all (b, t):
-        # the two bases (4 batched SpMMs instead of 4 per step) and, after the loop, the weight-gradient contractions
-        S1_all = torch.cat(_basis_raw(plan, torch.cat([X, Hp_all], dim=-1).reshape(B * T, N, C), K), dim=-1)
-        S2_all = torch.cat(_basis_raw(plan, torch.cat([X, Hp_all * R], dim=-1).reshape(B * T, N, C), K), dim=-1)
-        dph_all = torch.empty(B, T, N, Co, device=X.device, dtype=X.dtype)
-        dpzr_all = torch.empty(B, T, N, 2 * Co, device=X.device, dtype=X.dtype)
-        dX = torch.zeros_like(X) if ctx.needs_input_grad[0] else None
-        one_m_z, dt = 1 - Z, 1 - Ht * Ht
-        gz_fac, gr_fac = Z * one_m_z, Hp_all * R * (1 - R)
-        dH = gout.new_zeros(B, N, Co)
+        nb = 2 * K - 1
+        f32 = dict(device=X.device, dtype=torch.float32)
+        Whs = _stack_weight(wh)
+        Wzr = torch.cat([_stack_weight(wz), _stack_weight(wr)], dim=1)
         WhsT, WzrT = Whs.t().contiguous(), Wzr.t().contiguous()
+        gout = gout.contiguous()
+        Z, R, Ht = stash[:, :, 0], stash[:, :, 1], stash[:, :, 2]                          # (B,T,N,Co) strided views
+        # ---- hoisted: H_{t-1} for every t (time-major so that [t] is a dense (B,N,Co) block) and both bases ------------
+        Hp = torch.empty(T, B, N, Co, **f32)
+        if H0 is not None:
+            Hp[0] = H0
+        else:
+            Hp[0].zero_()
+        if T > 1:
+            Hp[1:] = out[:, :-1].transpose(0, 1)
+        S1 = torch.empty(T * B, N, nb * C, **f32)                                          # basis of [X | H_{t-1}]
+        S2 = torch.empty(T * B, N, nb * C, **f32)                                          # basis of [X | H_{t-1} * R]
+        Xt = X.transpose(0, 1).reshape(T * B, N, Ci)
+        S1[..., :Ci] = Xt
+        S2[..., :Ci] = Xt
+        S1[..., Ci:C] = Hp.view(T * B, N, Co)
+        torch.mul(Hp, R.transpose(0, 1), out=S2.view(T, B, N, nb * C)[..., Ci:C])
+        for S in (S1, S2):
+            for k in range(1, K):
+                for o in (0, 1):
+                    dst = (1 + 2 * (k - 1) + o) * C
+                    if k == 1:
+                        ops.spmm_cols(plan, o, S, 0, dst, C)
+                    else:
+                        ops.spmm_cols(plan, o, S, dst - 2 * C, dst, C, alpha=2.0, z_col=0, beta=-1.0)
+        # ---- the recurrence ---------------------------------------------------------------------------------------------
+        dph_all = torch.empty(T, B, N, Co, **f32)
+        dpzr_all = torch.empty(T, B, N, 2 * Co, **f32)
+        buf2 = torch.empty(B, N, nb * C, **f32)                                            # dL/dS2 -> (in place) dL/d[X | H*R]
+        buf1 = torch.empty(B, N, nb * C, **f32)                                            # dL/dS1 -> (in place) dL/d[X | H_{t-1}]
+        g = torch.empty(B, N, Co, **f32)
+        dX = torch.empty_like(X) if ctx.needs_input_grad[0] else None
+
+        def adjoint_inplace(buf):
+            """columns [0,C) of buf <- adjoint of U -> [U | P_o U | P_i U | 2 P_o T_1o - U | ..] applied to buf."""
+            for k in range(K - 1, 1, -1):                                                  # T_k = 2 P T_{k-1} - U
+                for o in (0, 1):
+                    src = (1 + 2 * (k - 1) + o) * C
+                    ops.spmm_cols(plan, o, buf, src, src - 2 * C, C, alpha=2.0, z_col=src - 2 * C, beta=1.0, transposed=True)
+                    buf[..., :C].sub_(buf[..., src:src + C])
+            if K > 1:                                                                      # T_1 = P U
+                ops.spmm_cols(plan, 0, buf, C, 0, C, z_col=0, beta=1.0, transposed=True)
+                ops.spmm_cols(plan, 1, buf, 2 * C, 0, C, z_col=0, beta=1.0, transposed=True)
+
         for t in range(T - 1, -1, -1):
-            g = gout[:, t] + dH
-            dph = g * one_m_z[:, t] * dt[:, t]
-            dph_all[:, t] = dph
-            dU2 = _basis_adjoint(plan, torch.matmul(dph, WhsT), C, K)
-            dHR = dU2[..., Ci:]
-            dpzr = torch.cat([g * (Hp_all[:, t] - Ht[:, t]) * gz_fac[:, t], dHR * gr_fac[:, t]], dim=-1)
-            dpzr_all[:, t] = dpzr
-            dU1 = _basis_adjoint(plan, torch.matmul(dpzr, WzrT), C, K)
-            dH = g * Z[:, t] + dHR * R[:, t] + dU1[..., Ci:]
-            if dX is not None:
-                dX[:, t] = dU2[..., :Ci] + dU1[..., :Ci]
-        nbC = S1_all.size(-1)
-        dWh = torch.matmul(S2_all.reshape(-1, nbC).t(), dph_all.reshape(-1, Co))
-        dWzr = torch.matmul(S1_all.reshape(-1, nbC).t(), dpzr_all.reshape(-1, 2 * Co))
-        dbh = dph_all.sum(dim=(0, 1, 2))
-        dbzr = dpzr_all.sum(dim=(0, 1, 2))
+            if t == T - 1:
+                ops.gru_bwd_carry(Ci, Co, buf2, buf1, gout=gout[:, t], z=Z[:, t], ht=Ht[:, t], g=g, dph=dph_all[t])
+            else:
+                ops.gru_bwd_carry(Ci, Co, buf2, buf1, g_prev=g, z_prev=Z[:, t + 1], r_prev=R[:, t + 1],
+                                  dx=None if dX is None else dX[:, t + 1], gout=gout[:, t], z=Z[:, t], ht=Ht[:, t], g=g, dph=dph_all[t])
+            torch.matmul(dph_all[t].view(B * N, Co), WhsT, out=buf2.view(B * N, nb * C))
+            adjoint_inplace(buf2)
+            ops.gru_bwd_zr(Ci, Co, g, Hp[t], Z[:, t], R[:, t], Ht[:, t], buf2, dpzr_all[t])
+            torch.matmul(dpzr_all[t].view(B * N, 2 * Co), WzrT, out=buf1.view(B * N, nb * C))
+            adjoint_inplace(buf1)
+        dH0 = torch.empty(B, N, Co, **f32)
+        ops.gru_bwd_carry(Ci, Co, buf2, buf1, g_prev=g, z_prev=Z[:, 0], r_prev=R[:, 0], dx=None if dX is None else dX[:, 0], dh_out=dH0)
+        # ---- hoisted: weight / bias gradients over all (t, b, n) rows ---------------------------------------------------
+        dWh = torch.matmul(S2.view(-1, nb * C).t(), dph_all.view(-1, Co))
+        dWzr = torch.matmul(S1.view(-1, nb * C).t(), dpzr_all.view(-1, 2 * Co))
         gz = _unstack_weight_grad(dWzr[:, :Co], K, C)
         gr = _unstack_weight_grad(dWzr[:, Co:], K, C)
         gh = _unstack_weight_grad(dWh, K, C)
-        gb = (dbzr[:Co], dbzr[Co:], dbh) if ctx.has_bias else (None, None, None)
-        gH0 = dH if (ctx.has_h0 and ctx.needs_input_grad[1]) else None
+        if ctx.has_bias:
+            dbzr = dpzr_all.sum(dim=(0, 1, 2))
+            gb = (dbzr[:Co], dbzr[Co:], dph_all.sum(dim=(0, 1, 2)))
+        else:
+            gb = (None, None, None)
+        gH0 = dH0 if (ctx.has_h0 and ctx.needs_input_grad[1]) else None
         return dX, gH0, gz, gr, gh, gb[0], gb[1], gb[2], None, None, None
 
 

@@ -152,10 +152,12 @@ def gru_seq_fwd(plan: GraphPlan, n_ops: int, x: torch.Tensor, wcat: torch.Tensor
 
 
 def spmm_cols(plan: GraphPlan, op: int, buf: torch.Tensor, src_col: int, dst_col: int, width: int, alpha: float = 1.0,
-              z_col: Optional[int] = None, beta: float = 0.0):
+              z_col: Optional[int] = None, beta: float = 0.0, transposed: bool = False):
     """In-place column-block product inside one basis buffer `buf` (..., N, LD):
     buf[..., dst_col:dst_col+width] = alpha * A_op buf[..., src_col:+width] + beta * buf[..., z_col:+width].
-    Lets T_k be written straight into its slot of S = [T_0 | T_1 | ...] (no torch.cat of large tensors)."""
+    Lets T_k be written straight into its slot of S = [T_0 | T_1 | ...] (no torch.cat of large tensors); with
+    `transposed` (A_op^T) and z_col == dst_col it is the accumulate step of the basis adjoint.  src and dst blocks must
+    not overlap; z may alias dst exactly (each output element reads its own z before it is written)."""
     _require_cuda(buf, "buf")
     b3 = buf if buf.dim() == 3 else buf.unsqueeze(0)
     B, N, LD = b3.shape
@@ -164,7 +166,7 @@ def spmm_cols(plan: GraphPlan, op: int, buf: torch.Tensor, src_col: int, dst_col
     base, es = b3.data_ptr(), 4
     pz = None if z_col is None else ctypes.c_void_p(base + z_col * es)
     with torch.cuda.device(buf.device):
-        rc = _lib.lib().stmp_spmm(plan.handle, op, 0, B, width, ctypes.c_void_p(base + src_col * es), LD, N * LD,
+        rc = _lib.lib().stmp_spmm(plan.handle, op, 1 if transposed else 0, B, width, ctypes.c_void_p(base + src_col * es), LD, N * LD,
                                   ctypes.c_void_p(base + dst_col * es), LD, N * LD, alpha, pz, LD, N * LD, beta, None,
                                   _lib.stream_ptr())
     _lib.check(rc)
@@ -259,6 +261,46 @@ def gru_out(ph, z, h):
         _lib.check(_lib.lib().stmp_gru_out(ph.numel(), _lib.ptr(ph), _lib.ptr(z), _lib.ptr(h), None, _lib.ptr(hn),
                                            _lib.stream_ptr()))
     return hn
+
+
+def _slice_ptr(t: Optional[torch.Tensor]):
+    """(pointer, batch stride in elements) of a (B, N, C) fp32 slice whose trailing two dims are dense."""
+    if t is None:
+        return None, 0
+    if t.dtype != torch.float32 or t.dim() != 3 or t.stride(2) != 1 or t.stride(1) != t.size(2):
+        raise RuntimeError("expected a float32 (B, N, C) slice with dense trailing dims")
+    return ctypes.c_void_p(t.data_ptr()), t.stride(0)
+
+
+def gru_bwd_carry(cin: int, cout: int, du2, du1, g_prev=None, z_prev=None, r_prev=None, dx=None, gout=None, z=None, ht=None,
+                  g=None, dph=None, dh_out=None):
+    """stmp_gru_bwd_carry: close step t+1 (g_prev, z_prev, r_prev, du2, du1 [, dx]) and/or open step t (gout, z, ht -> g, dph)."""
+    ref = g_prev if g_prev is not None else gout
+    B, N = ref.size(0), ref.size(1)
+    du_ld = du2.size(-1)
+    zp, s1 = _slice_ptr(z_prev)
+    rp, _ = _slice_ptr(r_prev)
+    zz, s2 = _slice_ptr(z)
+    hh, _ = _slice_ptr(ht)
+    go, gs = _slice_ptr(gout)
+    dxp, dxs = _slice_ptr(dx)
+    stash_bs = s1 if z_prev is not None else s2
+    if z_prev is not None and z is not None and s1 != s2:
+        raise RuntimeError("stash slices of one call must share their batch stride")
+    with torch.cuda.device(ref.device):
+        _lib.check(_lib.lib().stmp_gru_bwd_carry(B, N, cin, cout, du_ld, _lib.ptr(g_prev), zp, rp, _lib.ptr(du2), _lib.ptr(du1), dxp, dxs,
+                                                 go, gs, zz, hh, stash_bs, _lib.ptr(g), _lib.ptr(dph), _lib.ptr(dh_out), _lib.stream_ptr()))
+
+
+def gru_bwd_zr(cin: int, cout: int, g, hprev, z, r, ht, du2, dpzr):
+    B, N = g.size(0), g.size(1)
+    hp, hs = _slice_ptr(hprev)
+    zz, ss = _slice_ptr(z)
+    rr, _ = _slice_ptr(r)
+    hh, _ = _slice_ptr(ht)
+    with torch.cuda.device(g.device):
+        _lib.check(_lib.lib().stmp_gru_bwd_zr(B, N, cin, cout, du2.size(-1), _lib.ptr(g), hp, hs, zz, rr, hh, ss, _lib.ptr(du2),
+                                              _lib.ptr(dpzr), _lib.stream_ptr()))
 
 
 def lstm_ifc(pi, pf, pc, c, wci, wcf, bi, bf, bc):
