@@ -262,7 +262,7 @@ def train_probe(dev, world, rank, ei_d, ew_d, series, steps=5, windows=64):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item()) / steps
     return {"value": world * windows / (ms * 1e-3), "unit": "snapshots/s", "ms_per_step": ms, "windows_per_step_per_gpu": windows,
-            "path": "fused fwd (stmp_dcrnn_seq_fwd + stash) + hand-written reverse-time bwd (stmp_spmm + cuBLAS) + flat all-reduce + Adam", "launch": mode, "allreduce_bytes_per_step": sync.nbytes if world > 1 else 0,
+            "path": "fused fwd (stmp_dcrnn_seq_fwd + stash) + hand-written reverse-time bwd (8 launches/step: stmp_gru_bwd_* + cuBLAS + in-place transposed stmp_spmm) + flat all-reduce + Adam", "launch": mode, "allreduce_bytes_per_step": sync.nbytes if world > 1 else 0,
             "loss": float(loss.detach())}
 
 

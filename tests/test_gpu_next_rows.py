@@ -99,9 +99,12 @@ def test_stconv_goldens(golden_dir):
         out = m(Xg, ei, ew)                                     # training-mode BatchNorm: batch statistics
         _close(out, c["out_train"])
         _loss([out]).backward()
-        # BatchNorm divides by a batch std: gradients carry its conditioning, same bar as ASTGCN end-to-end
-        _check_grads(m, c["grads"], 2e-3, 2e-5)
-        _close(Xg.grad, c["gX"], 2e-3, 2e-5)
+        # training-mode BatchNorm backward is g - mean(g) - x^ mean(g x^): cancellation turns fp32 summation-order
+        # differences (GPU vs CPU reductions) into absolute errors that scale with the LARGEST gradient entry, so the
+        # bar is relative to the tensor's max: |err| <= 2e-4 * max|want|
+        for k, p in m.named_parameters():
+            _close(p.grad, c["grads"][k], 0.0, 2e-4 * float(c["grads"][k].abs().max()) + 1e-6)
+        _close(Xg.grad, c["gX"], 0.0, 2e-4 * float(c["gX"].abs().max()) + 1e-6)
 
 
 def test_stconv_batched_equals_per_slice_chebconv():
