@@ -169,6 +169,24 @@ int stmp_lstm_ifc(int64_t rows, int64_t cout, const float* pi, const float* pf, 
 int stmp_lstm_oh(int64_t rows, int64_t cout, const float* po, const float* cnew, const float* wco,
                  const float* bo, float* o, float* hnew, void* stream);
 
+/* ---- backward of the fused DCRNN sequence (what autograd replays for dcrnn.py:429-475 / :172-219), small graphs ----
+ * Served when stmp_dcrnn_bwd_supported(plan, cin, cout, K) != 0 (DCONV plan, K = 2, cout = 32, cin <= 4, graph + tiles
+ * fit one SM's shared memory: N <= ~235); otherwise callers use the per-step path (stmp_gru_bwd_* + stmp_spmm).
+ *   stmp_dcrnn_bwd_basis: for every (t, b) rebuild S1[t*B+b] = [U | P_o U | P_i U], U = [X_t | H_{t-1}] and S2 with
+ *                         U = [X_t | H_{t-1} * R_t] (row pitch ld >= 3(cin+cout)) from x, the forward output `out`
+ *                         (B,T,N,cout), h0 (nullable) and the gate stash (B,T,3,N,cout).  One launch.
+ *   stmp_dcrnn_bwd_seq:   the reverse-time recurrence, one CTA per window: consumes gout (B,T,N,cout), whsT (cout, 3C),
+ *                         wzrT (2cout, 3C) [transposed stacked weights]; writes d pre-activations dph_all (T,B,N,cout),
+ *                         dpzr_all (T,B,N,2cout) for the weight-gradient GEMMs, dx (B,T,N,cin; nullable), dh0 (B,N,cout).
+ */
+int stmp_dcrnn_bwd_supported(const stmp_plan* plan, int64_t cin, int64_t cout, int64_t K);
+int stmp_dcrnn_bwd_basis(const stmp_plan* plan, int64_t B, int64_t T, int64_t cin, int64_t cout, const float* x,
+                         int64_t x_bstride, int64_t x_tstride, const float* out, const float* h0, const float* stash,
+                         float* S1, float* S2, int64_t ld, void* stream);
+int stmp_dcrnn_bwd_seq(const stmp_plan* plan, int64_t B, int64_t T, int64_t cin, int64_t cout, const float* gout,
+                       const float* out, const float* h0, const float* stash, const float* whsT, const float* wzrT,
+                       float* dph_all, float* dpzr_all, float* dx, float* dh0, void* stream);
+
 /* GRU reverse-time gate derivatives: the pointwise part of the hand-written backward of the DCRNN sequence (what
  * autograd records for dcrnn.py:172-192, once per step).  Tensors are (B, N, cout) with a batch stride in elements
  * (slices of gout (B,T,N,cout) and of the forward stash (B,T,3,N,cout)); du2/du1 are (B, N, du_ld) buffers whose

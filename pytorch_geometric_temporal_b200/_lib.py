@@ -46,6 +46,9 @@ _SIGNATURES = {
     "stmp_gru_seq_supported": (c_int, [_P, c_int, c_int64, c_int64]),
     "stmp_gru_zr": (c_int, [c_int64, _P, _P, _P, _P, _P, _P, _P]),
     "stmp_gru_out": (c_int, [c_int64, _P, _P, _P, _P, _P, _P]),
+    "stmp_dcrnn_bwd_supported": (c_int, [_P, c_int64, c_int64, c_int64]),
+    "stmp_dcrnn_bwd_basis": (c_int, [_P] + [c_int64] * 4 + [_P, c_int64, c_int64, _P, _P, _P, _P, _P, c_int64, _P]),
+    "stmp_dcrnn_bwd_seq": (c_int, [_P] + [c_int64] * 4 + [_P] * 11),
     "stmp_gru_bwd_carry": (c_int, [c_int64] * 5 + [_P, _P, _P, _P, _P, _P, c_int64, _P, c_int64, _P, _P, c_int64, _P, _P, _P, _P]),
     "stmp_gru_bwd_zr": (c_int, [c_int64] * 5 + [_P, _P, c_int64, _P, _P, _P, c_int64, _P, _P, _P]),
     "stmp_lstm_ifc": (c_int, [c_int64, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),

@@ -85,6 +85,8 @@ class _DcrnnSeqFn(torch.autograd.Function):
     hand-written reverse-time loop over the stash (transposed SpMM for the diffusion adjoints, cuBLAS for the
     contractions).  Replaces autograd's replay of the ~1500-launch tiled graph."""
 
+    fused_backward = True    # False forces the per-step backward even where the persistent kernel is available (tests)
+
     @staticmethod
     def forward(ctx, X, H0, wz, wr, wh, bz, br, bh, plan, K, wimage):
         out, stash = ops.dcrnn_seq_fwd(plan, X, wz, wr, wh, bz, br, bh, K, h0=H0, stash=True, wimage=wimage)
@@ -109,6 +111,18 @@ class _DcrnnSeqFn(torch.autograd.Function):
         Wzr = torch.cat([_stack_weight(wz), _stack_weight(wr)], dim=1)
         WhsT, WzrT = Whs.t().contiguous(), Wzr.t().contiguous()
         gout = gout.contiguous()
+        if _DcrnnSeqFn.fused_backward and ops.dcrnn_bwd_supported(plan, Ci, Co, K):
+            # small graph: the whole reverse recurrence is ONE persistent launch (dL/dH stays in shared memory), the bases
+            # of all steps are one more, and the weight gradients are chunked GEMMs over all (t, b, n) rows
+            S1 = torch.empty(T * B, N, nb * C, **f32)
+            S2 = torch.empty(T * B, N, nb * C, **f32)
+            ops.dcrnn_bwd_basis(plan, X, out, H0, stash, S1, S2)
+            dph_all = torch.empty(T, B, N, Co, **f32)
+            dpzr_all = torch.empty(T, B, N, 2 * Co, **f32)
+            dX = torch.empty_like(X) if ctx.needs_input_grad[0] else None
+            dH0 = torch.empty(B, N, Co, **f32)
+            ops.dcrnn_bwd_seq(plan, Ci, gout, out, H0, stash, WhsT, WzrT, dph_all, dpzr_all, dX, dH0)
+            return _DcrnnSeqFn._finish(ctx, S1, S2, dph_all, dpzr_all, dX, dH0, K, C, Co)
         Z, R, Ht = stash[:, :, 0], stash[:, :, 1], stash[:, :, 2]                          # (B,T,N,Co) strided views
         # ---- hoisted: H_{t-1} for every t (time-major so that [t] is a dense (B,N,Co) block) and both bases ------------
         Hp = torch.empty(T, B, N, Co, **f32)
@@ -165,15 +179,29 @@ class _DcrnnSeqFn(torch.autograd.Function):
             adjoint_inplace(buf1)
         dH0 = torch.empty(B, N, Co, **f32)
         ops.gru_bwd_carry(Ci, Co, buf2, buf1, g_prev=g, z_prev=Z[:, 0], r_prev=R[:, 0], dx=None if dX is None else dX[:, 0], dh_out=dH0)
-        # ---- hoisted: weight / bias gradients over all (t, b, n) rows ---------------------------------------------------
-        dWh = torch.matmul(S2.view(-1, nb * C).t(), dph_all.view(-1, Co))
-        dWzr = torch.matmul(S1.view(-1, nb * C).t(), dpzr_all.view(-1, 2 * Co))
+        return _DcrnnSeqFn._finish(ctx, S1, S2, dph_all, dpzr_all, dX, dH0, K, C, Co)
+
+    @staticmethod
+    def _finish(ctx, S1, S2, dph_all, dpzr_all, dX, dH0, K, C, Co):
+        """weight / bias gradients over all (t, b, n) rows.  A single (3C x rows) @ (rows x Co) GEMM has only a handful of
+        output tiles (cuBLAS runs it on 2 CTAs); chunking the row axis gives every SM a partial product to reduce."""
+        rows, nbC = S1.size(0) * S1.size(1), S1.size(-1)
+        chunks = 1
+        for c in (128, 96, 64, 48, 32, 16, 8, 4, 2):
+            if rows % c == 0:
+                chunks = c
+                break
+        per = rows // chunks
+        dWh = torch.bmm(S2.view(chunks, per, nbC).transpose(1, 2), dph_all.view(chunks, per, Co)).sum(0)
+        dWzr = torch.bmm(S1.view(chunks, per, nbC).transpose(1, 2), dpzr_all.view(chunks, per, 2 * Co)).sum(0)
         gz = _unstack_weight_grad(dWzr[:, :Co], K, C)
         gr = _unstack_weight_grad(dWzr[:, Co:], K, C)
         gh = _unstack_weight_grad(dWh, K, C)
         if ctx.has_bias:
-            dbzr = dpzr_all.sum(dim=(0, 1, 2))
-            gb = (dbzr[:Co], dbzr[Co:], dph_all.sum(dim=(0, 1, 2)))
+            ones = S1.new_ones(chunks, 1, per)
+            dbzr = torch.bmm(ones, dpzr_all.view(chunks, per, 2 * Co)).sum(dim=(0, 1))
+            dbh = torch.bmm(ones, dph_all.view(chunks, per, Co)).sum(dim=(0, 1))
+            gb = (dbzr[:Co], dbzr[Co:], dbh)
         else:
             gb = (None, None, None)
         gH0 = dH0 if (ctx.has_h0 and ctx.needs_input_grad[1]) else None

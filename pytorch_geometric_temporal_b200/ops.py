@@ -263,6 +263,31 @@ def gru_out(ph, z, h):
     return hn
 
 
+def dcrnn_bwd_supported(plan: GraphPlan, cin: int, cout: int, K: int) -> bool:
+    return bool(_lib.lib().stmp_dcrnn_bwd_supported(plan.handle, cin, cout, K))
+
+
+def dcrnn_bwd_basis(plan: GraphPlan, x, out, h0, stash, S1, S2):
+    """S1/S2 (T*B, N, ld) <- bases of [X_t | H_{t-1}] and [X_t | H_{t-1}*R_t] for every (t, b): one launch."""
+    x, out, stash = _f32c(x, "x"), _f32c(out, "out"), _f32c(stash, "stash")
+    B, T, N, Ci = x.shape
+    h0 = None if h0 is None else _f32c(h0, "h0")
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().stmp_dcrnn_bwd_basis(plan.handle, B, T, Ci, out.size(-1), _lib.ptr(x), T * N * Ci, N * Ci, _lib.ptr(out),
+                                                   _lib.ptr(h0), _lib.ptr(stash), _lib.ptr(S1), _lib.ptr(S2), S1.size(-1), _lib.stream_ptr()))
+
+
+def dcrnn_bwd_seq(plan: GraphPlan, cin: int, gout, out, h0, stash, whsT, wzrT, dph_all, dpzr_all, dx, dh0):
+    """The reverse-time recurrence of the DCRNN backward in one persistent launch (one CTA per window)."""
+    gout, out, stash = _f32c(gout, "gout"), _f32c(out, "out"), _f32c(stash, "stash")
+    B, T, N, Co = gout.shape
+    h0 = None if h0 is None else _f32c(h0, "h0")
+    with torch.cuda.device(gout.device):
+        _lib.check(_lib.lib().stmp_dcrnn_bwd_seq(plan.handle, B, T, cin, Co, _lib.ptr(gout), _lib.ptr(out), _lib.ptr(h0), _lib.ptr(stash),
+                                                 _lib.ptr(_f32c(whsT, "whsT")), _lib.ptr(_f32c(wzrT, "wzrT")), _lib.ptr(dph_all),
+                                                 _lib.ptr(dpzr_all), _lib.ptr(dx), _lib.ptr(dh0), _lib.stream_ptr()))
+
+
 def _slice_ptr(t: Optional[torch.Tensor]):
     """(pointer, batch stride in elements) of a (B, N, C) fp32 slice whose trailing two dims are dense."""
     if t is None:

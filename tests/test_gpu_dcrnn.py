@@ -214,3 +214,70 @@ def test_training_path_fused_forward_manual_backward_matches_autograd():
     _close(Xa.grad, Xb.grad.cpu(), 1e-3, 1e-5)
     for (k, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
         _close(pa.grad, pb.grad.cpu(), 1e-3, 2e-4)
+
+
+@pytest.mark.parametrize("fused_bwd", [True, False])
+def test_training_backward_variants_cfg2(fused_bwd):
+    """cfg2 shape, with an initial state and a window batch that is not a multiple of anything: the persistent backward
+    kernel (stmp_dcrnn_bwd_basis + stmp_dcrnn_bwd_seq) and the per-step backward (stmp_gru_bwd_* + in-place transposed
+    SpMM) must both reproduce autograd through the tiled path."""
+    from pytorch_geometric_temporal_b200.nn.recurrent.dcrnn import _DcrnnSeqFn
+    from pytorch_geometric_temporal_b200.nn.recurrent import DCRNN
+    ei, ew, series = synthetic.metr_la_like(3, 64)
+    ei_t, ew_t = torch.from_numpy(ei).to(DEV), torch.from_numpy(ew).to(DEV)
+    X = torch.from_numpy(series[:35]).reshape(5, 7, 207, 2).to(DEV)
+    torch.manual_seed(1)
+    a = BatchedDCRNN(2, 32, 2).to(DEV)
+    b = BatchedDCRNN(2, 32, 2).to(DEV)
+    b.load_state_dict(a.state_dict())
+    b._fused_training = False
+    w = torch.randn(5, 7, 207, 32, device=DEV)
+    Xa, Xb = X.clone().requires_grad_(True), X.clone().requires_grad_(True)
+    _DcrnnSeqFn.fused_backward = fused_bwd
+    try:
+        n0 = _lib.launch_count()
+        oa = a(Xa, ei_t, ew_t)
+        (oa * w).sum().backward()
+        launches = _lib.launch_count() - n0
+    finally:
+        _DcrnnSeqFn.fused_backward = True
+    (b(Xb, ei_t, ew_t) * w).sum().backward()
+    if fused_bwd:
+        assert launches <= 3 + 60                   # forward + basis + recurrence (+ one-time plan build)
+    _close(Xa.grad, Xb.grad.cpu(), 1e-3, 1e-5)
+    for (k, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
+        _close(pa.grad, pb.grad.cpu(), 1e-3, 2e-4)
+    # single cell with an incoming state: gradient w.r.t. H flows through dh0
+    c, d = DCRNN(2, 32, 2).to(DEV), DCRNN(2, 32, 2).to(DEV)
+    d.load_state_dict(c.state_dict())
+    d._fused_training = False
+    x1 = torch.randn(207, 2, device=DEV)
+    hc, hd = (torch.randn(207, 32, device=DEV) * 0.5).requires_grad_(True), None
+    hd = hc.detach().clone().requires_grad_(True)
+    _DcrnnSeqFn.fused_backward = fused_bwd
+    try:
+        (c(x1, ei_t, ew_t, hc) * w[0, 0]).sum().backward()
+    finally:
+        _DcrnnSeqFn.fused_backward = True
+    (d(x1, ei_t, ew_t, hd) * w[0, 0]).sum().backward()
+    _close(hc.grad, hd.grad.cpu(), 1e-3, 1e-5)
+    for (k, pa), (_, pb) in zip(c.named_parameters(), d.named_parameters()):
+        _close(pa.grad, pb.grad.cpu(), 1e-3, 1e-4)
+
+
+def test_training_backward_general_K_small_graph():
+    """K=3 / 16 hidden on a 40-node graph: fused FFMA forward with stash + the per-step backward (general K)."""
+    import os
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "dcrnn_small_batched_K3.pt"), weights_only=False)
+    ei, ew = g["edge_index"].to(DEV), g["edge_weight"].to(DEV)
+    a, b = BatchedDCRNN(3, 16, 3).to(DEV), BatchedDCRNN(3, 16, 3).to(DEV)
+    a.load_state_dict(g["state"]); b.load_state_dict(g["state"])
+    b._fused_training = False
+    Xa, Xb = g["X"].to(DEV).requires_grad_(True), g["X"].to(DEV).requires_grad_(True)
+    oa, ob = a(Xa, ei, ew), b(Xb, ei, ew)
+    _close(oa, g["out"]); _close(ob, g["out"])
+    w = torch.randn_like(oa)
+    (oa * w).sum().backward(); (ob * w).sum().backward()
+    _close(Xa.grad, Xb.grad.cpu(), 1e-3, 1e-5)
+    for (k, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
+        _close(pa.grad, pb.grad.cpu(), 1e-3, 1e-4)
