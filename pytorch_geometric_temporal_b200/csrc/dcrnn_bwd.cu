@@ -22,60 +22,110 @@ namespace stmp {
 namespace {
 
 constexpr int kCo = 32;          // hidden size served by these kernels
-constexpr int kDpPitch = 2 * kCo + 1;   // odd pitch: lane = row reads of dp[row][k] are conflict-free
+constexpr int kBwdThreads = 512;
+constexpr int kBatch = 4;        // vector slots per thread whose global operands are fetched together (latency paid once)
+
+__host__ __device__ constexpr int ncol_of(int cin) { return (3 * (cin + kCo) + 7) / 8 * 8; }
+
+// ---- 1- or 2-float vector access (rows have C = cin + 32 channels; C even -> float2 slots halve the instruction count)
+template <int V> __device__ __forceinline__ void ldv(const float* p, float (&v)[V]);
+template <> __device__ __forceinline__ void ldv<1>(const float* p, float (&v)[1]) { v[0] = *p; }
+template <> __device__ __forceinline__ void ldv<2>(const float* p, float (&v)[2]) { const float2 t = *reinterpret_cast<const float2*>(p); v[0] = t.x; v[1] = t.y; }
+template <int V> __device__ __forceinline__ void ldgv(const float* p, float (&v)[V]);
+template <> __device__ __forceinline__ void ldgv<1>(const float* p, float (&v)[1]) { v[0] = __ldg(p); }
+template <> __device__ __forceinline__ void ldgv<2>(const float* p, float (&v)[2]) { const float2 t = __ldg(reinterpret_cast<const float2*>(p)); v[0] = t.x; v[1] = t.y; }
+template <int V> __device__ __forceinline__ void stv(float* p, const float (&v)[V]);
+template <> __device__ __forceinline__ void stv<1>(float* p, const float (&v)[1]) { *p = v[0]; }
+template <> __device__ __forceinline__ void stv<2>(float* p, const float (&v)[2]) { *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]); }
+
+// ---- one sparse operator, read from global memory (L1-cached) or from a compressed shared-memory copy
+template <bool SG> struct Gr;
+template <> struct Gr<false> {
+  const int* rp; const int2* cv;
+  __device__ __forceinline__ int begin(int n) const { return __ldg(rp + n); }
+  __device__ __forceinline__ int end(int n) const { return __ldg(rp + n + 1); }
+  __device__ __forceinline__ void edge(int k, int& col, float& w) const { const int2 e = __ldg(cv + k); col = e.x; w = __int_as_float(e.y); }
+};
+template <> struct Gr<true> {          // N <= 256: column in one byte; row pointers in 16 bits
+  const unsigned short* rp; const float* val; const unsigned char* col;
+  __device__ __forceinline__ int begin(int n) const { return rp[n]; }
+  __device__ __forceinline__ int end(int n) const { return rp[n + 1]; }
+  __device__ __forceinline__ void edge(int k, int& c, float& w) const { c = col[k]; w = val[k]; }
+};
 
 // ------------------------------------------------------------------------------------------------------------------
 struct BasisParams {
   const int* rp[2]; const int2* cv[2];      // forward CSRs (by destination): y[i] = sum_k val_k x[col_k]
-  int N, Ci, B, T, ld;
-  const float* x; long long x_bs, x_ts;     // X[b,t] = x + b*x_bs + t*x_ts, (N, Ci) dense
+  int N, B, T, ld;
+  const float* x; long long x_bs, x_ts;     // X[b,t] = x + b*x_bs + t*x_ts, (N, cin) dense
   const float* out; const float* h0; const float* stash;
-  float* S1; float* S2;                     // (T*B, N, ld), ld >= 3*(Ci+Co)
+  float* S1; float* S2;                     // (T*B, N, ld), ld >= 3*(cin+Co)
 };
 
+template <int CIN>
 __global__ void __launch_bounds__(256) k_dcrnn_bwd_basis(BasisParams p) {
-  extern __shared__ float sm[];
-  const int N = p.N, Ci = p.Ci, C = p.Ci + kCo;
+  constexpr int C = CIN + kCo, V = (C % 2 == 0) ? 2 : 1, CP = C / V;
+  extern __shared__ __align__(16) float sm[];
+  const int N = p.N, NP = N * CP;
   float* U1 = sm;
   float* U2 = sm + N * C;
   const int q = blockIdx.x, t = q / p.B, b = q - t * p.B;
   const long long bt = (long long)b * p.T + t;
   float* s1 = p.S1 + (long long)q * N * p.ld;
   float* s2 = p.S2 + (long long)q * N * p.ld;
-  for (int idx = threadIdx.x; idx < N * C; idx += blockDim.x) {
-    const int n = idx / C, c = idx - n * C;
-    float v1, v2;
-    if (c < Ci) {
-      v1 = v2 = __ldg(p.x + b * p.x_bs + t * p.x_ts + n * Ci + c);
-    } else {
-      const int cc = c - Ci;
-      float h = 0.f;
-      if (t > 0) h = __ldg(p.out + ((bt - 1) * N + n) * kCo + cc);
-      else if (p.h0) h = __ldg(p.h0 + ((long long)b * N + n) * kCo + cc);
-      const float r = __ldg(p.stash + ((bt * 3 + 1) * N + n) * kCo + cc);
-      v1 = h; v2 = h * r;
+  const float* hsrc = t > 0 ? p.out + (bt - 1) * N * kCo : (p.h0 ? p.h0 + (long long)b * N * kCo : nullptr);
+  const float* rsrc = p.stash + (bt * 3 + 1) * N * kCo;
+  const float* xsrc = p.x + b * p.x_bs + t * p.x_ts;
+#pragma unroll 1
+  for (int base = threadIdx.x; base < NP; base += kBatch * 256) {
+    float h[kBatch][V], r[kBatch][V];
+#pragma unroll
+    for (int j = 0; j < kBatch; ++j) {
+      const int s = base + j * 256, n = s / CP, c0 = (s - n * CP) * V;
+#pragma unroll
+      for (int e = 0; e < V; ++e) { h[j][e] = 0.f; r[j][e] = 1.f; }
+      if (s < NP) {
+        if (c0 < CIN) ldgv<V>(xsrc + n * CIN + c0, h[j]);
+        else {
+          if (hsrc) ldgv<V>(hsrc + n * kCo + c0 - CIN, h[j]);
+          ldgv<V>(rsrc + n * kCo + c0 - CIN, r[j]);
+        }
+      }
     }
-    U1[idx] = v1; U2[idx] = v2;
-    s1[(long long)n * p.ld + c] = v1;
-    s2[(long long)n * p.ld + c] = v2;
+#pragma unroll
+    for (int j = 0; j < kBatch; ++j) {
+      const int s = base + j * 256;
+      if (s < NP) {
+        const int n = s / CP, c0 = (s - n * CP) * V;
+        float v2[V];
+#pragma unroll
+        for (int e = 0; e < V; ++e) v2[e] = c0 < CIN ? h[j][e] : h[j][e] * r[j][e];
+        stv<V>(U1 + n * C + c0, h[j]); stv<V>(U2 + n * C + c0, v2);
+        stv<V>(s1 + (long long)n * p.ld + c0, h[j]); stv<V>(s2 + (long long)n * p.ld + c0, v2);
+      }
+    }
   }
   __syncthreads();
 #pragma unroll
   for (int op = 0; op < 2; ++op) {
-    const int* rp = p.rp[op];
-    const int2* cv = p.cv[op];
-    for (int idx = threadIdx.x; idx < N * C; idx += blockDim.x) {
-      const int n = idx / C, c = idx - n * C;
-      float a1 = 0.f, a2 = 0.f;
-      const int k1 = __ldg(rp + n + 1);
-      for (int k = __ldg(rp + n); k < k1; ++k) {     // same multiply / add order as k_spmm (bit-identical basis)
-        const int2 e = __ldg(cv + k);
-        const float w = __int_as_float(e.y);
-        a1 = __fadd_rn(a1, __fmul_rn(w, U1[e.x * C + c]));
-        a2 = __fadd_rn(a2, __fmul_rn(w, U2[e.x * C + c]));
+    const Gr<false> g{p.rp[op], p.cv[op]};
+    for (int s = threadIdx.x; s < NP; s += 256) {
+      const int n = s / CP, c0 = (s - n * CP) * V;
+      float a1[V], a2[V];
+#pragma unroll
+      for (int e = 0; e < V; ++e) a1[e] = a2[e] = 0.f;
+      const int k1 = g.end(n);
+#pragma unroll 4
+      for (int k = g.begin(n); k < k1; ++k) {        // same multiply / add order as k_spmm (bit-identical basis)
+        int col; float w;
+        g.edge(k, col, w);
+        float u1[V], u2[V];
+        ldv<V>(U1 + col * C + c0, u1); ldv<V>(U2 + col * C + c0, u2);
+#pragma unroll
+        for (int e = 0; e < V; ++e) { a1[e] = __fadd_rn(a1[e], __fmul_rn(w, u1[e])); a2[e] = __fadd_rn(a2[e], __fmul_rn(w, u2[e])); }
       }
-      s1[(long long)n * p.ld + (1 + op) * C + c] = a1;
-      s2[(long long)n * p.ld + (1 + op) * C + c] = a2;
+      stv<V>(s1 + (long long)n * p.ld + (1 + op) * C + c0, a1);
+      stv<V>(s2 + (long long)n * p.ld + (1 + op) * C + c0, a2);
     }
   }
 }
@@ -83,142 +133,226 @@ __global__ void __launch_bounds__(256) k_dcrnn_bwd_basis(BasisParams p) {
 // ------------------------------------------------------------------------------------------------------------------
 struct BwdParams {
   const int* rp[2]; const int2* cv[2];      // transposed CSRs (by source): (A^T y)[j] = sum over edges leaving j
-  int N, Ci, B, T;
+  int nnz[2];
+  int N, B, T;
   const float* gout; const float* out; const float* h0; const float* stash;
   const float* whsT; const float* wzrT;     // (Co, 3C) and (2Co, 3C), row-major
   float* dph_all; float* dpzr_all;          // (T,B,N,Co), (T,B,N,2Co)
-  float* dx;                                // (B,T,N,Ci) or null
+  float* dx;                                // (B,T,N,cin) or null
   float* dh0;                               // (B,N,Co)
 };
 
-// buf[row][half*HALF .. +HALF) = sum_k dp[row][k] * W[k][half*HALF ..]: one thread per (row, column half).
-template <int HALF, int KD>
-__device__ __forceinline__ void gemm_rows(const float* __restrict__ dp, const float* __restrict__ W, float* __restrict__ buf, int N) {
-  constexpr int NCOL = 2 * HALF;
+// buf[8rg..8rg+8)[8cg..8cg+8) = sum_k dpT[k][8rg..] (x) W[k][8cg..]: one thread per 8x8 output tile.  Per k a thread
+// issues 4 LDS.128 (2 for the 8 rows -- dp is kept TRANSPOSED, k-major, so they are contiguous -- and 2 for the 8 weight
+// columns) for 64 FFMA: the shared-memory pipe and the FMA pipe are balanced (a 1 x 52 tile was 4x LSU-bound).  Adjacent
+// lanes take adjacent column groups, so the tile stores of a warp spread over the banks.
+template <int NCOL, int KD>
+__device__ __forceinline__ void gemm_tiles(const float* __restrict__ dpT, int dpp, const float* __restrict__ W, float* __restrict__ buf,
+                                           int RG) {
+  constexpr int CGN = NCOL / 8;
   const int tid = threadIdx.x;
-  if (tid >= 2 * N) return;
-  const int half = tid >= N ? 1 : 0, row = tid - half * N;
-  float acc[HALF];
+  if (tid >= RG * CGN) return;
+  const int rg = tid / CGN, cg = tid - rg * CGN;
+  float acc[8][8];
 #pragma unroll
-  for (int j = 0; j < HALF; ++j) acc[j] = 0.f;
-  const float* a = dp + row * kDpPitch;
-  const float4* w = reinterpret_cast<const float4*>(W + half * HALF);
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  const float* ap = dpT + 8 * rg;
+  const float* wp = W + 8 * cg;
 #pragma unroll 2
   for (int k = 0; k < KD; ++k) {
-    const float av = a[k];
+    const float4 a0 = *reinterpret_cast<const float4*>(ap + k * dpp), a1 = *reinterpret_cast<const float4*>(ap + k * dpp + 4);
+    const float4 w0 = *reinterpret_cast<const float4*>(wp + k * NCOL), w1 = *reinterpret_cast<const float4*>(wp + k * NCOL + 4);
+    const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-    for (int j = 0; j < HALF / 4; ++j) {
-      const float4 w4 = w[k * (NCOL / 4) + j];        // same address across the warp: broadcast
-      acc[4 * j] = fmaf(av, w4.x, acc[4 * j]);
-      acc[4 * j + 1] = fmaf(av, w4.y, acc[4 * j + 1]);
-      acc[4 * j + 2] = fmaf(av, w4.z, acc[4 * j + 2]);
-      acc[4 * j + 3] = fmaf(av, w4.w, acc[4 * j + 3]);
-    }
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
   }
-  float4* o = reinterpret_cast<float4*>(buf + row * NCOL + half * HALF);
 #pragma unroll
-  for (int j = 0; j < HALF / 4; ++j) o[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+  for (int i = 0; i < 8; ++i) {
+    float4* o = reinterpret_cast<float4*>(buf + (8 * rg + i) * NCOL + 8 * cg);
+    o[0] = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    o[1] = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
+  }
 }
 
-// dU[n][c] = dS[n][c] + sum_op sum_{edges of row n of A_op^T} val * dS[col][(1+op)*C + c]   (adjoint of U -> [U|P_oU|P_iU])
-template <int NCOL>
-__device__ __forceinline__ float adjoint_at(const BwdParams& p, const float* __restrict__ buf, int n, int c, int C) {
-  float v = buf[n * NCOL + c];
+// dU[n][c..c+V) = dS[n][c..] + sum_op sum_{edges of row n of A_op^T} val * dS[col][(1+op)*C + c..]   (adjoint of U -> [U|P_oU|P_iU])
+template <int NCOL, int C, int V, bool SG>
+__device__ __forceinline__ void adjoint_at(const Gr<SG> (&g)[2], const float* __restrict__ buf, int n, int c, float (&v)[V]) {
+  ldv<V>(buf + n * NCOL + c, v);
 #pragma unroll
   for (int op = 0; op < 2; ++op) {
-    const int k1 = __ldg(p.rp[op] + n + 1);
+    const int k1 = g[op].end(n);
     const float* src = buf + (1 + op) * C + c;
-    for (int k = __ldg(p.rp[op] + n); k < k1; ++k) {
-      const int2 e = __ldg(p.cv[op] + k);
-      v = fmaf(__int_as_float(e.y), src[e.x * NCOL], v);
+#pragma unroll 4
+    for (int k = g[op].begin(n); k < k1; ++k) {
+      int col; float w;
+      g[op].edge(k, col, w);
+      float s[V];
+      ldv<V>(src + col * NCOL, s);
+#pragma unroll
+      for (int e = 0; e < V; ++e) v[e] = fmaf(w, s[e], v[e]);
     }
   }
-  return v;
 }
 
-template <int HALF>
-__global__ void __launch_bounds__(512, 1) k_dcrnn_bwd_seq(BwdParams p) {
-  constexpr int NCOL = 2 * HALF;
+template <int CIN, bool SG>
+__global__ void __launch_bounds__(kBwdThreads, 1) k_dcrnn_bwd_seq(BwdParams p) {
+  constexpr int C = CIN + kCo, NCOL = ncol_of(CIN), V = (C % 2 == 0) ? 2 : 1, CP = C / V;
   extern __shared__ __align__(16) float sm[];
-  const int N = p.N, Ci = p.Ci, C = p.Ci + kCo, T = p.T, b = blockIdx.x, tid = threadIdx.x;
+  const int N = p.N, T = p.T, b = blockIdx.x, tid = threadIdx.x;
+  const int RG = (N + 7) / 8, dpp = RG * 8 + 4, NP = N * CP, NH = N * kCo;
   float* Wh = sm;                            // [Co][NCOL]
   float* Wzr = Wh + kCo * NCOL;              // [2Co][NCOL]
-  float* buf = Wzr + 2 * kCo * NCOL;         // [N][NCOL]
-  float* dp = buf + N * NCOL;                // [N][kDpPitch]
-  float* G = dp + N * kDpPitch;              // [N][Co]   dL/dH_t (open) -> partial dL/dH_{t-1}
-  float* dXp = G + N * kCo;                  // [N][4]    dU2[:, :Ci] waiting for dU1
-  // ---- weights, zero padded to NCOL columns
-  for (int i = tid; i < 3 * kCo * NCOL; i += blockDim.x) {
+  float* buf = Wzr + 2 * kCo * NCOL;         // [8RG][NCOL]
+  float* dpT = buf + RG * 8 * NCOL;          // [2Co][dpp]  d pre-activations, k-major (transposed)
+  float* G = dpT + 2 * kCo * dpp;            // [N][Co]     dL/dH_t (open) -> partial dL/dH_{t-1}
+  float* dXp = G + N * kCo;                  // [N][4]      dU2[:, :cin] waiting for dU1
+  Gr<SG> g[2];
+  if constexpr (SG) {                        // compressed copy of both transposed operators: val f32 | col u8 | rowptr u16
+    float* gval = dXp + N * 4;
+    unsigned char* gcol = reinterpret_cast<unsigned char*>(gval + p.nnz[0] + p.nnz[1]);
+    unsigned short* grp = reinterpret_cast<unsigned short*>(gcol + ((p.nnz[0] + p.nnz[1] + 3) & ~3));
+#pragma unroll
+    for (int op = 0; op < 2; ++op) {
+      float* val = gval + (op ? p.nnz[0] : 0);
+      unsigned char* col = gcol + (op ? p.nnz[0] : 0);
+      unsigned short* rp = grp + op * (N + 1);
+      for (int k = tid; k < p.nnz[op]; k += kBwdThreads) { const int2 e = __ldg(p.cv[op] + k); val[k] = __int_as_float(e.y); col[k] = (unsigned char)e.x; }
+      for (int n = tid; n <= N; n += kBwdThreads) rp[n] = (unsigned short)__ldg(p.rp[op] + n);
+      g[op].rp = rp; g[op].val = val; g[op].col = col;
+    }
+  } else {
+#pragma unroll
+    for (int op = 0; op < 2; ++op) { g[op].rp = p.rp[op]; g[op].cv = p.cv[op]; }
+  }
+  // ---- weights, zero padded to NCOL columns; padded rows of dpT stay zero for the whole kernel
+  for (int i = tid; i < 3 * kCo * NCOL; i += kBwdThreads) {
     const int r = i / NCOL, c = i - r * NCOL;
     float v = 0.f;
     if (c < 3 * C) v = r < kCo ? __ldg(p.whsT + r * 3 * C + c) : __ldg(p.wzrT + (r - kCo) * 3 * C + c);
     sm[i] = v;
   }
+  for (int i = tid; i < 2 * kCo * dpp; i += kBwdThreads) dpT[i] = 0.f;
+  __syncthreads();
   // ---- open step T-1
   const long long bT = (long long)b * T;
-  for (int i = tid; i < N * kCo; i += blockDim.x) {
+  for (int i = tid; i < NH; i += kBwdThreads) {
     const int n = i / kCo, cc = i - n * kCo;
     const long long bt = bT + (T - 1);
-    const float g = __ldg(p.gout + bt * N * kCo + i);
-    const float z = __ldg(p.stash + (bt * 3 + 0) * N * kCo + i), ht = __ldg(p.stash + (bt * 3 + 2) * N * kCo + i);
-    const float d = g * (1.f - z) * (1.f - ht * ht);
-    G[i] = g;
-    dp[n * kDpPitch + cc] = d;
+    const float gg = __ldg(p.gout + bt * NH + i);
+    const float z = __ldg(p.stash + (bt * 3 + 0) * NH + i), ht = __ldg(p.stash + (bt * 3 + 2) * NH + i);
+    const float d = gg * (1.f - z) * (1.f - ht * ht);
+    G[i] = gg;
+    dpT[cc * dpp + n] = d;
     p.dph_all[(((long long)(T - 1) * p.B + b) * N) * kCo + i] = d;
   }
   __syncthreads();
 #pragma unroll 1
   for (int t = T - 1; t >= 0; --t) {
     const long long bt = bT + t;
-    const float* st = p.stash + bt * 3 * N * kCo;
-    const float* hprev = t > 0 ? p.out + (bt - 1) * N * kCo : (p.h0 ? p.h0 + (long long)b * N * kCo : nullptr);
+    const float* st = p.stash + bt * 3 * NH;
+    const float* hprev = t > 0 ? p.out + (bt - 1) * NH : (p.h0 ? p.h0 + (long long)b * NH : nullptr);
     // dS2 = dpre_h @ Wh^T
-    gemm_rows<HALF, kCo>(dp, Wh, buf, N);
+    gemm_tiles<NCOL, kCo>(dpT, dpp, Wh, buf, RG);
     __syncthreads();
     // dU2 = adjoint; d pre-activations of z and r; partial carry  g*Z + dHR*R
     float* dpzr = p.dpzr_all + (((long long)t * p.B + b) * N) * 2 * kCo;
-    for (int idx = tid; idx < N * C; idx += blockDim.x) {
-      const int n = idx / C, c = idx - n * C;
-      const float v = adjoint_at<NCOL>(p, buf, n, c, C);
-      if (c < Ci) {
-        dXp[n * 4 + c] = v;
-      } else {
-        const int cc = c - Ci, i = n * kCo + cc;
-        const float hp = hprev ? __ldg(hprev + i) : 0.f;
-        const float z = __ldg(st + i), r = __ldg(st + N * kCo + i), ht = __ldg(st + 2 * N * kCo + i);
-        const float g = G[i];
-        const float dpz = g * (hp - ht) * z * (1.f - z);
-        const float dpr = v * hp * r * (1.f - r);
-        dp[n * kDpPitch + cc] = dpz;
-        dp[n * kDpPitch + kCo + cc] = dpr;
-        dpzr[n * 2 * kCo + cc] = dpz;
-        dpzr[n * 2 * kCo + kCo + cc] = dpr;
-        G[i] = g * z + v * r;
+#pragma unroll 1
+    for (int base = tid; base < NP; base += kBatch * kBwdThreads) {
+      float hp[kBatch][V], zz[kBatch][V], rr[kBatch][V], hh[kBatch][V];
+#pragma unroll
+      for (int j = 0; j < kBatch; ++j) {                       // all global operands of the batch in flight together
+        const int s = base + j * kBwdThreads, n = s / CP, c0 = (s - n * CP) * V, i = n * kCo + c0 - CIN;
+#pragma unroll
+        for (int e = 0; e < V; ++e) hp[j][e] = zz[j][e] = rr[j][e] = hh[j][e] = 0.f;
+        if (s < NP && c0 >= CIN) {
+          if (hprev) ldgv<V>(hprev + i, hp[j]);
+          ldgv<V>(st + i, zz[j]); ldgv<V>(st + NH + i, rr[j]); ldgv<V>(st + 2 * NH + i, hh[j]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < kBatch; ++j) {
+        const int s = base + j * kBwdThreads;
+        if (s < NP) {
+          const int n = s / CP, c0 = (s - n * CP) * V;
+          float v[V];
+          adjoint_at<NCOL, C, V, SG>(g, buf, n, c0, v);
+          if (c0 < CIN) {
+#pragma unroll
+            for (int e = 0; e < V; ++e) dXp[n * 4 + c0 + e] = v[e];
+          } else {
+            const int cc = c0 - CIN, i = n * kCo + cc;
+            float gg[V], dz[V], dr[V], gn[V];
+            ldv<V>(G + i, gg);
+#pragma unroll
+            for (int e = 0; e < V; ++e) {
+              dz[e] = gg[e] * (hp[j][e] - hh[j][e]) * zz[j][e] * (1.f - zz[j][e]);
+              dr[e] = v[e] * hp[j][e] * rr[j][e] * (1.f - rr[j][e]);
+              gn[e] = gg[e] * zz[j][e] + v[e] * rr[j][e];
+              dpT[(cc + e) * dpp + n] = dz[e];
+              dpT[(kCo + cc + e) * dpp + n] = dr[e];
+            }
+            stv<V>(dpzr + n * 2 * kCo + cc, dz);
+            stv<V>(dpzr + n * 2 * kCo + kCo + cc, dr);
+            stv<V>(G + i, gn);
+          }
+        }
       }
     }
     __syncthreads();
     // dS1 = dpre_zr @ Wzr^T
-    gemm_rows<HALF, 2 * kCo>(dp, Wzr, buf, N);
+    gemm_tiles<NCOL, 2 * kCo>(dpT, dpp, Wzr, buf, RG);
     __syncthreads();
     // dU1 = adjoint; dX_t; dL/dH_{t-1}; open step t-1
-    const float* stn = st - 3 * N * kCo;     // stash of step t-1 (only dereferenced when t > 0)
-    for (int idx = tid; idx < N * C; idx += blockDim.x) {
-      const int n = idx / C, c = idx - n * C;
-      const float v = adjoint_at<NCOL>(p, buf, n, c, C);
-      if (c < Ci) {
-        if (p.dx) p.dx[(bt * N + n) * Ci + c] = dXp[n * 4 + c] + v;
-      } else {
-        const int cc = c - Ci, i = n * kCo + cc;
-        const float dh = G[i] + v;
-        if (t > 0) {
-          const float g = __ldg(p.gout + (bt - 1) * N * kCo + i) + dh;
-          const float z = __ldg(stn + i), ht = __ldg(stn + 2 * N * kCo + i);
-          const float d = g * (1.f - z) * (1.f - ht * ht);
-          G[i] = g;
-          dp[n * kDpPitch + cc] = d;
-          p.dph_all[(((long long)(t - 1) * p.B + b) * N) * kCo + i] = d;
-        } else {
-          p.dh0[(long long)b * N * kCo + i] = dh;
+    const float* stn = st - 3 * NH;          // stash of step t-1 (only dereferenced when t > 0)
+    float* dphn = p.dph_all + (((long long)(t - 1) * p.B + b) * N) * kCo;
+#pragma unroll 1
+    for (int base = tid; base < NP; base += kBatch * kBwdThreads) {
+      float go[kBatch][V], zz[kBatch][V], hh[kBatch][V];
+#pragma unroll
+      for (int j = 0; j < kBatch; ++j) {
+        const int s = base + j * kBwdThreads, n = s / CP, c0 = (s - n * CP) * V, i = n * kCo + c0 - CIN;
+#pragma unroll
+        for (int e = 0; e < V; ++e) go[j][e] = zz[j][e] = hh[j][e] = 0.f;
+        if (s < NP && c0 >= CIN && t > 0) {
+          ldgv<V>(p.gout + (bt - 1) * NH + i, go[j]); ldgv<V>(stn + i, zz[j]); ldgv<V>(stn + 2 * NH + i, hh[j]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < kBatch; ++j) {
+        const int s = base + j * kBwdThreads;
+        if (s < NP) {
+          const int n = s / CP, c0 = (s - n * CP) * V;
+          float v[V];
+          adjoint_at<NCOL, C, V, SG>(g, buf, n, c0, v);
+          if (c0 < CIN) {
+            if (p.dx) {
+#pragma unroll
+              for (int e = 0; e < V; ++e) p.dx[(bt * N + n) * CIN + c0 + e] = dXp[n * 4 + c0 + e] + v[e];
+            }
+          } else {
+            const int cc = c0 - CIN, i = n * kCo + cc;
+            float gg[V], d[V];
+            ldv<V>(G + i, gg);
+#pragma unroll
+            for (int e = 0; e < V; ++e) gg[e] += v[e];                       // dL/dH_{t-1}
+            if (t > 0) {
+#pragma unroll
+              for (int e = 0; e < V; ++e) {
+                gg[e] += go[j][e];
+                d[e] = gg[e] * (1.f - zz[j][e]) * (1.f - hh[j][e] * hh[j][e]);
+                dpT[(cc + e) * dpp + n] = d[e];
+              }
+              stv<V>(G + i, gg);
+              stv<V>(dphn + i, d);
+            } else {
+              stv<V>(p.dh0 + (long long)b * NH + i, gg);
+            }
+          }
         }
       }
     }
@@ -226,17 +360,36 @@ __global__ void __launch_bounds__(512, 1) k_dcrnn_bwd_seq(BwdParams p) {
   }
 }
 
-inline int ncol_for(int cin) { return (3 * (cin + kCo) + 7) / 8 * 8; }
-inline size_t seq_smem(int N, int cin) {
-  const int ncol = ncol_for(cin);
-  return sizeof(float) * ((size_t)3 * kCo * ncol + (size_t)N * (ncol + kDpPitch + kCo + 4));
+inline size_t seq_smem_base(int N, int cin) {
+  const int ncol = ncol_of(cin), rg = (N + 7) / 8;
+  return sizeof(float) * ((size_t)3 * kCo * ncol + (size_t)rg * 8 * ncol + (size_t)2 * kCo * (rg * 8 + 4) + (size_t)N * (kCo + 4));
+}
+inline size_t seq_smem_graph(const stmp_plan* plan) {
+  const size_t nnz = (size_t)plan->bwd[0].nnz + plan->bwd[1].nnz;
+  return 4 * nnz + ((nnz + 3) & ~(size_t)3) + 2 * 2 * ((size_t)plan->n + 1) + 8;
+}
+inline bool graph_in_smem(const stmp_plan* plan, int cin) {
+  return plan->n <= 256 && plan->bwd[0].nnz < 65536 && plan->bwd[1].nnz < 65536 &&
+         seq_smem_base(plan->n, cin) + seq_smem_graph(plan) <= 227 * 1024;
 }
 inline bool bwd_supported(const stmp_plan* plan, long long cin, long long cout, long long K) {
   if (!plan || plan->flavor != STMP_FLAVOR_DCONV || plan->n_ops != 2) return false;
   if (K != 2 || cout != kCo || cin < 1 || cin > 4) return false;
-  const int ncol = ncol_for((int)cin);
-  if (ncol != 104 && ncol != 112) return false;
-  return 2 * plan->n <= 512 && seq_smem(plan->n, (int)cin) <= 227 * 1024;
+  return ((plan->n + 7) / 8) * (ncol_of((int)cin) / 8) <= kBwdThreads && seq_smem_base(plan->n, (int)cin) <= 227 * 1024 &&
+         2 * sizeof(float) * (size_t)plan->n * (cin + kCo) <= 100 * 1024;
+}
+
+template <int CIN>
+int launch_basis(const BasisParams& p, size_t smem, cudaStream_t st) {
+  STMP_CUDA_OK(cudaFuncSetAttribute(k_dcrnn_bwd_basis<CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_dcrnn_bwd_basis<CIN><<<(unsigned)(p.B * p.T), 256, smem, st>>>(p);
+  return STMP_OK;
+}
+template <int CIN, bool SG>
+int launch_seq(const BwdParams& p, size_t smem, cudaStream_t st) {
+  STMP_CUDA_OK(cudaFuncSetAttribute(k_dcrnn_bwd_seq<CIN, SG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_dcrnn_bwd_seq<CIN, SG><<<(unsigned)p.B, kBwdThreads, smem, st>>>(p);
+  return STMP_OK;
 }
 
 }  // namespace
@@ -255,15 +408,24 @@ extern "C" int stmp_dcrnn_bwd_basis(const stmp_plan* plan, int64_t B, int64_t T,
   STMP_REQUIRE(bwd_supported(plan, cin, cout, 2), STMP_EUNSUPPORTED, "stmp_dcrnn_bwd_basis: configuration not served (K=2, cout=32, cin<=4, small graph)");
   STMP_REQUIRE(x && out && stash && S1 && S2, STMP_EINVAL, "stmp_dcrnn_bwd_basis: NULL tensor");
   STMP_REQUIRE(B >= 0 && T > 0 && ld >= 3 * (cin + cout), STMP_ESHAPE, "stmp_dcrnn_bwd_basis: bad sizes");
+  const bool vec2 = (cin + cout) % 2 == 0;
+  STMP_REQUIRE(!vec2 || (ld % 2 == 0 && x_bstride % 2 == 0 && x_tstride % 2 == 0 && ((uintptr_t)x % 8) == 0 && ((uintptr_t)S1 % 8) == 0 &&
+                         ((uintptr_t)S2 % 8) == 0), STMP_ESHAPE, "stmp_dcrnn_bwd_basis: operands must be 8-byte aligned with even strides");
   if (B == 0) return STMP_OK;
   BasisParams p;
   for (int o = 0; o < 2; ++o) { p.rp[o] = plan->fwd[o].rowptr; p.cv[o] = plan->fwd[o].cv; }
-  p.N = plan->n; p.Ci = (int)cin; p.B = (int)B; p.T = (int)T; p.ld = (int)ld;
+  p.N = plan->n; p.B = (int)B; p.T = (int)T; p.ld = (int)ld;
   p.x = x; p.x_bs = x_bstride; p.x_ts = x_tstride; p.out = out; p.h0 = h0; p.stash = stash; p.S1 = S1; p.S2 = S2;
   const size_t smem = sizeof(float) * 2 * (size_t)plan->n * (cin + cout);
-  STMP_REQUIRE(smem <= 100 * 1024, STMP_EUNSUPPORTED, "stmp_dcrnn_bwd_basis: graph too large for the shared-memory tile");
-  STMP_CUDA_OK(cudaFuncSetAttribute(k_dcrnn_bwd_basis, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_dcrnn_bwd_basis<<<(unsigned)(B * T), 256, smem, (cudaStream_t)stream>>>(p);
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = STMP_OK;
+  switch (cin) {
+    case 1: rc = launch_basis<1>(p, smem, st); break;
+    case 2: rc = launch_basis<2>(p, smem, st); break;
+    case 3: rc = launch_basis<3>(p, smem, st); break;
+    default: rc = launch_basis<4>(p, smem, st); break;
+  }
+  if (rc != STMP_OK) return rc;
   STMP_LAUNCH_OK("k_dcrnn_bwd_basis");
   return STMP_OK;
 }
@@ -275,20 +437,30 @@ extern "C" int stmp_dcrnn_bwd_seq(const stmp_plan* plan, int64_t B, int64_t T, i
   STMP_REQUIRE(bwd_supported(plan, cin, cout, 2), STMP_EUNSUPPORTED, "stmp_dcrnn_bwd_seq: configuration not served (K=2, cout=32, cin<=4, small graph)");
   STMP_REQUIRE(gout && out && stash && whsT && wzrT && dph_all && dpzr_all && dh0, STMP_EINVAL, "stmp_dcrnn_bwd_seq: NULL tensor");
   STMP_REQUIRE(B >= 0 && T > 0, STMP_ESHAPE, "stmp_dcrnn_bwd_seq: bad sizes");
+  auto al8 = [](const void* q) { return ((uintptr_t)q % 8) == 0; };
+  STMP_REQUIRE(al8(gout) && al8(out) && al8(stash) && al8(dph_all) && al8(dpzr_all) && al8(dh0) && (!h0 || al8(h0)), STMP_ESHAPE,
+               "stmp_dcrnn_bwd_seq: operands must be 8-byte aligned");
   if (B == 0) return STMP_OK;
   BwdParams p;
-  for (int o = 0; o < 2; ++o) { p.rp[o] = plan->bwd[o].rowptr; p.cv[o] = plan->bwd[o].cv; }
-  p.N = plan->n; p.Ci = (int)cin; p.B = (int)B; p.T = (int)T;
+  for (int o = 0; o < 2; ++o) { p.rp[o] = plan->bwd[o].rowptr; p.cv[o] = plan->bwd[o].cv; p.nnz[o] = plan->bwd[o].nnz; }
+  p.N = plan->n; p.B = (int)B; p.T = (int)T;
   p.gout = gout; p.out = out; p.h0 = h0; p.stash = stash; p.whsT = whsT; p.wzrT = wzrT;
   p.dph_all = dph_all; p.dpzr_all = dpzr_all; p.dx = dx; p.dh0 = dh0;
-  const size_t smem = seq_smem(plan->n, (int)cin);
-  if (ncol_for((int)cin) == 104) {
-    STMP_CUDA_OK(cudaFuncSetAttribute(k_dcrnn_bwd_seq<52>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_dcrnn_bwd_seq<52><<<(unsigned)B, 512, smem, (cudaStream_t)stream>>>(p);
-  } else {
-    STMP_CUDA_OK(cudaFuncSetAttribute(k_dcrnn_bwd_seq<56>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_dcrnn_bwd_seq<56><<<(unsigned)B, 512, smem, (cudaStream_t)stream>>>(p);
+  const bool sg = graph_in_smem(plan, (int)cin);
+  const size_t smem = seq_smem_base(plan->n, (int)cin) + (sg ? seq_smem_graph(plan) : 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = STMP_OK;
+  switch ((int)cin * 2 + (sg ? 1 : 0)) {
+    case 2: rc = launch_seq<1, false>(p, smem, st); break;
+    case 3: rc = launch_seq<1, true>(p, smem, st); break;
+    case 4: rc = launch_seq<2, false>(p, smem, st); break;
+    case 5: rc = launch_seq<2, true>(p, smem, st); break;
+    case 6: rc = launch_seq<3, false>(p, smem, st); break;
+    case 7: rc = launch_seq<3, true>(p, smem, st); break;
+    case 8: rc = launch_seq<4, false>(p, smem, st); break;
+    default: rc = launch_seq<4, true>(p, smem, st); break;
   }
+  if (rc != STMP_OK) return rc;
   STMP_LAUNCH_OK("k_dcrnn_bwd_seq");
   return STMP_OK;
 }
