@@ -68,16 +68,28 @@ def _basis_adjoint(plan, dS: torch.Tensor, C: int, K: int) -> torch.Tensor:
     return d0
 
 
+_UNSTACK_INDEX = {}
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device) -> "torch.cuda.Stream":
+    key = torch.device(device).index
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _SIDE_STREAMS[key]
+
+
 def _unstack_weight_grad(dWs: torch.Tensor, K: int, C: int) -> torch.Tensor:
-    """((2K-1)*C, O) gradient of `_stack_weight(W)` -> gradient of W (2,K,C,O)."""
+    """((2K-1)*C, O) gradient of `_stack_weight(W)` -> gradient of W (2,K,C,O): one gather of basis blocks
+    (block 0 feeds both W[0,0] and W[1,0]; block 1+2(k-1)+o feeds W[o,k])."""
+    key = (K, dWs.device)
+    idx = _UNSTACK_INDEX.get(key)
+    if idx is None:
+        order = [0 if k == 0 else 1 + 2 * (k - 1) + o for o in (0, 1) for k in range(K)]
+        idx = torch.tensor(order, dtype=torch.long, device=dWs.device)
+        _UNSTACK_INDEX[key] = idx
     O = dWs.size(1)
-    g = dWs.new_zeros(2, K, C, O)
-    g[0, 0] = dWs[:C]
-    g[1, 0] = dWs[:C]
-    for k in range(1, K):
-        g[0, k] = dWs[(1 + 2 * (k - 1)) * C:(2 + 2 * (k - 1)) * C]
-        g[1, k] = dWs[(2 + 2 * (k - 1)) * C:(3 + 2 * (k - 1)) * C]
-    return g
+    return dWs.reshape(2 * K - 1, C, O).index_select(0, idx).view(2, K, C, O)
 
 
 class _DcrnnSeqFn(torch.autograd.Function):
@@ -116,12 +128,20 @@ class _DcrnnSeqFn(torch.autograd.Function):
             # of all steps are one more, and the weight gradients are chunked GEMMs over all (t, b, n) rows
             S1 = torch.empty(T * B, N, nb * C, **f32)
             S2 = torch.empty(T * B, N, nb * C, **f32)
-            ops.dcrnn_bwd_basis(plan, X, out, H0, stash, S1, S2)
             dph_all = torch.empty(T, B, N, Co, **f32)
             dpzr_all = torch.empty(T, B, N, 2 * Co, **f32)
             dX = torch.empty_like(X) if ctx.needs_input_grad[0] else None
             dH0 = torch.empty(B, N, Co, **f32)
+            # the bases depend only on forward results, the recurrence only on gout: run them side by side -- the
+            # recurrence occupies one SM per window (64 of 148 at the reference's batch size), the basis kernel fills the
+            # rest.  Fork/join with events, so a CUDA-graph capture records two parallel branches.
+            main = torch.cuda.current_stream(X.device)
+            side = _side_stream(X.device)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                ops.dcrnn_bwd_basis(plan, X, out, H0, stash, S1, S2)
             ops.dcrnn_bwd_seq(plan, Ci, gout, out, H0, stash, WhsT, WzrT, dph_all, dpzr_all, dX, dH0)
+            main.wait_stream(side)
             return _DcrnnSeqFn._finish(ctx, S1, S2, dph_all, dpzr_all, dX, dH0, K, C, Co)
         Z, R, Ht = stash[:, :, 0], stash[:, :, 1], stash[:, :, 2]                          # (B,T,N,Co) strided views
         # ---- hoisted: H_{t-1} for every t (time-major so that [t] is a dense (B,N,Co) block) and both bases ------------
