@@ -137,3 +137,58 @@ def test_mstgcn_goldens(golden_dir):
         _loss([out]).backward()
         _check_grads(m, c["grads"], 2e-3, 2e-5)
         _close(Xg.grad, c["gX"], 2e-3, 2e-5)
+
+
+def test_dynamic_graph_signal_rebuilds_plans_on_device():
+    """a graph that changes per snapshot -> the layer's plan cache misses and the CSR operators are
+    rebuilt on the device for each new edge list; piecewise-constant stretches (same array object) reuse the plan."""
+    import numpy as np
+    from pytorch_geometric_temporal_b200.nn.recurrent import GConvGRU
+    from pytorch_geometric_temporal_b200.signal import DynamicGraphTemporalSignal
+    rng = np.random.default_rng(0)
+    n, T = 30, 6
+    graphs = []
+    for _ in range(3):
+        pairs = {(int(a), int(b)) for a, b in rng.integers(0, n, (90, 2)) if a != b} | {(i, (i + 1) % n) for i in range(n)}
+        ei = np.array(sorted(pairs)).T
+        graphs.append((ei, rng.random(ei.shape[1]) * 0.9 + 0.1))
+    order = [0, 0, 1, 1, 1, 2]                                   # piecewise-constant: 3 distinct graphs over 6 snapshots
+    xs = [rng.standard_normal((n, 4)).astype(np.float32) for _ in range(T)]
+    ys = [rng.standard_normal((n,)).astype(np.float32) for _ in range(T)]
+    ds = DynamicGraphTemporalSignal([graphs[g][0] for g in order], [graphs[g][1] for g in order], xs, ys)
+    torch.manual_seed(0)
+    m = GConvGRU(4, 16, 3)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    mg = m.to(DEV)
+    Hc = Hg = None
+    builds = []
+    for snap, dev_snap in zip(ds, ds.to(DEV)):
+        Hc = R.gconv_gru_cell(sd, snap.x, snap.edge_index, snap.edge_attr, Hc)
+        n0 = _lib.launch_count()
+        with torch.no_grad():
+            Hg = mg(dev_snap.x, dev_snap.edge_index, dev_snap.edge_attr, Hg)
+        builds.append(_lib.launch_count() - n0)
+        _close(Hg, Hc)
+    # snapshots 1, 3, 4 reuse the previous snapshot's graph: no plan build, only the (K-1) SpMMs + gate kernels
+    assert builds[1] < builds[0] and builds[3] < builds[2] and builds[4] == builds[3] and builds[5] > builds[4]
+
+
+def test_mstgcn_distinct_graph_per_timestep(golden_dir):
+    """per-timestep edge_index LIST with genuinely different graphs (mstgcn.py:96-115) against the oracle."""
+    from oracle import attention as OA
+    g = _load(golden_dir, "mstgcn_small")
+    c = g["cases"]["s1"]
+    base = g["edge_index"]
+    gen = torch.Generator().manual_seed(5)
+    eis = []
+    for t in range(6):
+        keep = torch.rand(base.size(1) // 2, generator=gen) > 0.25          # drop undirected pairs, keep symmetry
+        und = {(int(a), int(b)) for a, b in base.t().tolist() if a < b}
+        und = [p for p, k in zip(sorted(und), keep.tolist()) if k]
+        ei = torch.tensor(sorted(und + [(b, a) for a, b in und]), dtype=torch.long).t().contiguous()
+        eis.append(ei)
+    want = OA.mstgcn(c["state"], c["X"], eis, g["ctor"]["nb_block"], 1)
+    m = MSTGCN(time_strides=1, **g["ctor"]).to(DEV)
+    m.load_state_dict(c["state"])
+    with torch.no_grad():
+        _close(m(c["X"].to(DEV), [e.to(DEV) for e in eis]), want, 2e-4, 2e-5)

@@ -127,3 +127,81 @@ def test_offline_loaders_match_reference(tmp_path, mod, name, prefix):
     g = ours_cls(raw_data_dir=tmp, index=True).get_index_dataset(lags=6, batch_size=4, shuffle=True, world_size=2, ddp_rank=1)
     for (xa, ya), (xb, yb) in zip(w[0], g[0]):
         assert torch.equal(xa, xb) and torch.equal(ya, yb)
+
+
+# ---- dynamic-graph iterators ------------------------------------------------------------------------
+from pytorch_geometric_temporal_b200.signal import (DynamicGraphStaticSignal, DynamicGraphStaticSignalBatch,  # noqa: E402
+                                                     DynamicGraphTemporalSignal, DynamicGraphTemporalSignalBatch)
+
+
+def _dynamic_case(T=6, n=9, seed=0):
+    rng = np.random.default_rng(seed)
+    eis = [rng.integers(0, n, (2, int(rng.integers(5, 15)))) for _ in range(T)]
+    ews = [rng.random(e.shape[1]) for e in eis]
+    xs = [rng.random((n, 3)) for _ in range(T)]
+    ys = [rng.integers(0, 5, (n,)) if t % 2 else rng.random((n,)) for t in range(T)]
+    bs = [np.array([0] * 4 + [1] * (n - 4)) for _ in range(T)]
+    marks = [rng.random((n, 2)) for _ in range(T)]
+    return eis, ews, xs, ys, bs, marks
+
+
+def test_dynamic_signals_none_passthrough():
+    for snap in DynamicGraphTemporalSignal([None, None], [None, None], [None, None], [None, None]):       # dataset_test.py:117-125
+        assert snap.edge_index is None and snap.edge_attr is None and snap.x is None and snap.y is None
+    for snap in DynamicGraphStaticSignal([None], [None], None, [None]):                                    # :137-143
+        assert snap.edge_index is None and snap.edge_attr is None and snap.x is None and snap.y is None
+    for snap in DynamicGraphTemporalSignalBatch([None, None], [None, None], [None, None], [None, None], [None, None]):
+        assert snap.x is None and snap.batch is None
+    for snap in DynamicGraphStaticSignalBatch([None], [None], None, [None], [None]):
+        assert snap.x is None and snap.batch is None
+    with pytest.raises(AssertionError):
+        DynamicGraphTemporalSignal([None, None], [None], [None, None], [None, None])
+
+
+def test_dynamic_signals_iteration_typing_slicing():
+    eis, ews, xs, ys, bs, marks = _dynamic_case()
+    ds = DynamicGraphTemporalSignal(eis, ews, xs, ys, marks=marks)
+    for epoch in range(2):
+        for t, snap in enumerate(ds):
+            assert torch.equal(snap.edge_index, torch.from_numpy(eis[t])) and snap.edge_index.dtype == torch.int64
+            assert torch.equal(snap.edge_attr, torch.from_numpy(ews[t]).float())
+            assert torch.equal(snap.x, torch.from_numpy(xs[t]).float())
+            assert snap.y.dtype == (torch.int64 if t % 2 else torch.float32)
+            assert torch.equal(snap.marks, torch.from_numpy(marks[t]).float())
+        assert t == 5
+    tr, te = temporal_signal_split(ds, 0.5)
+    assert isinstance(tr, DynamicGraphTemporalSignal) and tr.snapshot_count == 3 and te.snapshot_count == 3
+    assert torch.equal(te[0].edge_index, torch.from_numpy(eis[3])) and torch.equal(te[0].marks, torch.from_numpy(marks[3]).float())
+    st = DynamicGraphStaticSignal(eis, ews, xs[0], ys)
+    assert len(st) == 6 and st[2].x is st[4].x and torch.equal(st[2].x, torch.from_numpy(xs[0]).float())   # static field converted once
+    assert isinstance(st[1:3], DynamicGraphStaticSignal) and st[1:3].snapshot_count == 2
+    bt = DynamicGraphTemporalSignalBatch(eis, ews, xs, ys, bs)
+    assert torch.equal(bt[3].batch, torch.from_numpy(bs[3])) and "batch" in bt[3].keys()
+    sb = DynamicGraphStaticSignalBatch(eis, ews, xs[0], ys, bs)
+    assert torch.equal(sb[5].batch, torch.from_numpy(bs[5])) and sb[0:2].snapshot_count == 2
+    # a piecewise-constant graph handing in the same array object twice shares the converted tensor (=> one cached plan)
+    pc = DynamicGraphTemporalSignal([eis[0], eis[0], eis[1]], [ews[0], ews[0], ews[1]], xs[:3], ys[:3])
+    assert pc[0].edge_index is pc[1].edge_index and pc[1].edge_index is not pc[2].edge_index
+
+
+@pytest.mark.skipif(not refload.available(), reason="/root/reference not present")
+def test_dynamic_signals_match_reference():
+    eis, ews, xs, ys, bs, marks = _dynamic_case(seed=3)
+    pairs = [
+        (refload.load("signal.dynamic_graph_temporal_signal").DynamicGraphTemporalSignal, DynamicGraphTemporalSignal, (eis, ews, xs, ys)),
+        (refload.load("signal.dynamic_graph_static_signal").DynamicGraphStaticSignal, DynamicGraphStaticSignal, (eis, ews, xs[0], ys)),
+        (refload.load("signal.dynamic_graph_temporal_signal_batch").DynamicGraphTemporalSignalBatch, DynamicGraphTemporalSignalBatch, (eis, ews, xs, ys, bs)),
+        (refload.load("signal.dynamic_graph_static_signal_batch").DynamicGraphStaticSignalBatch, DynamicGraphStaticSignalBatch, (eis, ews, xs[0], ys, bs)),
+        (refload.load("signal.static_graph_temporal_signal_batch").StaticGraphTemporalSignalBatch, StaticGraphTemporalSignalBatch, (eis[0], ews[0], xs, ys, bs[0])),
+    ]
+    for ref_cls, our_cls, args in pairs:
+        want, got = ref_cls(*args, marks=marks), our_cls(*args, marks=marks)
+        assert want.snapshot_count == got.snapshot_count
+        for a, b in zip(want, got):
+            for key in ("x", "edge_index", "edge_attr", "y", "marks"):
+                ta, tb = getattr(a, key), getattr(b, key)
+                assert ta.dtype == tb.dtype and torch.equal(ta, tb)
+            if hasattr(a, "batch") and a.batch is not None:
+                assert torch.equal(a.batch, b.batch)
+        wa, ga = want[1:4], got[1:4]
+        assert wa.snapshot_count == ga.snapshot_count and torch.equal(wa[0].x, ga[0].x) and torch.equal(wa[2].edge_index, ga[2].edge_index)
