@@ -187,6 +187,20 @@ int stmp_dcrnn_bwd_seq(const stmp_plan* plan, int64_t B, int64_t T, int64_t cin,
                        const float* out, const float* h0, const float* stash, const float* whsT, const float* wzrT,
                        float* dph_all, float* dpzr_all, float* dx, float* dh0, void* stream);
 
+/* Transposed stacked DConv weights for the backward kernels, one launch: whsT (cout, (2K-1)C) from wh, wzrT (2cout, (2K-1)C)
+ * from wz | wr; C = cin + cout; stacked block 0 = W[0,0] + W[1,0], block 1+2(k-1)+o = W[o,k] (the order of the basis). */
+int stmp_dcrnn_pack_bwd_weights(int64_t cin, int64_t cout, int64_t K, const float* wz, const float* wr, const float* wh,
+                                float* whsT, float* wzrT, void* stream);
+
+/* Masked MAE of the index-batching training loops (examples/indexBatching/DCRNN/utils.py:10-18, used at pems_ddp.py:104-121):
+ * loss = mean(nan_to_zero(|pred - y| * mask / mean(mask))), mask = (y != 0) == sum_i nz(|p_i - y_i| m_i) / sum_i m_i.
+ * fwd writes the scalar loss and s0 = sum(mask) (device scalars; deterministic two-stage reduction, workspace of
+ * stmp_masked_mae_workspace_floats() floats); bwd writes gpred = gout * sign(pred - y) * mask / s0. */
+int64_t stmp_masked_mae_workspace_floats(void);
+int stmp_masked_mae_fwd(int64_t n, const float* pred, const float* target, float* workspace, float* loss, float* s0, void* stream);
+int stmp_masked_mae_bwd(int64_t n, const float* pred, const float* target, const float* s0, const float* gout, float* gpred,
+                        void* stream);
+
 /* GRU reverse-time gate derivatives: the pointwise part of the hand-written backward of the DCRNN sequence (what
  * autograd records for dcrnn.py:172-192, once per step).  Tensors are (B, N, cout) with a batch stride in elements
  * (slices of gout (B,T,N,cout) and of the forward stash (B,T,3,N,cout)); du2/du1 are (B, N, du_ld) buffers whose

@@ -131,6 +131,65 @@ __global__ void __launch_bounds__(kT) k_gru_bwd_zr(long long total, int N, int C
   }
 }
 
+
+// ---- masked MAE of the index-batching examples (examples/indexBatching/DCRNN/utils.py:10-18) -----------------------
+//   mask = (y != 0); mask /= mean(mask); loss = mean(nan_to_zero(|p - y| * mask))   ==   sum_i nz(|p_i-y_i| m_i) / sum_i m_i
+// Deterministic two-stage reduction (per-block partials, then one block in fixed order).
+constexpr int kMaeBlocks = 512;
+__global__ void __launch_bounds__(kT) k_masked_mae_partial(long long n, const float* __restrict__ p, const float* __restrict__ y,
+                                                           float* __restrict__ part) {
+  float s = 0.f, m = 0.f;
+  for (long long i = blockIdx.x * (long long)kT + threadIdx.x; i < n; i += (long long)gridDim.x * kT) {
+    const float yy = y[i], t = fabsf(p[i] - yy);
+    if (yy != 0.f) { m += 1.f; if (t == t) s += t; }         // NaN terms are zeroed (utils.py:16), masked-out terms are 0
+  }
+  __shared__ float ss[kT / 32], sm[kT / 32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); m += __shfl_xor_sync(0xffffffffu, m, o); }
+  if ((threadIdx.x & 31) == 0) { ss[threadIdx.x >> 5] = s; sm[threadIdx.x >> 5] = m; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, b = 0.f;
+    for (int w = 0; w < kT / 32; ++w) { a += ss[w]; b += sm[w]; }
+    part[2 * blockIdx.x] = a; part[2 * blockIdx.x + 1] = b;
+  }
+}
+__global__ void k_masked_mae_final(int blocks, const float* __restrict__ part, float* __restrict__ loss, float* __restrict__ s0) {
+  if (threadIdx.x == 0) {
+    float a = 0.f, b = 0.f;
+    for (int i = 0; i < blocks; ++i) { a += part[2 * i]; b += part[2 * i + 1]; }
+    *s0 = b;
+    *loss = b > 0.f ? a / b : 0.f;                            // mean(mask) == 0 -> every term is NaN -> zeroed -> loss 0
+  }
+}
+__global__ void __launch_bounds__(kT) k_masked_mae_bwd(long long n, const float* __restrict__ p, const float* __restrict__ y,
+                                                       const float* __restrict__ s0, const float* __restrict__ gout,
+                                                       float* __restrict__ gp) {
+  const float b = *s0, scale = b > 0.f ? *gout / b : 0.f;
+  for (long long i = blockIdx.x * (long long)kT + threadIdx.x; i < n; i += (long long)gridDim.x * kT) {
+    const float yy = y[i], d = p[i] - yy;
+    float g = 0.f;
+    if (yy != 0.f && d == d) g = d > 0.f ? scale : (d < 0.f ? -scale : 0.f);
+    gp[i] = g;
+  }
+}
+
+// ---- transposed stacked DConv weights for the backward kernels: W (2,K,C,Co) -> rows of W_stacked^T ------------------
+// stacked block 0 = W[0,0] + W[1,0]; block 1+2(k-1)+o = W[o,k]  (nn/recurrent/dcrnn.py::_stack_weight)
+__global__ void __launch_bounds__(kT) k_pack_bwd_weights(int C, int Co, int K, const float* __restrict__ wz, const float* __restrict__ wr,
+                                                         const float* __restrict__ wh, float* __restrict__ whsT, float* __restrict__ wzrT) {
+  const int nbC = (2 * K - 1) * C, total = 3 * Co * nbC;
+  for (int i = blockIdx.x * kT + threadIdx.x; i < total; i += gridDim.x * kT) {
+    const int gate = i / (Co * nbC), r = i - gate * Co * nbC, o = r / nbC, col = r - o * nbC, blk = col / C, c = col - blk * C;
+    const float* w = gate == 0 ? wh : (gate == 1 ? wz : wr);
+    float v;
+    if (blk == 0) v = w[((0 * K + 0) * C + c) * Co + o] + w[((1 * K + 0) * C + c) * Co + o];
+    else { const int dir = (blk - 1) & 1, k = 1 + ((blk - 1) >> 1); v = w[((dir * K + k) * C + c) * Co + o]; }
+    if (gate == 0) whsT[o * nbC + col] = v;
+    else wzrT[((gate - 1) * Co + o) * nbC + col] = v;
+  }
+}
+
 }  // namespace
 }  // namespace stmp
 
@@ -217,5 +276,35 @@ extern "C" int stmp_gru_bwd_zr(int64_t B, int64_t N, int64_t cin, int64_t cout, 
   k_gru_bwd_zr<<<grid_for(B * N * cout), kT, 0, (cudaStream_t)stream>>>(B * N * cout, (int)N, (int)cin, (int)cout, du_ld, g, hprev,
                                                                          hprev_bstride, z, r, ht, stash_bstride, du2, dpzr);
   STMP_LAUNCH_OK("k_gru_bwd_zr");
+  return STMP_OK;
+}
+
+extern "C" int64_t stmp_masked_mae_workspace_floats(void) { return 2 * kMaeBlocks; }
+extern "C" int stmp_masked_mae_fwd(int64_t n, const float* pred, const float* target, float* workspace, float* loss, float* s0,
+                                   void* stream) {
+  STMP_REQUIRE(n >= 0 && pred && target && workspace && loss && s0, STMP_EINVAL, "stmp_masked_mae_fwd: bad argument");
+  int blocks = (int)((n + kT - 1) / kT);
+  if (blocks < 1) blocks = 1;
+  if (blocks > kMaeBlocks) blocks = kMaeBlocks;
+  k_masked_mae_partial<<<blocks, kT, 0, (cudaStream_t)stream>>>(n, pred, target, workspace);
+  STMP_LAUNCH_OK("k_masked_mae_partial");
+  k_masked_mae_final<<<1, 32, 0, (cudaStream_t)stream>>>(blocks, workspace, loss, s0);
+  STMP_LAUNCH_OK("k_masked_mae_final");
+  return STMP_OK;
+}
+extern "C" int stmp_masked_mae_bwd(int64_t n, const float* pred, const float* target, const float* s0, const float* gout,
+                                   float* gpred, void* stream) {
+  STMP_REQUIRE(n >= 0 && pred && target && s0 && gout && gpred, STMP_EINVAL, "stmp_masked_mae_bwd: bad argument");
+  if (n == 0) return STMP_OK;
+  k_masked_mae_bwd<<<grid_for(n), kT, 0, (cudaStream_t)stream>>>(n, pred, target, s0, gout, gpred);
+  STMP_LAUNCH_OK("k_masked_mae_bwd");
+  return STMP_OK;
+}
+extern "C" int stmp_dcrnn_pack_bwd_weights(int64_t cin, int64_t cout, int64_t K, const float* wz, const float* wr, const float* wh,
+                                           float* whsT, float* wzrT, void* stream) {
+  STMP_REQUIRE(cin >= 0 && cout > 0 && K > 0 && wz && wr && wh && whsT && wzrT, STMP_EINVAL, "stmp_dcrnn_pack_bwd_weights: bad argument");
+  const long long total = 3 * cout * (2 * K - 1) * (cin + cout);
+  k_pack_bwd_weights<<<grid_for(total), kT, 0, (cudaStream_t)stream>>>((int)(cin + cout), (int)cout, (int)K, wz, wr, wh, whsT, wzrT);
+  STMP_LAUNCH_OK("k_pack_bwd_weights");
   return STMP_OK;
 }

@@ -119,9 +119,7 @@ class _DcrnnSeqFn(torch.autograd.Function):
         C = Ci + Co
         nb = 2 * K - 1
         f32 = dict(device=X.device, dtype=torch.float32)
-        Whs = _stack_weight(wh)
-        Wzr = torch.cat([_stack_weight(wz), _stack_weight(wr)], dim=1)
-        WhsT, WzrT = Whs.t().contiguous(), Wzr.t().contiguous()
+        WhsT, WzrT = ops.dcrnn_pack_bwd_weights(wz, wr, wh, Ci, K)        # transposed stacked weights, one launch
         gout = gout.contiguous()
         if _DcrnnSeqFn.fused_backward and ops.dcrnn_bwd_supported(plan, Ci, Co, K):
             # small graph: the whole reverse recurrence is ONE persistent launch (dL/dH stays in shared memory), the bases

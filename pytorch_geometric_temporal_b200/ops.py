@@ -288,6 +288,48 @@ def dcrnn_bwd_seq(plan: GraphPlan, cin: int, gout, out, h0, stash, whsT, wzrT, d
                                                  _lib.ptr(dpzr_all), _lib.ptr(dx), _lib.ptr(dh0), _lib.stream_ptr()))
 
 
+def dcrnn_pack_bwd_weights(wz, wr, wh, cin: int, K: int):
+    """(whsT (Co, (2K-1)C), wzrT (2Co, (2K-1)C)): transposed stacked weights of the backward GEMMs, one launch."""
+    Co = wz.size(-1)
+    nbC = (2 * K - 1) * (cin + Co)
+    whsT = torch.empty(Co, nbC, device=wz.device, dtype=torch.float32)
+    wzrT = torch.empty(2 * Co, nbC, device=wz.device, dtype=torch.float32)
+    with torch.cuda.device(wz.device):
+        _lib.check(_lib.lib().stmp_dcrnn_pack_bwd_weights(cin, Co, K, _lib.ptr(_f32c(wz.detach(), "wz")), _lib.ptr(_f32c(wr.detach(), "wr")),
+                                                          _lib.ptr(_f32c(wh.detach(), "wh")), _lib.ptr(whsT), _lib.ptr(wzrT), _lib.stream_ptr()))
+    return whsT, wzrT
+
+
+class _MaskedMAE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, target):
+        pred, target = _f32c(pred, "pred"), _f32c(target, "target")
+        if pred.shape != target.shape:
+            raise RuntimeError(f"masked_mae: shape mismatch {tuple(pred.shape)} vs {tuple(target.shape)}")
+        ws = torch.empty(int(_lib.lib().stmp_masked_mae_workspace_floats()), device=pred.device, dtype=torch.float32)
+        out = torch.empty(2, device=pred.device, dtype=torch.float32)           # [loss, sum(mask)]
+        with torch.cuda.device(pred.device):
+            _lib.check(_lib.lib().stmp_masked_mae_fwd(pred.numel(), _lib.ptr(pred), _lib.ptr(target), _lib.ptr(ws), ctypes.c_void_p(out.data_ptr()),
+                                                      ctypes.c_void_p(out.data_ptr() + 4), _lib.stream_ptr()))
+        ctx.save_for_backward(pred, target, out)
+        return out[0].clone()
+
+    @staticmethod
+    def backward(ctx, gout):
+        pred, target, out = ctx.saved_tensors
+        gp = torch.empty_like(pred)
+        gout = gout.contiguous().to(torch.float32)
+        with torch.cuda.device(pred.device):
+            _lib.check(_lib.lib().stmp_masked_mae_bwd(pred.numel(), _lib.ptr(pred), _lib.ptr(target), ctypes.c_void_p(out.data_ptr() + 4),
+                                                      _lib.ptr(gout), _lib.ptr(gp), _lib.stream_ptr()))
+        return gp, None
+
+
+def masked_mae(pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+    """Fused masked MAE (forward 2 launches, backward 1) with the semantics of examples/indexBatching/DCRNN/utils.py:10-18."""
+    return _MaskedMAE.apply(pred, target)
+
+
 def _slice_ptr(t: Optional[torch.Tensor]):
     """(pointer, batch stride in elements) of a (B, N, C) fp32 slice whose trailing two dims are dense."""
     if t is None:

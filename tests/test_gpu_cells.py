@@ -233,3 +233,30 @@ def test_a3tgcn_fused_tc_vs_oracle():
     want1 = R.a3tgcn(m1.state_dict(), X1, ei, ew, H1)
     with torch.no_grad():
         _close(m1.to(DEV)(X1.to(DEV), ei.to(DEV), ew.to(DEV), H1.to(DEV)), want1)
+
+
+def test_masked_mae_fused_matches_reference_form():
+    """stmp_masked_mae_fwd/bwd vs the op-for-op loss of examples/indexBatching/DCRNN/utils.py:10-18 (value and gradient),
+    incl. masked zeros, NaN predictions, an all-zero target (0/0 mask -> loss 0) and a non-contiguous prediction."""
+    from pytorch_geometric_temporal_b200 import distributed as D
+    torch.manual_seed(0)
+    for shape, frac_zero, nan in (((64, 207), 0.2, False), ((7, 13), 0.5, True), ((300001,), 0.0, False), ((5, 9), 1.0, False)):
+        y = torch.randn(shape, device=DEV)
+        y[torch.rand(shape, device=DEV) < frac_zero] = 0.0
+        p = torch.randn(shape, device=DEV)
+        if nan:
+            p.view(-1)[3] = float("nan")
+        pa, pb = p.clone().requires_grad_(True), p.clone().requires_grad_(True)
+        la, lb = D.masked_mae_loss(pa, y), D.masked_mae_loss_reference(pb, y)
+        assert torch.allclose(la, lb, rtol=1e-5, atol=1e-7), (float(la), float(lb))
+        (la * 3.0).backward(); (lb * 3.0).backward()
+        ga, gb = pa.grad, torch.nan_to_num(pb.grad, nan=0.0)      # the reference's where() leaves NaN grads at NaN terms
+        assert torch.allclose(torch.nan_to_num(ga, nan=0.0), gb, rtol=1e-5, atol=1e-9)
+    base = torch.randn(64, 207, 2, device=DEV)
+    pa = base.clone().requires_grad_(True)
+    y = torch.randn(64, 207, device=DEV)
+    la = D.masked_mae_loss(pa[..., 0], y)                        # strided view
+    lb = D.masked_mae_loss_reference(base[..., 0], y)
+    assert torch.allclose(la, lb, rtol=1e-5)
+    la.backward()
+    assert pa.grad[..., 1].abs().max() == 0 and pa.grad[..., 0].abs().max() > 0
