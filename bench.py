@@ -207,7 +207,7 @@ def train_probe(dev, world, rank, ei_d, ew_d, series, steps=5, windows=64):
     tr, _, _ = index_splits(series.size(0), HORIZON)
     loader = IndexBatchLoader(series.to(dev), tr, HORIZON, windows, shuffle=True, world_size=world, rank=rank, seed=0)
     it = iter(loader)
-    opt = torch.optim.Adam(params, lr=1e-3, capturable=True, fused=True)   # one multi-tensor kernel for the whole update
+    opt = torch.optim.Adam(params, lr=1e-3, capturable=True)   # (torch's fused=True variant follows a different trajectory: tools/train_check.py)
     sx = torch.empty((windows, HORIZON, N_NODES, F_IN), device=dev)
     sy = torch.empty((windows, HORIZON, N_NODES, F_IN), device=dev)
     loss_buf = torch.zeros((), device=dev)
