@@ -78,3 +78,24 @@ def test_masked_mae():
     y, t = torch.tensor([1.0, 2.0, 3.0, 4.0]), torch.tensor([0.0, 2.5, 0.0, 3.0])
     # mask = [0,1,0,1]/0.5 ; |diff| = [1,.5,3,1] -> mean([0,1,0,2]) = 0.75
     assert abs(float(D.masked_mae_loss(y, t)) - 0.75) < 1e-6
+
+
+def test_masked_mae_matches_reference_example_util():
+    """The op-for-op form (the checker of the fused CUDA loss) against the unmodified reference function
+    examples/indexBatching/DCRNN/utils.py:10-18, loaded by path where /root/reference exists."""
+    import importlib.util
+    import os
+    path = "/root/reference/examples/indexBatching/DCRNN/utils.py"
+    if not os.path.isfile(path):
+        pytest.skip("/root/reference not present")
+    spec = importlib.util.spec_from_file_location("ref_dcrnn_utils", path)
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    torch.manual_seed(0)
+    for zero_frac in (0.0, 0.3, 1.0):
+        y = torch.randn(64, 207)
+        y[torch.rand(64, 207) < zero_frac] = 0.0
+        p = torch.randn(64, 207)
+        a, b = D.masked_mae_loss_reference(p, y), ref.masked_mae_loss(p, y)
+        assert torch.equal(a, b)
+        assert torch.equal(D.masked_mae_loss(p, y), b)          # CPU tensors take the op-for-op form
