@@ -24,6 +24,8 @@ import time
 import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
+_T0 = time.time()                                                   # process start: the secondary legs share one wall-clock budget
+BUDGET_S = float(os.environ.get("STMP_BENCH_BUDGET_S", "210"))     # after this many seconds the line is printed with what is done
 sys.path.insert(0, ROOT)
 
 N_NODES, N_EDGES, F_IN, HORIZON, HIDDEN, K_HOPS = 207, 1722, 2, 12, 32, 2
@@ -371,14 +373,6 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * B * args.steps / (float(t.item()) * 1e-3)
 
-    train = None
-    if not args.no_train:
-        train = train_probe(dev, world, rank, ei_d, ew_d, series)
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-
     # ---- roofline of the dominant kernel (k_dcrnn_seq = the whole step) ---------------------------------------
     achieved_gbs = B * BYTES_PER_SNAPSHOT / (ms_step * 1e-3) / 1e9
     traffic = None
@@ -393,13 +387,6 @@ def run_ours(args):
                 "algorithmic_bytes_per_launch": B * BYTES_PER_SNAPSHOT,
                 "note": "fused kernel is shared-memory-bandwidth bound (gather/scatter of the diffusion); contraction on tcgen05; HBM fraction reported as north_star asks",
                 "fp32_tflops_achieved": B * FLOPS_PER_SNAPSHOT / (ms_step * 1e-3) / 1e12}
-    spmm = spmm_probe(dev, pk) if not args.no_spmm else None
-    cpu = None
-    if world == 1 and not args.no_cpu:
-        r = cpu_reference(steps=10, warmup=1, budget_s=15.0)
-        cpu = {"value": r["value"], "unit": "snapshots/s", "cores": r["cores"], "kind": "port",
-               "sample": f"{r['windows']} windows x {r['steps_done']} steps, oracle port of BatchedDCRNN.forward on torch CPU ops; "
-                         f"{r['cores']} threads (best of calibration) on {r['host_cores']} host cores"}
     line = {
         "metric": "graph-snapshots/sec", "value": value, "unit": "snapshots/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -409,11 +396,62 @@ def run_ours(args):
                    "l2_policy": "8 rotating input batches + 318 KB/window output: per-step traffic > 126 MB L2"},
         "e2e": {"value": e2e_value, "unit": "snapshots/s", "h2d_bytes_per_step": B * HORIZON * N_NODES * F_IN * 4,
                 "d2h_bytes_per_step": 4, "api": "signal.DevicePrefetcher(host batches) -> BatchedDCRNN.forward(X, edge_index, edge_weight) -> scalar metric of every step read on the host, one step behind the launch front"},
-        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "spmm": spmm, "train": train, "cpu_baseline": cpu,
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "spmm": None, "train": None, "cpu_baseline": None,
     }
-    emit(line)
+    # ---- secondary legs under a hard wall-clock budget ----------------------------------------------------------------
+    # The headline numbers above are complete.  cpu_baseline / SpMM probe / training probe run under a deadline counted
+    # from process start: on a slow or contended host (the oracle leg is CPU-bound) the line is printed with the legs
+    # finished so far instead of running past the "few minutes" the contract allows.
+    legs = _LegDeadline(line, ["cpu_baseline", "spmm", "train"], emit_line=(rank == 0), seconds=max(20.0, BUDGET_S - (time.time() - _T0)))
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        r = cpu_reference(steps=10, warmup=1, budget_s=15.0)
+        cpu = {"value": r["value"], "unit": "snapshots/s", "cores": r["cores"], "kind": "port",
+               "sample": f"{r['windows']} windows x {r['steps_done']} steps, oracle port of BatchedDCRNN.forward on torch CPU ops; "
+                         f"{r['cores']} threads (best of calibration) on {r['host_cores']} host cores"}
+    legs.done("cpu_baseline", cpu)
+    legs.done("spmm", spmm_probe(dev, pk) if (rank == 0 and not args.no_spmm) else None)
+    legs.done("train", train_probe(dev, world, rank, ei_d, ew_d, series) if not args.no_train else None)
+    legs.finish()
     if world > 1:
         dist.destroy_process_group()
+
+
+class _LegDeadline(object):
+    """Wall-clock deadline for the secondary legs of a bench line.  `done(key, value)` fills a leg in; `finish()` prints
+    the line (once).  If the deadline expires first, the line is printed with the legs finished so far plus a
+    `legs_skipped` note and the process exits 0 -- from a timer thread, so a leg stuck in native code cannot hold it up."""
+
+    def __init__(self, line, legs, emit_line, seconds):
+        self.line, self.pending, self.emit_line = line, list(legs), emit_line
+        self.lock, self.closed = threading.Lock(), False
+        self.timer = threading.Timer(seconds, self._expire)
+        self.timer.daemon = True
+        self.timer.start()
+
+    def _expire(self):
+        with self.lock:
+            if self.closed:
+                return
+            self.closed = True
+            if self.emit_line:
+                self.line["legs_skipped"] = {"legs": list(self.pending), "why": f"wall-clock budget of {BUDGET_S:.0f} s reached"}
+                emit(self.line)
+            os._exit(0)
+
+    def done(self, key, value):
+        with self.lock:
+            self.line[key] = value
+            self.pending.remove(key)
+
+    def finish(self):
+        with self.lock:
+            if self.closed:
+                return
+            self.closed = True
+            self.timer.cancel()
+            if self.emit_line:
+                emit(self.line)
 
 
 _REAL_STDOUT = None
