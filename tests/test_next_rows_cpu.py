@@ -205,3 +205,16 @@ def test_dynamic_signals_match_reference():
                 assert torch.equal(a.batch, b.batch)
         wa, ga = want[1:4], got[1:4]
         assert wa.snapshot_count == ga.snapshot_count and torch.equal(wa[0].x, ga[0].x) and torch.equal(wa[2].edge_index, ga[2].edge_index)
+
+
+# ---- host-side algebra of the hand-written DCRNN backward ---------------------------------------------------------------
+@pytest.mark.parametrize("K", [1, 2, 3, 4])
+def test_unstack_weight_grad_is_the_adjoint_of_stack_weight(K):
+    """dL/dW from dL/d(stacked W): block 0 of the stacked basis feeds BOTH W[0,0] and W[1,0] (dcrnn.py:81-84 adds the two
+    k=0 products of the same X), block 1+2(k-1)+o feeds W[o,k].  Checked against autograd of `_stack_weight`."""
+    from pytorch_geometric_temporal_b200.nn.recurrent.dcrnn import _stack_weight, _unstack_weight_grad
+    C, O = 5, 3
+    W = torch.randn(2, K, C, O, requires_grad=True)
+    G = torch.randn((2 * K - 1) * C, O)
+    (_stack_weight(W) * G).sum().backward()
+    assert torch.equal(W.grad, _unstack_weight_grad(G, K, C))
