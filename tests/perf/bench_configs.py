@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Secondary measurements for the other BASELINE.json configs (parity-test cases, not bench lines):
+"""(lives under tests/: it times the oracle as the CPU side, and only tests/, smoke() and bench.py may touch oracle/)
+Secondary measurements for the other BASELINE.json configs (parity-test cases, not bench lines):
 cfg1 GConvGRU/chickenpox, cfg3 A3TGCN2/PEMS-BAY-shape, cfg4 ASTGCN/PeMS04-shape, cfg5 GConvLSTM 10k/100k.
 Prints one JSON object per config: ours (CUDA events, after warm-up) and the oracle port on the host cores."""
 import json
@@ -9,7 +10,7 @@ import time
 
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from oracle import attention as OA, recurrent as R  # noqa: E402
 from pytorch_geometric_temporal_b200.dataset import ChickenpoxDatasetLoader, synthetic  # noqa: E402
