@@ -402,6 +402,14 @@ def run_ours(args):
     # The headline numbers above are complete.  cpu_baseline / SpMM probe / training probe run under a deadline counted
     # from process start: on a slow or contended host (the oracle leg is CPU-bound) the line is printed with the legs
     # finished so far instead of running past the "few minutes" the contract allows.
+    _secondary_legs(line, args, rank, world, dev, pk, ei_d, ew_d, series)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _secondary_legs(line, args, rank, world, dev, pk, ei_d, ew_d, series):
+    """cpu_baseline (rank 0, N=1), SpMM probe (rank 0), training probe (all ranks: it holds the all-reduce), each written
+    into `line` as it finishes; the line is printed by rank 0 when all are done or when the deadline expires."""
     legs = _LegDeadline(line, ["cpu_baseline", "spmm", "train"], emit_line=(rank == 0), seconds=max(20.0, BUDGET_S - (time.time() - _T0)))
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -413,8 +421,6 @@ def run_ours(args):
     legs.done("spmm", spmm_probe(dev, pk) if (rank == 0 and not args.no_spmm) else None)
     legs.done("train", train_probe(dev, world, rank, ei_d, ew_d, series) if not args.no_train else None)
     legs.finish()
-    if world > 1:
-        dist.destroy_process_group()
 
 
 class _LegDeadline(object):

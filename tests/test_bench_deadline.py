@@ -41,3 +41,31 @@ def test_deadline_not_reached_prints_once():
 def test_non_zero_rank_exits_silently():
     r = _run("d = bench._LegDeadline({'x': None}, ['x'], False, 0.3)\ntime.sleep(30)\n")
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_secondary_legs_fill_the_line_in_order_and_print_once():
+    """The tail of bench.py's own arm with the three legs stubbed: rank 0 prints one line carrying all legs; other ranks
+    print nothing; --no-* flags leave nulls; cpu_baseline only at N=1."""
+    body = (
+        "import argparse\n"
+        "calls = []\n"
+        "bench.cpu_reference = lambda **k: calls.append('cpu') or {'value': 700.0, 'cores': 16, 'windows': 64, 'steps_done': 10, 'host_cores': 128}\n"
+        "bench.spmm_probe = lambda dev, pk: calls.append('spmm') or {'achieved': 1500.0}\n"
+        "bench.train_probe = lambda *a: calls.append('train') or {'value': 59000.0}\n"
+        "def run(rank, world, **flags):\n"
+        "    args = argparse.Namespace(no_cpu=False, no_spmm=False, no_train=False); args.__dict__.update(flags)\n"
+        "    line = {'value': 1.0, 'spmm': None, 'train': None, 'cpu_baseline': None}\n"
+        "    bench._secondary_legs(line, args, rank, world, None, {}, None, None, None)\n"
+        "    return line\n"
+        "a = run(0, 1); assert calls == ['cpu', 'spmm', 'train'], calls\n"
+        "assert a['cpu_baseline']['value'] == 700.0 and a['cpu_baseline']['kind'] == 'port' and a['spmm'] and a['train']\n"
+        "calls.clear(); b = run(1, 2); assert calls == ['train'] and b['cpu_baseline'] is None and b['spmm'] is None\n"
+        "calls.clear(); c = run(0, 2); assert calls == ['spmm', 'train'] and c['cpu_baseline'] is None\n"
+        "calls.clear(); d = run(0, 1, no_cpu=True, no_spmm=True, no_train=True); assert calls == [] and d['train'] is None\n"
+    )
+    r = _run(body)
+    assert r.returncode == 0, r.stderr
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 3                                      # the three rank-0 calls; rank 1 printed nothing
+    first = json.loads(lines[0])
+    assert first["cpu_baseline"]["cores"] == 16 and "legs_skipped" not in first
