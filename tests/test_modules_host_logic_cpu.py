@@ -119,3 +119,89 @@ def test_mstgcn_host_logic_with_gradients(golden_dir, dense_graph_ops):
         _close(X.grad, c["gX"], 2e-3, 2e-5)
         with torch.no_grad():
             _close(m(c["X"], [g["edge_index"]] * 6), c["out_list"], 2e-4, 2e-5)
+
+
+# ---- DConv / DCRNN (tiled path) and the GCNConv family ------------------------------------------------------------------
+import pytorch_geometric_temporal_b200.nn.recurrent.attentiontemporalgcn as a3_mod  # noqa: E402
+import pytorch_geometric_temporal_b200.nn.recurrent.dcrnn as dcrnn_mod  # noqa: E402
+import pytorch_geometric_temporal_b200.nn.recurrent.temporalgcn as tgcn_mod  # noqa: E402
+from oracle import recurrent as R  # noqa: E402
+from pytorch_geometric_temporal_b200.nn.recurrent import A3TGCN, A3TGCN2, DCRNN, BatchedDCRNN, TGCN, TGCN2  # noqa: E402
+
+
+class _DensePair(object):
+    def __init__(self, mats):
+        self.mats = mats
+
+
+def _dense(edge_index, w, n):
+    M = torch.zeros(n, n)
+    M.index_put_((edge_index[1], edge_index[0]), w, accumulate=True)
+    return M
+
+
+@pytest.fixture()
+def dense_dconv_gcn_ops(monkeypatch):
+    def dconv_plan(self, edge_index, edge_weight, num_nodes):
+        ew = edge_weight if edge_weight is not None else torch.ones(edge_index.size(1))
+        eo, no, ei, ni = R.dconv_operators(edge_index, ew, self._batched_semantics, num_nodes)
+        return _DensePair([_dense(eo, no, num_nodes), _dense(ei, ni, num_nodes)])
+
+    def gcn_plan(self, edge_index, edge_weight, num_nodes):
+        e, w = pyg.gcn_norm(edge_index, edge_weight, num_nodes, self.improved, self.add_self_loops, torch.float32)
+        return _DensePair([_dense(e, w, num_nodes)])
+
+    def spmm(plan, op, x, alpha=1.0, z=None, beta=0.0, att=None):
+        y = alpha * torch.matmul(plan.mats[op], x)
+        return y if z is None else y + beta * z
+
+    monkeypatch.setattr(dcrnn_mod.DConv, "_plan", dconv_plan)
+    monkeypatch.setattr(dcrnn_mod.DCRNN, "_plan", dconv_plan)
+    monkeypatch.setattr(tgcn_mod.TGCN, "_plan", gcn_plan)
+    monkeypatch.setattr(ops, "spmm", spmm)
+    monkeypatch.setattr(ops, "dcrnn_seq_supported", lambda *a, **k: False)          # no fused kernels on the CPU
+    monkeypatch.setattr(tgcn_mod.TGCN, "_fused_ok", lambda self, plan, X, H: False)
+    for m in (dcrnn_mod, tgcn_mod, a3_mod):
+        monkeypatch.setattr(m, "_require_cuda", lambda *a, **k: None)
+
+
+def test_dcrnn_tiled_host_logic_with_gradients(golden_dir, dense_dconv_gcn_ops):
+    for K in (1, 3, 4):
+        g = _load(golden_dir, f"dcrnn_small_K{K}")
+        m = DCRNN(3, 16, K)
+        m.load_state_dict(g["state"])
+        x, h = g["X"].clone().requires_grad_(True), g["H"].clone().requires_grad_(True)
+        out = m(x, g["edge_index"], g["edge_weight"], h)
+        _close(out, g["out"])
+        _loss([out]).backward()
+        for k, p in m.named_parameters():
+            _close(p.grad, g["grads"][k], 1e-3, 1e-5)
+        _close(x.grad, g["gX"], 1e-3, 1e-5); _close(h.grad, g["gH"], 1e-3, 1e-5)
+    g = _load(golden_dir, "dcrnn_small_batched_K3")
+    m = BatchedDCRNN(3, 16, 3)
+    m.load_state_dict(g["state"])
+    _close(m(g["X"], g["edge_index"], g["edge_weight"]), g["out"])
+    g = _load(golden_dir, "dcrnn_cfg2_cell")
+    m = DCRNN(2, 32, 2)
+    m.load_state_dict(g["state"])
+    _close(m(g["X"], g["edge_index"], g["edge_weight"], g["H"]), g["out"])
+    _close(m(g["X"], g["edge_index"]), g["out_noew_noh"])                      # edge_weight None, H None
+
+
+def test_tgcn_family_host_logic(golden_dir, dense_dconv_gcn_ops):
+    g = _load(golden_dir, "tgcn_small")
+    for c in g["cases"].values():
+        m = TGCN(4, 16, improved=c["improved"], add_self_loops=c["add_self_loops"])
+        m.load_state_dict(c["state"])
+        _close(m(c["X"], g["edge_index"], g["edge_weight"], c["H"]), c["out"])
+        m2 = TGCN2(4, 16, 3, improved=c["improved"], add_self_loops=c["add_self_loops"])
+        m2.load_state_dict(c["state2"])
+        _close(m2(c["X2"], g["edge_index"], g["edge_weight"], c["H2"]), c["out2"])
+    g = _load(golden_dir, "a3tgcn_small")
+    m = A3TGCN2(2, 16, 6, 3)
+    m.load_state_dict(g["state"])
+    _close(m(g["X"], g["edge_index"], g["edge_weight"]), g["out"])
+    _close(m(g["X"], g["edge_index"], g["edge_weight"], torch.ones(3, 40, 16) * 0.3), g["outH"])
+    m1 = A3TGCN(2, 16, 6)
+    m1.load_state_dict(g["state1"])
+    _close(m1(g["X1"], g["edge_index"], g["edge_weight"]), g["out1"])
