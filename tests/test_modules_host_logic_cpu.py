@@ -205,3 +205,42 @@ def test_tgcn_family_host_logic(golden_dir, dense_dconv_gcn_ops):
     m1 = A3TGCN(2, 16, 6)
     m1.load_state_dict(g["state1"])
     _close(m1(g["X1"], g["edge_index"], g["edge_weight"]), g["out1"])
+
+
+# ---- ASTGCN: attention-weighted first hop, timesteps folded into the feature axis, fp32 time convolutions ---------------
+import pytorch_geometric_temporal_b200.nn.attention.astgcn as astgcn_mod  # noqa: E402
+from oracle import attention as OA  # noqa: E402
+from pytorch_geometric_temporal_b200.nn.attention import ASTGCN  # noqa: E402
+
+
+@pytest.fixture()
+def dense_att_ops(monkeypatch):
+    def plan(self, edge_index, edge_weight, num_nodes, lambda_max):
+        lam = torch.tensor(2.0 if lambda_max is None else float(lambda_max))
+        ei, w = OA.cheb_att_norm(edge_index, num_nodes, edge_weight, self._normalization, lam)
+        W = torch.zeros(num_nodes, num_nodes)
+        W.index_put_((ei[0], ei[1]), w, accumulate=True)          # propagated on the TRANSPOSED index: out[row] += w x[col]
+        return _DensePlan(W)
+
+    def spmm(plan, op, x, alpha=1.0, z=None, beta=0.0, att=None):
+        A = plan.L if att is None else plan.L.unsqueeze(0) * att  # first hop: norm * S[b,row,col]
+        y = alpha * torch.matmul(A, x)
+        return y if z is None else y + beta * z
+
+    monkeypatch.setattr(astgcn_mod.ChebConvAttention, "_plan", plan)
+    monkeypatch.setattr(ops, "spmm", spmm)
+    monkeypatch.setattr(astgcn_mod, "_require_cuda", lambda *a, **k: None)
+
+
+def test_astgcn_host_logic(golden_dir, dense_att_ops):
+    g = _load(golden_dir, "astgcn_small")
+    for name, c in g["cases"].items():
+        m = ASTGCN(**g["ctor"], normalization=c["normalization"])
+        m.load_state_dict(c["state"])
+        X = c["X"].clone().requires_grad_(True)
+        out = m(X, g["edge_index"])
+        _close(out, c["out"], 2e-4, 2e-5)
+        out.sum().backward()                                      # the whole block is differentiable through the stand-ins
+        assert torch.isfinite(X.grad).all() and all(torch.isfinite(p.grad).all() for p in m.parameters())
+        with torch.no_grad():
+            _close(m(c["X"], [g["edge_index"]] * 6), c["out"], 2e-4, 2e-5)      # per-timestep list of the same graph
