@@ -76,6 +76,13 @@ enum stmp_plan_flags {
 int stmp_plan_create(int flavor, int64_t num_nodes, int64_t num_edges, const int64_t* edge_index,
                      const float* edge_weight, int normalization, float lambda_max, uint32_t flags,
                      void* stream, stmp_plan** out);
+/* Multi-graph mini-batches (StaticGraphTemporalSignalBatch; PyG ChebConv `lambda_max[batch[edge_index[0]]]`, and
+ * ChebConvAttention.__norm__, astgcn.py:98-99; exercised by the reference's test/attention_test.py:205-218): the scaling
+ * 2 w / lambda uses the lambda_max of the entry's ROW node.  lambda_node: device float [num_nodes] = lambda_max[batch].
+ * Flavors CHEB and CHEB_ATT only. */
+int stmp_plan_create_pergraph(int flavor, int64_t num_nodes, int64_t num_edges, const int64_t* edge_index,
+                              const float* edge_weight, int normalization, const float* lambda_node, uint32_t flags,
+                              void* stream, stmp_plan** out);
 void stmp_plan_destroy(stmp_plan* plan);
 
 /* Introspection (tests, bit-exact index parity): number of operators, nodes, entries of operator `op`. */
@@ -254,6 +261,10 @@ const char* stmp_last_error(void);
 const char* stmp_version(void);
 /* Number of kernels this library has launched in the calling process (bench.py's gpu_launches). */
 int64_t stmp_launch_count(void);
+/* Which kernels served the calls so far ("did the fused tcgen05 path run, or the tiled one?" -- the dispatchers fall back
+ * silently on STMP_EUNSUPPORTED, e.g. dcrnn.py:429-475 at N > 207).  Fills up to max_entries (kernel name, launches) pairs,
+ * names are static strings such as "k_dcrnn_seq_tc"; returns the number of distinct kernels launched. */
+int stmp_path_counters(const char** names, int64_t* counts, int max_entries);
 
 #ifdef __cplusplus
 }

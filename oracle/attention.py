@@ -9,17 +9,19 @@ from . import pyg
 from .recurrent import _sub
 
 
-def cheb_att_norm(edge_index, num_nodes, edge_weight, normalization, lambda_max, dtype=torch.float32):
+def cheb_att_norm(edge_index, num_nodes, edge_weight, normalization, lambda_max, dtype=torch.float32, batch=None):
     """ChebConvAttention.__norm__ (astgcn.py:82-110): remove loops -> get_laplacian (appends N loops)
-    -> 2w/lam, inf->0 -> add_self_loops(fill=-1) (appends N MORE loops)."""
+    -> [per-graph lambda_max[batch[row]], :98-99] -> 2w/lam, inf->0 -> add_self_loops(fill=-1) (appends N MORE loops)."""
     ei, ew = pyg.remove_self_loops(edge_index, edge_weight)
     ei, ew = pyg.get_laplacian(ei, ew, normalization, dtype, num_nodes)
+    if batch is not None and lambda_max.numel() > 1:
+        lambda_max = lambda_max[batch[ei[0]]]
     ew = (2.0 * ew) / lambda_max
     ew = ew.masked_fill(ew == float("inf"), 0)
     return pyg.add_self_loops(ei, ew, fill_value=-1.0, num_nodes=num_nodes)
 
 
-def cheb_conv_attention(p, x, edge_index, S, normalization=None, edge_weight=None, lambda_max=None):
+def cheb_conv_attention(p, x, edge_index, S, normalization=None, edge_weight=None, lambda_max=None, batch=None):
     """ChebConvAttention.forward (astgcn.py:112-183).  x (B,N,Fin), S (B,N,N)."""
     if normalization != "sym" and lambda_max is None:
         raise ValueError("You need to pass `lambda_max` to `forward() in`case the normalization is non-symmetric.")
@@ -27,7 +29,7 @@ def cheb_conv_attention(p, x, edge_index, S, normalization=None, edge_weight=Non
         lambda_max = torch.tensor(2.0, dtype=x.dtype)
     if not isinstance(lambda_max, torch.Tensor):
         lambda_max = torch.tensor(lambda_max, dtype=x.dtype)
-    ei, norm = cheb_att_norm(edge_index, x.size(-2), edge_weight, normalization, lambda_max, x.dtype)
+    ei, norm = cheb_att_norm(edge_index, x.size(-2), edge_weight, normalization, lambda_max, x.dtype, batch)
     row, col = ei[0], ei[1]
     att = norm * S[:, row, col]                                   # (B,E2)            :156-157
     T0 = torch.diagonal(S, dim1=1, dim2=2).unsqueeze(-1) * x      # (I*S)^T @ x       :160-165

@@ -34,12 +34,12 @@ def dconv_operators(edge_index: Tensor, edge_weight: Optional[Tensor], batched: 
     if not batched:
         adj = pyg.to_dense_adj(edge_index, edge_attr=edge_weight)
         adj = adj.reshape(adj.size(1), adj.size(2))
-        deg_out = torch.matmul(adj, torch.ones(adj.size(0), 1)).flatten()
-        deg_in = torch.matmul(torch.ones(1, adj.size(0)), adj).flatten()
+        deg_out = torch.matmul(adj, torch.ones(adj.size(0), 1, device=adj.device)).flatten()
+        deg_in = torch.matmul(torch.ones(1, adj.size(0), device=adj.device), adj).flatten()
         rev, _ = pyg.dense_to_sparse(adj.transpose(0, 1))
     else:
-        deg_out = torch.zeros(num_nodes).scatter_add_(0, row, edge_weight)
-        deg_in = torch.zeros(num_nodes).scatter_add_(0, col, edge_weight)
+        deg_out = torch.zeros(num_nodes, device=row.device).scatter_add_(0, row, edge_weight)
+        deg_in = torch.zeros(num_nodes, device=row.device).scatter_add_(0, col, edge_weight)
         rev = torch.stack([col, row], dim=0)
         rev = rev[:, (rev[0] * num_nodes + rev[1]).argsort()]
     norm_out = torch.reciprocal(deg_out)[row]
@@ -79,20 +79,29 @@ def dcrnn_cell(p, X: Tensor, edge_index: Tensor, edge_weight: Optional[Tensor] =
     """DCRNN.forward (dcrnn.py:194-219); H None -> zeros (:167-170)."""
     out = p["conv_x_z.weight"].size(-1)
     if H is None:
-        H = torch.zeros(X.shape[0], out)
+        H = torch.zeros(X.shape[0], out, device=X.device)
     ops = dconv_operators(edge_index, edge_weight, batched=False, num_nodes=X.shape[0])
     return _dcrnn_step(p, X, ops, H)
 
 
-def batched_dcrnn(p, X: Tensor, edge_index: Tensor, edge_weight: Tensor) -> Tensor:
-    """BatchedDCRNN.forward (dcrnn.py:429-475): X (B,T,N,F) -> (B,T,N,out); graph replicated
-    block-diagonally (:363-369), H0 = 0, Python loop over t."""
-    B, T, N, F = X.shape
-    out = p["conv_x_z.weight"].size(-1)
+def batched_dcrnn_operators(edge_index: Tensor, edge_weight: Tensor, B: int, N: int):
+    """The cached part of BatchedDCRNN.forward (dcrnn.py:363-369,446-460): the block-diagonal edge list and, through
+    BatchedDConv's `cached_idx`, its norms and sorted reverse list -- built once per (graph, batch size)."""
     ei = torch.cat([edge_index + i * N for i in range(B)], dim=1)
     ew = edge_weight.repeat(B)
-    ops = dconv_operators(ei, ew, batched=True, num_nodes=B * N)
-    H = torch.zeros(B * N, out)
+    return dconv_operators(ei, ew, batched=True, num_nodes=B * N)
+
+
+def batched_dcrnn(p, X: Tensor, edge_index: Tensor, edge_weight: Tensor, ops=None) -> Tensor:
+    """BatchedDCRNN.forward (dcrnn.py:429-475): X (B,T,N,F) -> (B,T,N,out); graph replicated
+    block-diagonally (:363-369), H0 = 0, Python loop over t.  `ops` = batched_dcrnn_operators(...) when the caller
+    keeps them across calls, as the reference does (`cached_idx`, dcrnn.py:446-460).  Device-agnostic: tensors on
+    `cuda` give the reference's op-for-op sequence on the GPU (bench.py's `reference_gpu` leg)."""
+    B, T, N, F = X.shape
+    out = p["conv_x_z.weight"].size(-1)
+    if ops is None:
+        ops = batched_dcrnn_operators(edge_index, edge_weight, B, N)
+    H = torch.zeros(B * N, out, device=X.device)
     outs = []
     for t in range(T):
         H = _dcrnn_step(p, X[:, t].reshape(B * N, F), ops, H)

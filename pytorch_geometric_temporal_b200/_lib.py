@@ -28,6 +28,7 @@ class StmpUnsupported(StmpError):
 _P = c_void_p
 _SIGNATURES = {
     "stmp_plan_create": (c_int, [c_int, c_int64, c_int64, _P, _P, c_int, c_float, c_uint32, _P, POINTER(c_void_p)]),
+    "stmp_plan_create_pergraph": (c_int, [c_int, c_int64, c_int64, _P, _P, c_int, _P, c_uint32, _P, POINTER(c_void_p)]),
     "stmp_plan_destroy": (None, [_P]),
     "stmp_plan_num_ops": (c_int, [_P]),
     "stmp_plan_num_nodes": (c_int64, [_P]),
@@ -66,6 +67,7 @@ _SIGNATURES = {
     "stmp_last_error": (c_char_p, []),
     "stmp_version": (c_char_p, []),
     "stmp_launch_count": (c_int64, []),
+    "stmp_path_counters": (c_int, [_P, _P, c_int]),
 }
 
 _lib = None
@@ -115,6 +117,15 @@ def set_option(name: str, value: int):
 
 def launch_count() -> int:
     return int(lib().stmp_launch_count())
+
+
+def path_counters() -> dict:
+    """{kernel name: launches so far} -- lets tests and users assert which path (tcgen05 / FFMA / tiled) served a call."""
+    n = 96
+    names = (c_char_p * n)()
+    counts = (c_int64 * n)()
+    k = lib().stmp_path_counters(ctypes.cast(names, c_void_p), ctypes.cast(counts, c_void_p), n)
+    return {names[i].decode(): int(counts[i]) for i in range(min(k, n))}
 
 
 def ptr(t):

@@ -15,6 +15,9 @@ char* err_buf();
 int set_error(int code, const char* fmt, ...);
 extern std::atomic<long long> g_launches;
 inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+// per-kernel launch counters ("which path served this call"): a call site registers its kernel name once and then bumps its slot
+int path_slot(const char* name);
+void count_path(int slot);
 
 #define STMP_CUDA_OK(expr)                                                                    \
   do {                                                                                        \
@@ -30,6 +33,8 @@ inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_
     if (_e != cudaSuccess)                                                                    \
       return stmp::set_error(STMP_ECUDA, "launch of %s failed: %s", name, cudaGetErrorString(_e)); \
     stmp::count_launch();                                                                     \
+    static const int _path_slot = stmp::path_slot(name);                                      \
+    stmp::count_path(_path_slot);                                                             \
   } while (0)
 
 #define STMP_REQUIRE(cond, code, ...)                      \

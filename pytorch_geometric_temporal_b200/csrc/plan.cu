@@ -12,6 +12,9 @@
 #include <cmath>
 #include <vector>
 
+#include <cstring>
+#include <mutex>
+
 #include "common.cuh"
 #include "dcrnn_common.cuh"
 
@@ -21,6 +24,25 @@ namespace stmp {
 // error plumbing
 // ---------------------------------------------------------------------------------------------------------
 std::atomic<long long> g_launches{0};
+
+// ---- per-kernel launch counters (stmp_path_counters) ----------------------------------------------------
+constexpr int kMaxPaths = 96;
+static const char* g_path_names[kMaxPaths];
+static std::atomic<long long> g_path_counts[kMaxPaths];
+static std::atomic<int> g_n_paths{0};
+static std::mutex g_path_mu;
+int path_slot(const char* name) {
+  std::lock_guard<std::mutex> lk(g_path_mu);
+  const int n = g_n_paths.load();
+  for (int i = 0; i < n; ++i)
+    if (strcmp(g_path_names[i], name) == 0) return i;
+  if (n >= kMaxPaths) return kMaxPaths - 1;
+  g_path_names[n] = name;
+  g_path_counts[n].store(0);
+  g_n_paths.store(n + 1);
+  return n;
+}
+void count_path(int slot) { g_path_counts[slot].fetch_add(1, std::memory_order_relaxed); }
 
 char* err_buf() {
   static thread_local char buf[512] = {0};
@@ -186,10 +208,14 @@ __global__ void k_laplacian_vals(int e2, int n, int normalization, const int* __
 }
 
 // w_hat = 2*w/lam ; inf -> 0 ; (cheb) loops -= 1.  lam read from device memory.
-__global__ void k_scale_lambda(int nnz, int e2, const float* __restrict__ lam, int sub_loops, float* __restrict__ val) {
+// lam_node (nullable): per-node lambda_max = lambda_max[batch[node]] of a multi-graph mini-batch; the entry's lambda is the one
+// of its ROW node (PyG: lambda_max[batch[edge_index[0]]] on the get_laplacian list; loop entry k >= e2 has row (k - e2) % n).
+__global__ void k_scale_lambda(int nnz, int e2, const float* __restrict__ lam, int sub_loops, float* __restrict__ val,
+                               const float* __restrict__ lam_node = nullptr, const int* __restrict__ r2 = nullptr, int n = 1) {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= nnz) return;
-  float v = __fdiv_rn(__fmul_rn(2.0f, val[k]), *lam);
+  const float l = lam_node ? lam_node[k < e2 ? r2[k] : (k - e2) % n] : *lam;
+  float v = __fdiv_rn(__fmul_rn(2.0f, val[k]), l);
   if (v == INFINITY) v = 0.f;  // masked_fill_(== inf): only +inf
   if (sub_loops && k >= e2) v = __fsub_rn(v, 1.0f);
   val[k] = v;
@@ -444,15 +470,16 @@ int laplacian(Builder& b, int n, int e, const int* row, const int* col, const fl
   return 0;
 }
 
-int build_cheb(Builder& b, stmp_plan* p, int n, int e, const int* row, const int* col, const float* w, float lambda_max) {
+int build_cheb(Builder& b, stmp_plan* p, int n, int e, const int* row, const int* col, const float* w, float lambda_max,
+               const float* lam_node = nullptr) {
   int *r2, *c2, e2, r;
   float* val;
   if ((r = laplacian(b, n, e, row, col, w, p->normalization, 0, &r2, &c2, &val, &e2))) return r;
   int nnz = e2 + n;
   float* d_lam = b.talloc<float>(1);
   if (!d_lam) return b.rc;
-  if (lambda_max > 0.f) {
-    k_set<<<1, 1, 0, b.st>>>(d_lam, lambda_max);
+  if (lambda_max > 0.f || lam_node) {
+    k_set<<<1, 1, 0, b.st>>>(d_lam, lam_node ? 0.f : lambda_max);
     STMP_LAUNCH_OK("k_set");
   } else {
     // current PyG: lambda_max = 2 * edge_weight.max()   
@@ -465,7 +492,7 @@ int build_cheb(Builder& b, stmp_plan* p, int n, int e, const int* row, const int
     k_times2<<<1, 1, 0, b.st>>>(d_lam);
     STMP_LAUNCH_OK("k_times2");
   }
-  k_scale_lambda<<<blocks_for(nnz), kThreads, 0, b.st>>>(nnz, e2, d_lam, 1, val);
+  k_scale_lambda<<<blocks_for(nnz), kThreads, 0, b.st>>>(nnz, e2, d_lam, 1, val, lam_node, r2, n);
   STMP_LAUNCH_OK("k_scale_lambda");
   STMP_CUDA_OK(cudaMemcpyAsync(&p->lambda_max, d_lam, sizeof(float), cudaMemcpyDeviceToHost, b.st));
   int* dst = b.talloc<int>(nnz);
@@ -478,7 +505,8 @@ int build_cheb(Builder& b, stmp_plan* p, int n, int e, const int* row, const int
   return 0;
 }
 
-int build_cheb_att(Builder& b, stmp_plan* p, int n, int e, const int* row, const int* col, const float* w, float lambda_max) {
+int build_cheb_att(Builder& b, stmp_plan* p, int n, int e, const int* row, const int* col, const float* w, float lambda_max,
+                   const float* lam_node = nullptr) {
   int *r2, *c2, e2, r;
   float* val;
   if ((r = laplacian(b, n, e, row, col, w, p->normalization, 1, &r2, &c2, &val, &e2))) return r;
@@ -489,7 +517,7 @@ int build_cheb_att(Builder& b, stmp_plan* p, int n, int e, const int* row, const
   p->lambda_max = lam;
   k_set<<<1, 1, 0, b.st>>>(d_lam, lam);
   STMP_LAUNCH_OK("k_set");
-  k_scale_lambda<<<blocks_for(e2 + n), kThreads, 0, b.st>>>(e2 + n, e2, d_lam, 0, val);
+  k_scale_lambda<<<blocks_for(e2 + n), kThreads, 0, b.st>>>(e2 + n, e2, d_lam, 0, val, lam_node, r2, n);
   STMP_LAUNCH_OK("k_scale_lambda");
   k_fill_tail<<<blocks_for(n), kThreads, 0, b.st>>>(e2 + n, n, -1.0f, val);  // add_self_loops(fill=-1)  astgcn.py:104-106
   STMP_LAUNCH_OK("k_fill_tail");
@@ -607,9 +635,28 @@ void free_csr(Csr& c) {
 
 using namespace stmp;
 
+static int plan_create_impl(int flavor, int64_t num_nodes, int64_t num_edges, const int64_t* edge_index,
+                            const float* edge_weight, int normalization, float lambda_max, const float* lambda_node,
+                            uint32_t flags, void* stream, stmp_plan** out);
+
 extern "C" int stmp_plan_create(int flavor, int64_t num_nodes, int64_t num_edges, const int64_t* edge_index,
                                 const float* edge_weight, int normalization, float lambda_max, uint32_t flags,
                                 void* stream, stmp_plan** out) {
+  return plan_create_impl(flavor, num_nodes, num_edges, edge_index, edge_weight, normalization, lambda_max, nullptr, flags, stream, out);
+}
+
+extern "C" int stmp_plan_create_pergraph(int flavor, int64_t num_nodes, int64_t num_edges, const int64_t* edge_index,
+                                         const float* edge_weight, int normalization, const float* lambda_node, uint32_t flags,
+                                         void* stream, stmp_plan** out) {
+  STMP_REQUIRE(lambda_node != nullptr, STMP_EINVAL, "stmp_plan_create_pergraph: lambda_node is NULL");
+  STMP_REQUIRE(flavor == STMP_FLAVOR_CHEB || flavor == STMP_FLAVOR_CHEB_ATT, STMP_EINVAL,
+               "per-graph lambda_max applies to the Chebyshev flavors only (got flavor %d)", flavor);
+  return plan_create_impl(flavor, num_nodes, num_edges, edge_index, edge_weight, normalization, 0.f, lambda_node, flags, stream, out);
+}
+
+static int plan_create_impl(int flavor, int64_t num_nodes, int64_t num_edges, const int64_t* edge_index,
+                            const float* edge_weight, int normalization, float lambda_max, const float* lambda_node,
+                            uint32_t flags, void* stream, stmp_plan** out) {
   STMP_REQUIRE(out != nullptr, STMP_EINVAL, "stmp_plan_create: out is NULL");
   *out = nullptr;
   STMP_REQUIRE(flavor >= STMP_FLAVOR_DCONV && flavor <= STMP_FLAVOR_CHEB_ATT, STMP_EINVAL, "unknown flavor %d", flavor);
@@ -645,9 +692,9 @@ extern "C" int stmp_plan_create(int flavor, int64_t num_nodes, int64_t num_edges
     }
     switch (flavor) {
       case STMP_FLAVOR_DCONV: rc = build_dconv(b, p, n, e, row, col, edge_weight); break;
-      case STMP_FLAVOR_CHEB: rc = build_cheb(b, p, n, e, row, col, edge_weight, lambda_max); break;
+      case STMP_FLAVOR_CHEB: rc = build_cheb(b, p, n, e, row, col, edge_weight, lambda_max, lambda_node); break;
       case STMP_FLAVOR_GCN: rc = build_gcn(b, p, n, e, row, col, edge_weight); break;
-      case STMP_FLAVOR_CHEB_ATT: rc = build_cheb_att(b, p, n, e, row, col, edge_weight, lambda_max); break;
+      case STMP_FLAVOR_CHEB_ATT: rc = build_cheb_att(b, p, n, e, row, col, edge_weight, lambda_max, lambda_node); break;
     }
     if (rc) break;
     Info h;
@@ -710,3 +757,11 @@ extern "C" int stmp_plan_export(const stmp_plan* p, int op, int transposed, int3
 extern "C" const char* stmp_last_error(void) { return err_buf(); }
 extern "C" const char* stmp_version(void) { return "stmp 0.1.0 sm_100a"; }
 extern "C" int64_t stmp_launch_count(void) { return g_launches.load(); }
+extern "C" int stmp_path_counters(const char** names, int64_t* counts, int max_entries) {
+  const int n = stmp::g_n_paths.load();
+  for (int i = 0; i < n && i < max_entries; ++i) {
+    if (names) names[i] = stmp::g_path_names[i];
+    if (counts) counts[i] = stmp::g_path_counts[i].load();
+  }
+  return n;
+}

@@ -1,7 +1,7 @@
 """ChickenpoxDatasetLoader -- offline drop-in for dataset/chickenpox.py (:13-132).  The reference
-downloads chickenpox.json (:32-38); this loader reads the same content from a local .npz/.json
-(tests/golden/chickenpox.npz is generated from the reference's in-tree dataset/chickenpox.json by
-tests/golden/make_goldens.py).  20 nodes, 102 edges (weights 1), FX (521,20)."""
+downloads chickenpox.json (:32-38); this loader reads the same content from the .npz shipped inside the
+package (dataset/data/chickenpox.npz: the dataset's `edges` and `FX` arrays re-encoded by
+tests/golden/make_goldens.py) or from a user-supplied .npz/.json.  20 nodes, 102 edges (weights 1), FX (521,20)."""
 import json
 import os
 
@@ -10,8 +10,7 @@ import torch
 
 from ..signal import StaticGraphTemporalSignal, IndexDataset
 
-_DEFAULT = os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))),
-                        "tests", "golden", "chickenpox.npz")
+_DEFAULT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "chickenpox.npz")
 
 
 class ChickenpoxDatasetLoader(object):

@@ -51,12 +51,28 @@ class FlatGradSync(object):
         n = sum(p.numel() for p in self.params)
         self.flat = torch.zeros(n, device=dev, dtype=dt)
         self.average = average
+        self._offsets = []
         off = 0
         for p in self.params:
             if p.device != dev or p.dtype != dt:
                 raise ValueError("all parameters must share device and dtype")
             p.grad = self.flat[off:off + p.numel()].view_as(p)  # autograd accumulates in place into the view
+            self._offsets.append(off)
             off += p.numel()
+
+    def _check_aliasing(self):
+        """`optimizer.zero_grad()` / `module.zero_grad()` default to set_to_none=True, which drops the views into the flat
+        buffer: autograd would then allocate fresh gradients and the collective would reduce a stale buffer.  Gradients
+        found outside the buffer are copied in and re-attached (use `sync.zero()` instead of zero_grad())."""
+        base, es = self.flat.data_ptr(), self.flat.element_size()
+        for p, off in zip(self.params, self._offsets):
+            view = self.flat[off:off + p.numel()].view_as(p)
+            if p.grad is None:
+                view.zero_()
+                p.grad = view
+            elif p.grad.data_ptr() != base + off * es:
+                view.copy_(p.grad)
+                p.grad = view
 
     @property
     def nbytes(self) -> int:
@@ -64,6 +80,7 @@ class FlatGradSync(object):
 
     def all_reduce(self, async_op: bool = False):
         """ONE collective for the whole model; grads become the mean over ranks (DDP semantics)."""
+        self._check_aliasing()
         w = world_size()
         if w == 1:
             return None

@@ -75,7 +75,9 @@ class ChebConvAttention(nn.Module):
         if self._bias is not None:
             nn.init.uniform_(self._bias)
 
-    def _plan(self, edge_index, edge_weight, num_nodes, lambda_max):
+    def _plan(self, edge_index, edge_weight, num_nodes, lambda_max, batch=None):
+        if batch is not None and torch.is_tensor(lambda_max) and lambda_max.numel() > 1:     # astgcn.py:98-99
+            return self._plans.get(_lib.FLAVOR_CHEB_ATT, edge_index, edge_weight, num_nodes, self._normalization, lambda_max, batch=batch)
         lam = None if lambda_max is None else float(lambda_max)
         return self._plans.get(_lib.FLAVOR_CHEB_ATT, edge_index, edge_weight, num_nodes, self._normalization, lam)
 
@@ -85,11 +87,10 @@ class ChebConvAttention(nn.Module):
         spatial_attention (B,N,N) -> (B,N,[T,]Fout)."""
         if self._normalization != "sym" and lambda_max is None:
             raise ValueError("You need to pass `lambda_max` to `forward() in`case the normalization is non-symmetric.")
-        if batch is not None:
-            raise ValueError("multi-graph mini-batches (`batch`) are not supported by the static-graph engine")
         _require_cuda(x, "x")
         B, N = x.shape[0], x.shape[1]
-        plan = self._plan(edge_index, edge_weight, N, lambda_max)
+        # `batch` (node -> graph id of a multi-graph mini-batch) only selects the per-graph lambda_max (astgcn.py:98-99)
+        plan = self._plan(edge_index, edge_weight, N, lambda_max, batch)
         xs = x.reshape(B, N, -1)                                    # timesteps folded into the feature axis
         S = spatial_attention.contiguous()
         T0 = torch.diagonal(S, dim1=1, dim2=2).unsqueeze(-1) * xs   # (I*S)^T @ x            :160-165

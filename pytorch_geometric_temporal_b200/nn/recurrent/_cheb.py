@@ -43,8 +43,8 @@ class ChebParams(torch.nn.Module):
 
 class ChebPlanMixin:
     """lambda_max semantics of PyG ChebConv (current): None => 2*max(w_hat) (computed on the device
-    inside the plan); a scalar/0-d tensor => used as is.  Per-graph lambda_max vectors need the `batch`
-    vector of multi-graph mini-batches and are rejected."""
+    inside the plan); a scalar/0-d tensor => used as is; a per-graph vector together with the node->graph
+    `batch` vector of a multi-graph mini-batch => `lambda_max[batch[edge_index[0]]]` inside the plan."""
 
     def _init_plans(self):
         self._plans = PlanCache()
@@ -66,9 +66,11 @@ class ChebPlanMixin:
             return hit[0]
         return float(lambda_max)
 
-    def _cheb_plan(self, edge_index, edge_weight, num_nodes, normalization, lambda_max):
+    def _cheb_plan(self, edge_index, edge_weight, num_nodes, normalization, lambda_max, batch=None):
         if normalization not in (None, "sym", "rw"):
             raise AssertionError("Invalid normalization")
+        if batch is not None and torch.is_tensor(lambda_max) and lambda_max.numel() > 1:
+            return self._plans.get(_lib.FLAVOR_CHEB, edge_index, edge_weight, num_nodes, normalization, lambda_max, batch=batch)
         return self._plans.get(_lib.FLAVOR_CHEB, edge_index, edge_weight, num_nodes, normalization,
                                self._lambda_value(lambda_max))
 
@@ -96,10 +98,8 @@ class ChebConv(ChebParams, ChebPlanMixin):
         self._init_plans()
 
     def forward(self, x, edge_index, edge_weight=None, batch=None, lambda_max=None):
-        if batch is not None:
-            raise ValueError("multi-graph `batch` vectors are not supported; pass (B,N,F) instead")
         if self.K > 1:
-            plan = self._cheb_plan(edge_index, edge_weight, x.size(-2), self.normalization, lambda_max)
+            plan = self._cheb_plan(edge_index, edge_weight, x.size(-2), self.normalization, lambda_max, batch)
             S = torch.cat(cheb_basis(plan, x, self.K), dim=-1)
         else:
             S = x                                                        # K=1: no propagation at all

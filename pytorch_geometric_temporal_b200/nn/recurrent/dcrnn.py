@@ -103,7 +103,8 @@ class _DcrnnSeqFn(torch.autograd.Function):
     def forward(ctx, X, H0, wz, wr, wh, bz, br, bh, plan, K, wimage):
         out, stash = ops.dcrnn_seq_fwd(plan, X, wz, wr, wh, bz, br, bh, K, h0=H0, stash=True, wimage=wimage)
         ctx.plan, ctx.K, ctx.has_bias, ctx.has_h0 = plan, K, bz is not None, H0 is not None
-        ctx.save_for_backward(X, H0, wz, wr, wh, out, stash)
+        # the backward kernels address X / dX as dense (B,T,N,Cin): keep the contiguous copy the forward kernel read
+        ctx.save_for_backward(X.contiguous(), H0, wz, wr, wh, out, stash)
         return out
 
     @staticmethod
@@ -128,7 +129,7 @@ class _DcrnnSeqFn(torch.autograd.Function):
             S2 = torch.empty(T * B, N, nb * C, **f32)
             dph_all = torch.empty(T, B, N, Co, **f32)
             dpzr_all = torch.empty(T, B, N, 2 * Co, **f32)
-            dX = torch.empty_like(X) if ctx.needs_input_grad[0] else None
+            dX = torch.empty(X.shape, **f32) if ctx.needs_input_grad[0] else None   # dense: the kernels write (B,T,N,Cin) row-major
             dH0 = torch.empty(B, N, Co, **f32)
             # the bases depend only on forward results, the recurrence only on gout: run them side by side -- the
             # recurrence occupies one SM per window (64 of 148 at the reference's batch size), the basis kernel fills the
@@ -171,7 +172,7 @@ class _DcrnnSeqFn(torch.autograd.Function):
         buf2 = torch.empty(B, N, nb * C, **f32)                                            # dL/dS2 -> (in place) dL/d[X | H*R]
         buf1 = torch.empty(B, N, nb * C, **f32)                                            # dL/dS1 -> (in place) dL/d[X | H_{t-1}]
         g = torch.empty(B, N, Co, **f32)
-        dX = torch.empty_like(X) if ctx.needs_input_grad[0] else None
+        dX = torch.empty(X.shape, **f32) if ctx.needs_input_grad[0] else None   # dense: the kernels write (B,T,N,Cin) row-major
 
         def adjoint_inplace(buf):
             """columns [0,C) of buf <- adjoint of U -> [U | P_o U | P_i U | 2 P_o T_1o - U | ..] applied to buf."""
@@ -384,7 +385,10 @@ class BatchedDCRNN(DCRNN):
         _require_cuda(series, "series")
         plan = self._plan(edge_index, edge_weight, series.size(1))
         if not self._needs_grad(series) and ops.dcrnn_seq_supported(plan, self.in_channels, self.out_channels, self.K):
-            return ops.dcrnn_seq_fwd(plan, series, *self._params(), self.K, win_start=win_start, horizon=horizon,
-                                     wimage=self._weight_image())
+            try:
+                return ops.dcrnn_seq_fwd(plan, series, *self._params(), self.K, win_start=win_start, horizon=horizon,
+                                         wimage=self._weight_image())
+            except _lib.StmpUnsupported:      # e.g. a horizon whose shared-memory layout the FFMA kernel cannot hold
+                pass
         X = ops.window_gather(series, win_start, horizon, with_target=False)
         return self.forward(X, edge_index, edge_weight)

@@ -22,7 +22,8 @@ def _require_cuda(t: torch.Tensor, name: str):
 
 class GraphPlan:
     def __init__(self, flavor: int, edge_index: torch.Tensor, edge_weight: Optional[torch.Tensor], num_nodes: int,
-                 normalization=None, lambda_max: Optional[float] = None, flags: int = 0):
+                 normalization=None, lambda_max: Optional[float] = None, flags: int = 0,
+                 lambda_node: Optional[torch.Tensor] = None):
         _require_cuda(edge_index, "edge_index")
         if edge_index.dim() != 2 or edge_index.size(0) != 2:
             raise ValueError(f"edge_index must have shape [2, E], got {tuple(edge_index.shape)}")
@@ -40,9 +41,17 @@ class GraphPlan:
         self._h = ctypes.c_void_p()
         lam = -1.0 if lambda_max is None else float(lambda_max)
         with torch.cuda.device(ei.device):
-            rc = _lib.lib().stmp_plan_create(flavor, self.num_nodes, self.num_edges, _lib.ptr(ei), _lib.ptr(ew),
-                                             _lib.NORM_CODE[normalization], lam, flags, _lib.stream_ptr(),
-                                             ctypes.byref(self._h))
+            if lambda_node is not None:      # per-graph lambda_max of a multi-graph mini-batch, already expanded to nodes
+                ln = lambda_node.detach().to(device=ei.device, dtype=torch.float32).contiguous()
+                if ln.numel() != self.num_nodes:
+                    raise RuntimeError(f"lambda_max[batch] has {ln.numel()} entries for {self.num_nodes} nodes")
+                rc = _lib.lib().stmp_plan_create_pergraph(flavor, self.num_nodes, self.num_edges, _lib.ptr(ei), _lib.ptr(ew),
+                                                          _lib.NORM_CODE[normalization], _lib.ptr(ln), flags, _lib.stream_ptr(),
+                                                          ctypes.byref(self._h))
+            else:
+                rc = _lib.lib().stmp_plan_create(flavor, self.num_nodes, self.num_edges, _lib.ptr(ei), _lib.ptr(ew),
+                                                 _lib.NORM_CODE[normalization], lam, flags, _lib.stream_ptr(),
+                                                 ctypes.byref(self._h))
         _lib.check(rc)
         self.n_ops = _lib.lib().stmp_plan_num_ops(self._h)
 
@@ -86,17 +95,25 @@ class PlanCache:
     def _tkey(t):
         return None if t is None else (t.data_ptr(), t._version, tuple(t.shape), t.dtype, t.device)
 
-    def get(self, flavor, edge_index, edge_weight, num_nodes, normalization=None, lambda_max=None, flags=0) -> GraphPlan:
-        lam = None
+    def get(self, flavor, edge_index, edge_weight, num_nodes, normalization=None, lambda_max=None, flags=0, batch=None) -> GraphPlan:
+        """`lambda_max`: None, a host scalar / 0-d tensor, or -- with the node->graph vector `batch` -- one value per graph
+        (PyG: `lambda_max[batch[edge_index[0]]]`)."""
+        lam, lam_node, extra = None, None, ()
         if lambda_max is not None:
-            lam = float(lambda_max)  # scalar lambda_max (host value or 0-d tensor; a sync only if it is a tensor)
-        key = (flavor, self._tkey(edge_index), self._tkey(edge_weight), int(num_nodes), normalization, lam, flags)
+            if torch.is_tensor(lambda_max) and lambda_max.numel() > 1:
+                if batch is None:
+                    raise ValueError("a lambda_max vector needs the `batch` vector of the mini-batch (one graph id per node)")
+                lam_node = lambda_max.to(torch.float32)[batch]
+                extra = (self._tkey(lambda_max), self._tkey(batch))
+            else:
+                lam = float(lambda_max)  # scalar lambda_max (host value or 0-d tensor; a sync only if it is a tensor)
+        key = (flavor, self._tkey(edge_index), self._tkey(edge_weight), int(num_nodes), normalization, lam, flags) + extra
         hit = self._entries.get(key)
         if hit is not None:
             return hit[0]
-        plan = GraphPlan(flavor, edge_index, edge_weight, num_nodes, normalization, lam, flags)
+        plan = GraphPlan(flavor, edge_index, edge_weight, num_nodes, normalization, lam, flags, lambda_node=lam_node)
         if len(self._entries) >= self._max:
             self._entries.pop(next(iter(self._entries)))
         # keep the keyed tensors alive so their addresses cannot be recycled while the entry exists
-        self._entries[key] = (plan, edge_index, edge_weight)
+        self._entries[key] = (plan, edge_index, edge_weight, lambda_max if extra else None, batch if extra else None)
         return plan

@@ -13,6 +13,8 @@ A changing `edge_index` means a fresh tensor per snapshot, so the layers' plan c
 rebuilt on the device for each snapshot (`stmp_plan_create`: ~30 small launches, no host round trip).  Snapshots of
 one signal that reuse the same numpy array object for their edges (common: piecewise-constant graphs) share the
 converted tensor, and therefore the plan."""
+import collections
+import zlib
 from typing import Sequence, Union
 
 import numpy as np
@@ -41,7 +43,7 @@ class _DynamicSignal(object):
         lengths |= {len(getattr(self, k)) for k in self.additional_feature_keys}
         assert len(lengths) == 1, "Temporal dimension inconsistency."
         self.snapshot_count = len(self.targets)
-        self._converted = {}     # id(numpy array) -> (array, tensor): static fields and re-used per-snapshot arrays convert once
+        self._converted = collections.OrderedDict()     # id(numpy array) -> (array, tensor): static fields and re-used per-snapshot arrays convert once
         self.t = 0
 
     def _place(self, tensor):
@@ -53,14 +55,18 @@ class _DynamicSignal(object):
         if array is None:
             return None
         if share:
-            hit = self._converted.get(id(array))
+            # keyed on identity AND content: a caller may refill an edge buffer in place between snapshots (the reference
+            # re-wraps the array on every __getitem__), so a stale tensor / plan must never be returned
+            ck = (id(array), getattr(array, "shape", None), zlib.crc32(memoryview(np.ascontiguousarray(array)).cast("B")))
+            hit = self._converted.get(ck)
             if hit is not None and hit[0] is array:
+                self._converted.move_to_end(ck)
                 return hit[1]
         t = self._place(_as_tensor(array, _FORCED.get(key)))
         if share:
-            if len(self._converted) > 4096:
-                self._converted.clear()
-            self._converted[id(array)] = (array, t)
+            self._converted[ck] = (array, t)
+            while len(self._converted) > 64:            # small LRU: bounds the device tensors a signal pins
+                self._converted.popitem(last=False)
         return t
 
     def _snapshot(self, t: int) -> Data:

@@ -95,8 +95,24 @@ class IndexBatchLoader(object):
         return shard_indices(len(self.indices), self.world_size, self.rank, self.shuffle, self.seed, self.epoch)
 
     def __len__(self):
-        n = len(self._positions())
+        if self.world_size > 1:
+            n = math.ceil(len(self.indices) / self.world_size)     # DistributedSampler pads every shard to this length
+        else:
+            n = len(self.indices)
         return n // self.batch_size if self.drop_last else math.ceil(n / self.batch_size)
+
+    def host_batches(self):
+        """Host-side iteration: pinned int64 window-start tensors, one per batch (what a `DevicePrefetcher` ships to the
+        GPU -- B x 8 bytes per step instead of the B x h x N x F windows themselves)."""
+        pos = self._positions()
+        starts = torch.from_numpy(self.indices[pos])
+        if torch.cuda.is_available():
+            starts = starts.pin_memory()
+        for s in range(0, starts.numel(), self.batch_size):
+            st = starts[s:s + self.batch_size]
+            if self.drop_last and st.numel() < self.batch_size:
+                break
+            yield st
 
     def __iter__(self):
         pos = self._positions()
@@ -134,7 +150,9 @@ class DevicePrefetcher(object):
         self.next = None
         self._preload()
 
-    def _to_dev(self, t, pos):
+    def _staging(self, t, pos):
+        """Staging buffer of the current slot for tensor position `pos` (allocated on the CONSUMER's stream, so the
+        caching allocator accounts it to the stream that reads it)."""
         key = (pos, tuple(t.shape), t.dtype)
         bank = self.bufs[self.slot]
         if bank is None:
@@ -142,7 +160,6 @@ class DevicePrefetcher(object):
         buf = bank.get(key)
         if buf is None:
             buf = bank[key] = torch.empty(t.shape, dtype=t.dtype, device=self.device)
-        buf.copy_(t, non_blocking=True)
         return buf
 
     def _preload(self):
@@ -151,13 +168,16 @@ class DevicePrefetcher(object):
         except StopIteration:
             self.next = None
             return
+        tensors = (batch,) if torch.is_tensor(batch) else tuple(batch)
+        cur = torch.cuda.current_stream(self.device)          # the consumer's stream -- taken BEFORE switching streams
+        bufs = tuple(self._staging(t, i) for i, t in enumerate(tensors))
+        # the staging buffers of this slot were last read two batches ago by kernels already enqueued on the consumer's
+        # stream: the copy that overwrites them must wait for everything enqueued there so far
+        self.copy_stream.wait_stream(cur)
         with torch.cuda.stream(self.copy_stream):
-            # the staging buffer of this slot was last read two batches ago on the compute stream
-            self.copy_stream.wait_stream(torch.cuda.current_stream(self.device))
-            if torch.is_tensor(batch):
-                self.next = self._to_dev(batch, 0)
-            else:
-                self.next = tuple(self._to_dev(t, i) for i, t in enumerate(batch))
+            for buf, t in zip(bufs, tensors):
+                buf.copy_(t, non_blocking=True)
+        self.next = bufs[0] if torch.is_tensor(batch) else bufs
         self.slot ^= 1
 
     def __iter__(self):

@@ -163,9 +163,11 @@ def main():
     # ---- chickenpox fixture (in-tree JSON of the reference, dataset/chickenpox.json) -> npz ------------------
     with open(os.path.join(refload.REFERENCE_ROOT, "dataset", "chickenpox.json")) as f:
         d = json.load(f)
-    np.savez_compressed(os.path.join(OUT, "chickenpox.npz"), edges=np.array(d["edges"], dtype=np.int64),
+    pkg_data = os.path.join(os.path.dirname(os.path.dirname(OUT)), "pytorch_geometric_temporal_b200", "dataset", "data")
+    os.makedirs(pkg_data, exist_ok=True)       # the dataset ships INSIDE the package (ChickenpoxDatasetLoader's default)
+    np.savez_compressed(os.path.join(pkg_data, "chickenpox.npz"), edges=np.array(d["edges"], dtype=np.int64),
                         FX=np.array(d["FX"], dtype=np.float64))
-    print("chickenpox.npz", os.path.getsize(os.path.join(OUT, "chickenpox.npz")) // 1024, "KB")
+    print("chickenpox.npz", os.path.getsize(os.path.join(pkg_data, "chickenpox.npz")) // 1024, "KB")
 
 
 if __name__ == "__main__":

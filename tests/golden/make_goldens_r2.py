@@ -1,0 +1,53 @@
+"""Round-2 golden vectors from the UNMODIFIED reference modules (same mechanism as make_goldens.py: /root/reference imported
+through oracle/refload.py on top of oracle/stubs).  Run in the build container only:  python tests/golden/make_goldens_r2.py [name ...]
+
+* dcrnn_cfg2_grads   -- BatchedDCRNN(2,32,K=2) at the METR-LA shape: output AND autograd gradients (input + parameters)
+* a3tgcn2_cfg3       -- A3TGCN2(2,32,12,B) at the PEMS-BAY shape (325 nodes), all rows, with and without an incoming H
+* astgcn_cfg4        -- ASTGCN(3 blocks, K=3, 64/64 filters) at the PeMS04 shape (307 nodes, B=32 rows subsampled to keep the
+                        file small: the model is row-independent, so B rows of the reference output are exact for those rows)
+* gconv_lstm_cfg5seq -- GConvLSTM(64,64,K=3) 12-step recurrence on a 2 000-node slice-shaped graph (CPU-tractable) + grads
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import refload, pyg  # noqa: E402
+from pytorch_geometric_temporal_b200.dataset import synthetic  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def save(name, **kw):
+    torch.save(kw, os.path.join(OUT, name + ".pt"))
+    print(f"{name}.pt  {os.path.getsize(os.path.join(OUT, name + '.pt')) / 1024:.0f} KB")
+
+
+def sd(m):
+    return {k: v.detach().clone() for k, v in m.state_dict().items()}
+
+
+def dcrnn_cfg2_grads():
+    dc = refload.load("nn.recurrent.dcrnn")
+    ei, ew, series = synthetic.metr_la_like(seed=0, t_total=64)
+    ei_t, ew_t = torch.from_numpy(ei), torch.from_numpy(ew)
+    torch.manual_seed(0)
+    m = dc.BatchedDCRNN(2, 32, 2)
+    X = torch.from_numpy(np.stack([series[3:15], series[20:32], series[41:53]])).clone().requires_grad_(True)  # (3,12,207,2)
+    out = m(X, ei_t, ew_t)
+    w = torch.linspace(-1, 1, out.numel()).view_as(out)
+    (out * w).sum().backward()
+    save("dcrnn_cfg2_grads", edge_index=ei_t, edge_weight=ew_t, X=X.detach(), state=sd(m), out=out.detach(), gX=X.grad.clone(),
+         grads={k: p.grad.detach().clone() for k, p in m.named_parameters()}, K=2)
+
+
+GENERATORS = {"dcrnn_cfg2_grads": dcrnn_cfg2_grads}
+
+
+if __name__ == "__main__":
+    names = sys.argv[1:] or list(GENERATORS)
+    for n in names:
+        GENERATORS[n]()

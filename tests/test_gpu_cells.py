@@ -150,6 +150,48 @@ def test_chebconv_attention_errors_and_repr():
         ChebConvAttention(2, 3, 3, "bogus")
 
 
+@pytest.mark.parametrize("norm", ["sym", None, "rw"])
+def test_chebconv_attention_per_graph_lambda_max_vs_oracle(norm):
+    """Multi-graph mini-batch: node->graph `batch` vector + one lambda_max per graph (test/attention_test.py:205-218;
+    astgcn.py:98-99) -> stmp_plan_create_pergraph."""
+    from oracle import attention as A
+    torch.manual_seed(0)
+    conv = ChebConvAttention(5, 7, K=3, normalization=norm)
+    batch = torch.tensor([0, 0, 0, 1, 1, 1, 1])
+    ei = torch.tensor([[0, 1, 1, 2, 3, 4, 5, 6, 3, 6], [1, 0, 2, 1, 4, 3, 6, 5, 6, 3]])
+    ew = torch.rand(ei.size(1)) + 0.1
+    x, S = torch.randn(3, 7, 5), torch.softmax(torch.rand(3, 7, 7), dim=1)
+    lam = torch.tensor([2.0, 3.0])
+    with torch.no_grad():
+        want = A.cheb_conv_attention(conv.state_dict(), x, ei, S, norm, ew, lam, batch)
+        want4 = A.cheb_conv_attention(conv.state_dict(), x, ei, S, norm, ew, torch.tensor(2.0), batch) if norm == "sym" else None
+        m = conv.to(DEV)
+        got = m(x.to(DEV), ei.to(DEV), S.to(DEV), ew.to(DEV), batch.to(DEV), lam.to(DEV))
+        _close(got, want)
+        if norm == "sym":                      # `batch` without lambda_max: the default 2.0 for every graph (out4 of the reference test)
+            _close(m(x.to(DEV), ei.to(DEV), S.to(DEV), ew.to(DEV), batch.to(DEV)), want4)
+
+
+def test_chebconv_layer_per_graph_lambda_max_vs_oracle():
+    """PyG ChebConv with `batch` + lambda_max vector (`lambda_max[batch[edge_index[0]]]`)."""
+    from oracle import pyg
+    from pytorch_geometric_temporal_b200.nn.recurrent._cheb import ChebConv
+    torch.manual_seed(0)
+    batch = torch.tensor([0, 0, 0, 1, 1, 1, 1])
+    ei = torch.tensor([[0, 1, 1, 2, 3, 4, 5, 6, 3, 6], [1, 0, 2, 1, 4, 3, 6, 5, 6, 3]])
+    ew = torch.rand(ei.size(1)) + 0.1
+    x = torch.randn(7, 5)
+    lam = torch.tensor([2.0, 3.5])
+    for norm in ("sym", "rw", None):
+        conv = ChebConv(5, 6, 3, normalization=norm)
+        ref = pyg.ChebConv(5, 6, 3, normalization=norm)
+        ref.load_state_dict(conv.state_dict())
+        with torch.no_grad():
+            want = ref(x, ei, ew, batch, lam)
+            got = conv.to(DEV)(x.to(DEV), ei.to(DEV), ew.to(DEV), batch.to(DEV), lam.to(DEV))
+        _close(got, want)
+
+
 def test_astgcn_backward_runs_and_matches_oracle_grad(golden_dir):
     """Training path: gradients flow through the attention-weighted SpMM (stmp_spmm_att_grad)."""
     from oracle import attention as A

@@ -281,3 +281,67 @@ def test_training_backward_general_K_small_graph():
     _close(Xa.grad, Xb.grad.cpu(), 1e-3, 1e-5)
     for (k, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
         _close(pa.grad, pb.grad.cpu(), 1e-3, 1e-4)
+
+
+@pytest.mark.parametrize("fused_bwd", [True, False])
+def test_cfg2_training_gradients_vs_reference_golden(golden_dir, fused_bwd):
+    """cfg2 shape: output and ALL gradients (input + parameters) of the fused forward + hand-written backward against the
+    UNMODIFIED reference module's autograd (tests/golden/make_goldens_r2.py) -- not self-vs-self."""
+    from pytorch_geometric_temporal_b200.nn.recurrent.dcrnn import _DcrnnSeqFn
+    g = _load(golden_dir, "dcrnn_cfg2_grads")
+    m = BatchedDCRNN(2, 32, 2).to(DEV)
+    m.load_state_dict(g["state"])
+    X = g["X"].to(DEV).requires_grad_(True)
+    before = _lib.path_counters()
+    _DcrnnSeqFn.fused_backward = fused_bwd
+    try:
+        out = m(X, g["edge_index"].to(DEV), g["edge_weight"].to(DEV))
+        w = torch.linspace(-1, 1, out.numel(), device=DEV).view_as(out)
+        (out * w).sum().backward()
+    finally:
+        _DcrnnSeqFn.fused_backward = True
+    after = _lib.path_counters()
+    ran = {k for k, v in after.items() if v > before.get(k, 0)}
+    assert "k_dcrnn_seq_tc" in ran                                     # the tcgen05 forward served the training call
+    assert ("k_dcrnn_bwd_seq" in ran) == fused_bwd                     # and the persistent backward exactly when asked
+    _close(out, g["out"])
+    _close(X.grad, g["gX"], 1e-3, 1e-3 * g["gX"].abs().max().item())
+    for k, p in m.named_parameters():
+        ref = g["grads"][k]
+        _close(p.grad, ref, 1e-3, 1e-3 * ref.abs().max().item())
+
+
+def test_training_backward_with_permuted_input_requiring_grad():
+    """X handed in as a dense non-contiguous view (B,N,F,T).permute(0,3,1,2) with requires_grad: dX must come back in X's
+    index order (the kernels write dense (B,T,N,Cin) rows; a strided dX buffer would be scrambled)."""
+    ei, ew, series = synthetic.metr_la_like(1, 64)
+    ei_t, ew_t = torch.from_numpy(ei).to(DEV), torch.from_numpy(ew).to(DEV)
+    base = torch.from_numpy(series[:24]).reshape(2, 12, 207, 2).to(DEV)
+    torch.manual_seed(0)
+    m = BatchedDCRNN(2, 32, 2).to(DEV)
+    w = torch.randn(2, 12, 207, 32, device=DEV)
+    Xc = base.clone().requires_grad_(True)
+    (m(Xc, ei_t, ew_t) * w).sum().backward()
+    src = base.permute(0, 2, 3, 1).contiguous().requires_grad_(True)     # (B,N,F,T) storage
+    Xp = src.permute(0, 3, 1, 2)                                         # (B,T,N,F) view, not contiguous
+    assert not Xp.is_contiguous()
+    m.zero_grad()
+    (m(Xp, ei_t, ew_t) * w).sum().backward()
+    _close(src.grad.permute(0, 3, 1, 2), Xc.grad.cpu(), 1e-5, 1e-6)
+
+
+def test_path_counters_name_the_kernel_that_served_the_call():
+    ei, ew, series = synthetic.metr_la_like(0, 32)
+    ei_t, ew_t = torch.from_numpy(ei).to(DEV), torch.from_numpy(ew).to(DEV)
+    X = torch.from_numpy(series[:24]).reshape(2, 12, 207, 2).to(DEV)
+    m = BatchedDCRNN(2, 32, 2).to(DEV)
+    c0 = _lib.path_counters()
+    with torch.no_grad():
+        m(X, ei_t, ew_t)
+    c1 = _lib.path_counters()
+    assert c1.get("k_dcrnn_seq_tc", 0) == c0.get("k_dcrnn_seq_tc", 0) + 1
+    m3 = BatchedDCRNN(2, 16, 3).to(DEV)                       # K=3 / 16 hidden: the FFMA sequence kernel
+    with torch.no_grad():
+        m3(X, ei_t, ew_t)
+    c2 = _lib.path_counters()
+    assert c2.get("k_dcrnn_seq", 0) == c1.get("k_dcrnn_seq", 0) + 1 and c2["k_dcrnn_seq_tc"] == c1["k_dcrnn_seq_tc"]

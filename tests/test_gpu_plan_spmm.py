@@ -199,6 +199,42 @@ def test_window_gather_bit_exact():
     assert torch.equal(x[2].cpu(), series3[17:21]) and torch.equal(y[1].cpu(), series3[9:13])
 
 
+def test_device_prefetcher_slow_consumer_never_sees_a_torn_batch():
+    """The H2D copy of batch i+2 reuses the staging buffer of batch i: it must wait for the consumer kernels of batch i
+    (enqueued on the compute stream) -- checked with a consumer that is much slower than the copies and a host that runs
+    far ahead of the GPU."""
+    from pytorch_geometric_temporal_b200.signal import DevicePrefetcher
+    n, shape = 12, (1 << 20,)
+    host = [torch.full(shape, float(i)).pin_memory() for i in range(n)]
+    spin = torch.randn(2048, 2048, device=DEV)
+    sums = []
+    for i, xb in enumerate(DevicePrefetcher(iter(host), DEV)):
+        for _ in range(6):                      # slow consumer: several GEMMs enqueued before the batch is read
+            spin = torch.tanh(spin @ spin) * 0.5
+        sums.append((xb.sum(), xb.min(), xb.max()))      # reads the staging buffer late on the compute stream
+    torch.cuda.synchronize()
+    for i, (s, lo, hi) in enumerate(sums):
+        assert float(lo) == float(hi) == float(i), (i, float(lo), float(hi))
+        assert float(s) == float(i) * shape[0]
+
+
+def test_index_batch_loader_host_batches_and_forward_indexed_match_materialised_windows():
+    """e2e shape of bench.py: window starts from the host -> DevicePrefetcher -> forward_indexed == forward on gathered windows."""
+    from pytorch_geometric_temporal_b200.dataset import synthetic
+    from pytorch_geometric_temporal_b200.nn.recurrent import BatchedDCRNN
+    from pytorch_geometric_temporal_b200.signal import DevicePrefetcher, IndexBatchLoader, index_splits
+    ei, ew, series = synthetic.metr_la_like(0, 128)
+    ei_t, ew_t, sd = torch.from_numpy(ei).to(DEV), torch.from_numpy(ew).to(DEV), torch.from_numpy(series).to(DEV)
+    tr, _, _ = index_splits(128, 12)
+    loader = IndexBatchLoader(sd, tr, 12, 16, shuffle=True, seed=3, drop_last=True, materialize=False)
+    mat = IndexBatchLoader(sd, tr, 12, 16, shuffle=True, seed=3, drop_last=True, materialize=True)
+    m = BatchedDCRNN(2, 32, 2).to(DEV)
+    with torch.no_grad():
+        for st, (x, _) in zip(DevicePrefetcher(loader.host_batches(), DEV), mat):
+            assert st.dtype == torch.int64 and st.numel() == 16
+            assert torch.equal(m.forward_indexed(sd, st, 12, ei_t, ew_t), m(x, ei_t, ew_t))
+
+
 # ---- K4: tcgen05 split-fp16 GEMM (stmp_gemm_f32) and its fused LSTM epilogue ------------------------------------------
 @pytest.mark.parametrize("M,K,N", [(1, 4, 32), (127, 36, 64), (128, 64, 96), (1000, 384, 256), (20000, 132, 128)])
 def test_gemm_tc_matches_fp64(M, K, N):

@@ -24,7 +24,7 @@ class _DensePlan(object):
 
 @pytest.fixture()
 def dense_graph_ops(monkeypatch):
-    def plan(self, edge_index, edge_weight, num_nodes, normalization, lambda_max):
+    def plan(self, edge_index, edge_weight, num_nodes, normalization, lambda_max, batch=None):
         lam = self._lambda_value(lambda_max)
         e, w = pyg.cheb_norm(edge_index, num_nodes, edge_weight, normalization, lam)
         L = torch.zeros(num_nodes, num_nodes)
@@ -215,7 +215,7 @@ from pytorch_geometric_temporal_b200.nn.attention import ASTGCN  # noqa: E402
 
 @pytest.fixture()
 def dense_att_ops(monkeypatch):
-    def plan(self, edge_index, edge_weight, num_nodes, lambda_max):
+    def plan(self, edge_index, edge_weight, num_nodes, lambda_max, batch=None):
         lam = torch.tensor(2.0 if lambda_max is None else float(lambda_max))
         ei, w = OA.cheb_att_norm(edge_index, num_nodes, edge_weight, self._normalization, lam)
         W = torch.zeros(num_nodes, num_nodes)

@@ -84,6 +84,24 @@ def test_astgcn(norm):
     assert torch.allclose(want, got, rtol=1e-6, atol=1e-6)  # diag-scale vs dense matmul: 1 ulp
 
 
+@pytest.mark.parametrize("norm", ["sym", None, "rw"])
+def test_chebconv_attention_per_graph_lambda_max(norm):
+    """The multi-graph mini-batch call of the reference's own test (test/attention_test.py:205-218): a node->graph `batch`
+    vector and one lambda_max per graph."""
+    torch.manual_seed(0)
+    ref = refload.load("nn.attention.astgcn").ChebConvAttention(5, 7, K=3, normalization=norm)
+    batch = torch.tensor([0, 0, 0, 1, 1, 1, 1])
+    ei = torch.tensor([[0, 1, 1, 2, 3, 4, 5, 6, 3, 6], [1, 0, 2, 1, 4, 3, 6, 5, 6, 3]])
+    ew = torch.rand(ei.size(1)) + 0.1
+    x, S = torch.randn(3, 7, 5), torch.softmax(torch.rand(3, 7, 7), dim=1)
+    lam = torch.tensor([2.0, 3.0])
+    with torch.no_grad():
+        want = ref(x, ei, S, ew, batch, lam)
+        got = A.cheb_conv_attention(ref.state_dict(), x, ei, S, norm, ew, lam, batch)
+        assert torch.allclose(want, got, rtol=1e-6, atol=1e-6)
+        assert not torch.allclose(want, ref(x, ei, S, ew, None, 2.0), rtol=1e-3, atol=1e-4)   # the second graph really uses 3.0
+
+
 # ---- SURVEY 8f rank 1: GCLSTM, STConv, MSTGCN ---------------------------------------------------------------
 @pytest.mark.parametrize("K", [1, 2, 3])
 @pytest.mark.parametrize("norm", ["sym", "rw", None])
