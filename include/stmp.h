@@ -158,6 +158,18 @@ int stmp_dcrnn_pack_weights(int64_t cin, int64_t cout, int64_t K, const float* w
 int stmp_gru_pack_weights(const float* wcat, const float* bcat, void* image, void* stream);
 int stmp_gru_seq_supported(const stmp_plan* plan, int n_ops, int64_t cin, int64_t cout);
 
+/* ---- fused temporal-attention + GCN-GRU: A3TGCN / A3TGCN2 (attentiontemporalgcn.py:51-79,130-157) and, with periods = 1 and
+ * probs = NULL, a TGCN / TGCN2 cell (temporalgcn.py:104-130,212-233) -- graphs of any size, out_channels = 32.
+ *   out[b,n,:] = sum_t probs[t] * GRU(A^ X[b,:,:,t], H[b])        A^ = operator 0 of `plan` (GCN flavor: gcn_norm)
+ * with GCNConv's Linear and the gate Linear folded on the host:  pre_g = (A^X_t) A[:, g] + H' Bm[:, g] + c[g],  g in z|r|h
+ *   x: [B][N][fin][periods] contiguous;  h: [B][N][32] with batch stride h_bstride (0: one state shared by all rows) or NULL (zeros)
+ *   A: [fin][96], Bm: [32][96], c: [96] (columns z | r | h);  probs: [periods] = softmax(attention) or NULL;  out: [B][N][32]
+ * One gather per node serves every period (A^(XW) = (A^X)W); X[b] is staged in shared memory by one TMA bulk copy per CTA.
+ * STMP_EUNSUPPORTED unless fin <= 4 and fin * periods <= 128. */
+int stmp_tgcn_attn_fwd(const stmp_plan* plan, int64_t B, int64_t fin, int64_t periods, const float* x, const float* h,
+                       int64_t h_bstride, const float* A, const float* Bm, const float* c, const float* probs, float* out,
+                       void* stream);
+
 /* ---- K5: gate epilogues for the tiled path -------------------------------------------------------
  * GRU (dcrnn.py:172-192, gconv_gru.py:119-139, temporalgcn.py:82-102), n = number of elements:
  *   stmp_gru_zr:   z = sigmoid(pz); r = sigmoid(pr); hr = h * r

@@ -45,6 +45,7 @@ _SIGNATURES = {
     "stmp_dcrnn_pack_weights": (c_int, [c_int64, c_int64, c_int64, _P, _P, _P, _P, _P, _P, _P, _P]),
     "stmp_gru_pack_weights": (c_int, [_P, _P, _P, _P]),
     "stmp_gru_seq_supported": (c_int, [_P, c_int, c_int64, c_int64]),
+    "stmp_tgcn_attn_fwd": (c_int, [_P, c_int64, c_int64, c_int64, _P, _P, c_int64, _P, _P, _P, _P, _P, _P]),
     "stmp_gru_zr": (c_int, [c_int64, _P, _P, _P, _P, _P, _P, _P]),
     "stmp_gru_out": (c_int, [c_int64, _P, _P, _P, _P, _P, _P]),
     "stmp_dcrnn_bwd_supported": (c_int, [_P, c_int64, c_int64, c_int64]),

@@ -26,6 +26,7 @@
 
 namespace stmp {
 // tcgen05 variant (dcrnn_seq_tc.cu)
+extern int g_spmm_variant;
 bool dcrnn_tc_supported(const stmp_plan* plan, long long cin, long long cout, long long K);
 int dcrnn_tc_launch(const stmp_plan* plan, long long B, long long T, long long cin, const float* x, const long long* win_start,
                     long long x_bstride, long long x_tstride, const float* w_z, const float* w_r, const float* w_h, const float* b_z,
@@ -35,7 +36,7 @@ int tc_pack_weight_image(const float* wcat, const float* bcat, const float* w0, 
                          const float* b1, const float* b2, int cin, void* image, cudaStream_t st);
 int tc_weight_image_bytes();
 
-bool gru_tc_supported(const stmp_plan* plan, long long cin);
+bool gru_tc_supported(const stmp_plan* plan, long long cin, int n_ops);
 int gru_tc_launch(const stmp_plan* plan, int n_ops, long long B, long long T, long long cin, const float* x, const long long* win_start,
                   long long x_bstride, long long x_tstride, const float* wcat, const float* bcat, const float* h0, long long h0_bstride,
                   float* out, float* stash, const void* wimage, cudaStream_t st);
@@ -480,7 +481,7 @@ extern "C" int stmp_dcrnn_seq_fwd(const stmp_plan* plan, int64_t B, int64_t T, i
 
 extern "C" int stmp_gru_seq_supported(const stmp_plan* plan, int n_ops, int64_t cin, int64_t cout) {
   if (!plan || n_ops < 0 || n_ops > 2 || n_ops > plan->n_ops || cout != 32) return 0;
-  return gru_tc_supported(plan, cin) ? 1 : 0;
+  return gru_tc_supported(plan, cin, n_ops) ? 1 : 0;
 }
 
 extern "C" int stmp_gru_seq_fwd(const stmp_plan* plan, int n_ops, int64_t B, int64_t T, int64_t cin, const float* x,
@@ -491,7 +492,7 @@ extern "C" int stmp_gru_seq_fwd(const stmp_plan* plan, int n_ops, int64_t B, int
   STMP_REQUIRE(n_ops >= 0 && n_ops <= 2 && n_ops <= plan->n_ops, STMP_EINVAL, "stmp_gru_seq_fwd: n_ops=%d not available in this plan", n_ops);
   STMP_REQUIRE(B >= 0 && T >= 0, STMP_EINVAL, "stmp_gru_seq_fwd: negative B/T");
   STMP_REQUIRE(x && wcat && bcat && out, STMP_EINVAL, "stmp_gru_seq_fwd: NULL tensor");
-  if (!gru_tc_supported(plan, cin))
+  if (!gru_tc_supported(plan, cin, n_ops))
     return set_error(STMP_EUNSUPPORTED, "fused graph-GRU kernel supports N<=207, cin<=4, cout=32 (got N=%d cin=%lld)", plan->n, (long long)cin);
   if (B == 0 || T == 0) return STMP_OK;
   return gru_tc_launch(plan, n_ops, B, T, cin, x, reinterpret_cast<const long long*>(win_start), x_bstride, x_tstride, wcat, bcat, h0,
@@ -503,6 +504,7 @@ extern "C" int stmp_gru_seq_fwd(const stmp_plan* plan, int n_ops, int64_t B, int
 extern "C" int stmp_set_option(const char* name, int value) {
   STMP_REQUIRE(name != nullptr, STMP_EINVAL, "stmp_set_option: NULL name");
   if (strcmp(name, "dcrnn_tc") == 0) { g_use_tc = value ? 1 : 0; return STMP_OK; }
+  if (strcmp(name, "spmm_variant") == 0) { g_spmm_variant = value; return STMP_OK; }
   return set_error(STMP_EINVAL, "stmp_set_option: unknown option '%s'", name);
 }
 

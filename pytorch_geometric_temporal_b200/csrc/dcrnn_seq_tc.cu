@@ -9,15 +9,16 @@
 // the product is formed as lo*hi + hi*lo + hi*hi -- three MMAs.  Validated stand-alone in tools/tc_probe.cu:
 // max |err| 6e-6 vs fp64 on K=112 dot products, the same order as an fp32 FMA chain (3e-6).
 //
-// Shared memory (<= 227 KB), all operands written by hand in the canonical K-major SWIZZLE_128B layout
+// Shared memory (~204 KB of 227), all operands written by hand in the canonical K-major SWIZZLE_128B layout
 // (row pitch 128 B = 64 fp16, 16-byte chunk index XOR (row % 8), 8-row atoms of 1024 B):
 //   A_hi / A_lo : 2 K-panels x 208 rows   k = [H|H*R (32) , P_o H (32)] , [P_i H (32), X(4) P_oX(4) P_iX(4) 0(4)]
 //   B_hi / B_lo : 2 K-panels x 96 rows    rows = output channels of z | r | h, same k order (7 k-steps of 16)
-//   U  fp32 [N][36] = [H | X] : the gather source of the diffusion (tensor cores only see the fp16 split)
-//   graph (padded / pre-scaled / length-sorted, dcrnn_common.cuh), biases, 4 mbarriers.
+//   U  fp32 [208][36] = H (or H*R) + 16 B of row padding: the gather source of the diffusion (tensor cores only see the fp16 split); row 207 = 0
+//   graph image (graph_image.cuh: balanced warp-task lists, 8-bit source rows four per word, values four per 128 bits),
+//   biases, 6 mbarriers, 2 arrival counters.
 // TMEM (256 columns): z|r accumulators of the two 128-row tiles at columns [0,64) [64,128), candidate at
 // [128,160) [160,192).  TMEM lane == row, so thread (warp w, lane l) owns row 128*(w/4) + 32*(w%4) + l for the
-// whole step: it reads its 64+32 accumulator columns with tcgen05.ld, applies the gates, keeps Z and H in
+// whole step: it reads its 64+32 accumulator columns with tcgen05.ld, applies the gates, keeps H in
 // registers, and writes H*R / H_t back as fp32 (U), as fp16 hi/lo (A panel) and to HBM.  16 warps: each row is
 // shared by two threads (channel halves), which also doubles the warps available to hide the gather latency.
 #include <cuda_fp16.h>
@@ -26,14 +27,16 @@
 
 #include "common.cuh"
 #include "dcrnn_common.cuh"
+#include "graph_image.cuh"
 #include "tc_common.cuh"
 
 namespace stmp {
 namespace {
 
 constexpr int kMaxSmemTc = 232448;
-constexpr int TC_NT_MAX = 512;             // 16 warps: 2 row tiles x 4 lane quadrants x 2 channel halves (HALVES=2)
-constexpr int TC_UP = 36;                  // U row pitch (floats): [H(32) | X(4)]
+constexpr int TC_UP = 36;                  // U row pitch (floats): a 128-byte row of H (or of T*Cin X values in the window prologue) + 16 B, so that the
+                                           // epilogue's row-strided 16-byte stores rotate through the banks (pitch 32: 8-way conflicts, measured -14 %)
+constexpr int TC_UROWS = 208;              // rows of U; row 207 is the all-zero row that pad entries of the graph image point at
 constexpr int TC_AROWS = 208;              // rows stored per A panel (tile 1 over-reads into the next buffer: harmless)
 constexpr int TC_PANEL_A = TC_AROWS * 128;
 constexpr int TC_PANEL_B = 96 * 128;
@@ -42,8 +45,6 @@ constexpr int TC_TMEM_COLS = 256;
 struct TcParams {
   int N, CIN, T;
   long long B;
-  const int* rowptr[2];
-  const int2* cv[2];
   const float* x;
   const long long* win_start;
   long long x_bstride, x_tstride;
@@ -54,51 +55,13 @@ struct TcParams {
   const float* wcat;      // optional prepacked fp32 weights [96][112] in the kernel's k order (else: DConv weights p.w[])
   const float* bcat;      // with wcat: biases [96]
   int n_ops;              // 2: DConv (P_o, P_i); 1: single operator (ChebConv K=2 / GCN); 0: no propagation
-  const void* gimg;       // plan's prebuilt shared-memory graph image (TMA bulk source) or null
-  int gimg_bytes;
+  const void* gimg;       // plan's prebuilt shared-memory graph image for n_ops operators (TMA bulk source)
+  GraphImageLayout gl;    // its internal offsets
   const void* wimage;     // prebuilt B-operand image (fp16 hi/lo, swizzled, + biases) or null
   float* out;
   float* stash;
-  int off_A, off_B, off_U, off_gstart, off_order, off_ce, off_bias, off_bar;
+  int off_A, off_B, off_U, off_img, off_bias, off_bar;
 };
-
-// split 32 floats (one row's H-like vector) into panel 0, k 0..31 : 4 swizzled 16-byte chunks for hi and for lo
-__device__ __forceinline__ void store_split_row32(unsigned char* a_hi, unsigned char* a_lo, int row, const float (&v)[32]) {
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    uint32_t hw[4], lw[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float a = v[8 * c + 2 * j], b = v[8 * c + 2 * j + 1];
-      const __half2 h = __floats2half2_rn(a, b);
-      const float2 f = __half22float2(h);
-      hw[j] = pack_h2(h);
-      lw[j] = pack_h2(__floats2half2_rn(a - f.x, b - f.y));
-    }
-    const int off = row * 128 + ((c ^ (row & 7)) << 4);
-    *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-    *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-  }
-}
-
-// same for one channel half (16 floats -> chunks 2*half, 2*half+1 of panel 0)
-__device__ __forceinline__ void store_split_row16(unsigned char* a_hi, unsigned char* a_lo, int row, int half, const float (&v)[16]) {
-#pragma unroll
-  for (int c = 0; c < 2; ++c) {
-    uint32_t hw[4], lw[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float a = v[8 * c + 2 * j], b = v[8 * c + 2 * j + 1];
-      const __half2 h = __floats2half2_rn(a, b);
-      const float2 f = __half22float2(h);
-      hw[j] = pack_h2(h);
-      lw[j] = pack_h2(__floats2half2_rn(a - f.x, b - f.y));
-    }
-    const int off = row * 128 + (((2 * half + c) ^ (row & 7)) << 4);
-    *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-    *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-  }
-}
 
 // CW = 32 (whole row) or 16 (channel half `half`): chunks [half*CW/8, +CW/8) of panel 0
 template <int CW>
@@ -162,50 +125,72 @@ __global__ void k_pack_weight_image(const float* wcat, const float* bcat, const 
 __device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float tanh_fast(float x) { return 2.0f * __fdividef(1.0f, 1.0f + __expf(-2.0f * x)) - 1.0f; }
 
-// One diffusion round: gather fp32 rows of U, write the products as fp16 hi/lo into the A panels.
-//   op 0 (P_o): H part -> panel 0 k 32..63, X part -> panel 1 k 36..39
-//   op 1 (P_i): H part -> panel 1 k 0..31,  X part -> panel 1 k 40..43
-template <int TC_NT>
-__device__ __forceinline__ void diffuse_tc(const float* U, const GraphSmem g, int N, unsigned char* a_hi, unsigned char* a_lo,
-                                           bool with_x, int tid, int s_beg, int s_end) {
-  const int j = tid & 7;
-  for (int slot = s_beg + (tid >> 3); slot < s_end; slot += TC_NT / 8) {
-    const int task = g.order[slot];
-    const int op = task >= N ? 1 : 0;
-    const int i = task - op * N;
-    const float4 acc = gather_row(U + 4 * j, g.ce, g.gstart[task], g.gstart[task + 1]);
-    const int pb = op ? TC_PANEL_A : 0;
-    store_split4(a_hi + pb, a_lo + pb, i, (op ? 0 : 32) + 4 * j, acc);
+// ---- gather ------------------------------------------------------------------------------------------------------------
+// Weighted sum of the source rows of one task (graph_image.cuh): quarter-warp lane j accumulates floats 4j..4j+3 of the row.
+// Four edges per group: one broadcast 32-bit load carries their four 8-bit source rows, one 128-bit load their values; the
+// next group's entries are fetched while the current group's four feature rows are in flight.  Summation order = CSR order
+// (the reference's scatter order), products by FMA as in the round-1 kernel.
+__device__ __forceinline__ float4 gather_groups(const float* __restrict__ Uj, const uint32_t* __restrict__ idx4,
+                                                const float4* __restrict__ val4, int g0, int ng) {
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  uint32_t u = idx4[g0];
+  float4 v = val4[g0];
+  for (int g = 1; g <= ng; ++g) {
+    const uint32_t un = idx4[g0 + g];      // (one spare group at the end of the arrays)
+    const float4 vn = val4[g0 + g];
+    const float4 x0 = ld4(Uj + (u & 0xffu) * TC_UP);
+    const float4 x1 = ld4(Uj + ((u >> 8) & 0xffu) * TC_UP);
+    const float4 x2 = ld4(Uj + ((u >> 16) & 0xffu) * TC_UP);
+    const float4 x3 = ld4(Uj + (u >> 24) * TC_UP);
+    fma4(acc, v.x, x0);
+    fma4(acc, v.y, x1);
+    fma4(acc, v.z, x2);
+    fma4(acc, v.w, x3);
+    u = un;
+    v = vn;
   }
-  if (with_x) {
-    for (int slot = s_beg + tid; slot < s_end; slot += TC_NT) {
-      const int task = g.order[slot];
-      const int op = task >= N ? 1 : 0;
-      const int i = task - op * N;
-      const float4 acc = gather_row(U + 32, g.ce, g.gstart[task], g.gstart[task + 1]);
-      store_split4(a_hi + TC_PANEL_A, a_lo + TC_PANEL_A, i, op ? 40 : 36, acc);
-    }
-  }
+  return acc;
 }
 
-template <int HALVES>
-__global__ void __launch_bounds__(256 * HALVES, 1) k_dcrnn_seq_tc(const TcParams p) {
-  constexpr int TC_NT = 256 * HALVES;
-  constexpr int CW = 32 / HALVES;   // channels per thread
+__device__ __forceinline__ uint32_t atom_add_acq_rel_shared(uint32_t* p, uint32_t v) {
+  uint32_t old;
+  asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(p)), "r"(v) : "memory");
+  return old;
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Step anatomy (all 16 warps; T_k = MMA row tile k = rows [128k, 128k+128)):
+//   round 1  gather [P_o H | P_i H] of T_0's rows -> A panels;  the LAST warp to finish issues GEMM1(T_0) (z|r pre-activations)
+//            gather T_1's rows                                   last warp issues GEMM1(T_1); every warp arrives on `gdone`
+//   epi 1    wait GEMM1(own tile) + gdone (nobody reads U any more): R, H*R -> U, A panel               __syncthreads
+//   round 2  same gathers over H*R, GEMM2 (candidate)
+//   epi 2    wait GEMM2(own tile) + gdone: Z (recomputed from TMEM), H~, H_t -> U, A panel, HBM;  X_{t+1} k-step  __syncthreads
+// so the tensor core works on T_0 while the LSU still gathers T_1, and a step has two block-wide barriers instead of four.
+// X is never gathered per step: P_o X_t, P_i X_t of ALL steps of a window are produced by one gather pass over rows of
+// T*Cin floats in the window prologue and parked in the window's own (not yet written) output rows out[b, t, :, 0:8].
+template <int CIN>
+__global__ void __launch_bounds__(512, 1) k_dcrnn_seq_tc(const TcParams p) {
+  constexpr int CW = 16;   // channels per thread (two threads share a row)
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int N = p.N, CIN = p.CIN, T = p.T;
+  const int N = p.N, T = p.T;
   unsigned char* a_hi = smem + p.off_A;
   unsigned char* a_lo = a_hi + 2 * TC_PANEL_A;
   unsigned char* b_hi = smem + p.off_B;
   unsigned char* b_lo = b_hi + 2 * TC_PANEL_B;
   float* U = reinterpret_cast<float*>(smem + p.off_U);
-  int* s_gstart = reinterpret_cast<int*>(smem + p.off_gstart);
-  int* s_order = reinterpret_cast<int*>(smem + p.off_order);
-  int2* s_ce = reinterpret_cast<int2*>(smem + p.off_ce);
+  const unsigned char* img = smem + p.off_img;
+  const uint16_t* s_wstart = reinterpret_cast<const uint16_t*>(img + p.gl.off_wstart);
+  const uint16_t* s_wcount = reinterpret_cast<const uint16_t*>(img + p.gl.off_wcount);
+  const uint32_t* s_wt = reinterpret_cast<const uint32_t*>(img + p.gl.off_wt);
+  const uint32_t* s_idx = reinterpret_cast<const uint32_t*>(img + p.gl.off_idx);
+  const float4* s_val = reinterpret_cast<const float4*>(img + p.gl.off_val);
   float* Bs = reinterpret_cast<float*>(smem + p.off_bias);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.off_bar);   // [4]: gemm1 tile0/1, gemm2 tile0/1
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.off_bar);   // [0..3] MMA done (gemm*2+tile; 3 commits each), [4] prologue TMA, [5] gather done
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+  uint32_t* cnt = tmem_slot + 1;                                    // [4] warps that finished segment (tile*2+op) (monotonic)
 
   if (blockIdx.x >= p.B) return;
 
@@ -214,31 +199,32 @@ __global__ void __launch_bounds__(256 * HALVES, 1) k_dcrnn_seq_tc(const TcParams
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TC_TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
-  // bars[0..3]: MMA completion (gemm1 tile0/1, gemm2 tile0/1); bars[4]: prologue TMA copies
   if (tid == 0) {
-    for (int i = 0; i < 5; ++i) mbar_init(&bars[i], 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&bars[i], 3);
+    mbar_init(&bars[4], 1);
+    mbar_init(&bars[5], 16);
+    cnt[0] = cnt[1] = cnt[2] = cnt[3] = 0;
     fence_mbar_init();
-    const uint32_t tx = (p.gimg ? (uint32_t)p.gimg_bytes : 0u) + (p.wimage ? (uint32_t)TC_WIMAGE_BYTES : 0u);
+    const uint32_t tx = (p.n_ops ? (uint32_t)p.gl.bytes : 0u) + (p.wimage ? (uint32_t)TC_WIMAGE_BYTES : 0u);
     if (tx) {   // graph image and weight image arrive by TMA bulk copies while the CTA zeroes its panels
       mbar_arrive_expect_tx(&bars[4], tx);
-      if (p.gimg) tma_bulk_g2s(smem + p.off_gstart, p.gimg, (uint32_t)p.gimg_bytes, &bars[4]);
+      if (p.n_ops) tma_bulk_g2s(smem + p.off_img, p.gimg, (uint32_t)p.gl.bytes, &bars[4]);
       if (p.wimage) {
         tma_bulk_g2s(b_hi, p.wimage, 4u * TC_PANEL_B, &bars[4]);
         tma_bulk_g2s(Bs, reinterpret_cast<const unsigned char*>(p.wimage) + 4 * TC_PANEL_B, 96u * 4u, &bars[4]);
       }
     }
   }
-  {  // zero A (pad columns / rows must be finite); B too unless the TMA image overwrites all of it
+  {  // zero A (pad columns / rows must be finite) and U (row 207 stays the zero row); B too unless the TMA image overwrites all of it
     uint4* z = reinterpret_cast<uint4*>(a_hi);
     const int nz = (4 * TC_PANEL_A + (p.wimage ? 0 : 4 * TC_PANEL_B)) / 16;
-    for (int i = tid; i < nz; i += TC_NT) z[i] = make_uint4(0, 0, 0, 0);
-    for (int i = tid; i < N * TC_UP; i += TC_NT) U[i] = 0.f;
+    for (int i = tid; i < nz; i += 512) z[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < TC_UROWS * TC_UP; i += 512) U[i] = 0.f;
   }
-  if (!p.gimg) stage_graph<TC_NT>(p.rowptr[0], p.rowptr[1], p.cv[0], p.cv[1], N, TC_UP, s_ce, s_gstart, s_order, tid, 1 << 30, p.n_ops, 2);
   __syncthreads();
   if (!p.wimage) {
     // weights -> B operand (fp16 hi/lo, swizzled).  Row n = gate*32 + out channel; k order as the A panels.
-    for (int idx = tid; idx < 96 * 112; idx += TC_NT) {
+    for (int idx = tid; idx < 96 * 112; idx += 512) {
       const int n = idx / 112, kk = idx - n * 112;
       const float v = tc_weight_value(p.wcat, p.w[0], p.w[1], p.w[2], CIN, n, kk);
       const __half h = __float2half_rn(v);
@@ -247,57 +233,166 @@ __global__ void __launch_bounds__(256 * HALVES, 1) k_dcrnn_seq_tc(const TcParams
       *reinterpret_cast<__half*>(b_hi + off) = h;
       *reinterpret_cast<__half*>(b_lo + off) = l;
     }
-    for (int idx = tid; idx < 96; idx += TC_NT) {
+    for (int idx = tid; idx < 96; idx += 512) {
       const int gte = idx >> 5;
       const float* bg = gte == 0 ? p.bias[0] : (gte == 1 ? p.bias[1] : p.bias[2]);
       Bs[idx] = p.bcat ? p.bcat[idx] : (bg ? bg[idx & 31] : 0.f);
     }
   }
-  if (p.gimg || p.wimage) mbar_wait(&bars[4], 0);
+  if (p.n_ops || p.wimage) mbar_wait(&bars[4], 0);
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  const GraphSmem gs{s_ce, s_gstart, s_order};
   // thread = (row, channel half): warp = half*8 + tile*4 + q ; TMEM lane == row, a warp may only touch lanes 32*(warp%4)..
-  const int half = HALVES == 2 ? (warp >> 3) : 0, tile = (warp >> 2) & 1, q = warp & 3;
+  const int half = warp >> 3, tile = (warp >> 2) & 1, q = warp & 3;
   const int row = tile * 128 + q * 32 + lane;
   const int ch0 = CW * half;
   const bool live = row < N;
+  const bool owner = live && half == 0;      // the thread that feeds its row's X k-step
   const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
   const uint32_t a_hi_s = smem_u32(a_hi), a_lo_s = smem_u32(a_lo), b_hi_s = smem_u32(b_hi), b_lo_s = smem_u32(b_lo);
   constexpr uint32_t ID64 = umma_idesc_f16(128, 64), ID32 = umma_idesc_f16(128, 32);
-  uint32_t parity = 0;
+  uint32_t parity = 0, gpar = 0, rounds = 0;
   const bool two_tiles = N > 128;
+  const int j = lane & 7, quarter = lane >> 3;
+  const float* Uj = U + 4 * j;
 
-  // issue the 3 x 7 MMAs of one (tile, gemm) and commit them to `bar`          (one thread)
-  auto issue = [&](int tl, int gm, uint64_t* bar) {
+  // The 3 x 7 MMAs of one (tile, gemm) are issued in three groups, each as soon as its k-steps are in shared memory, each with
+  // its own commit to the (tile, gemm) barrier (count 3):
+  //   group 0: k-steps of H | H*R and X  -- complete when the round starts; its first MMA overwrites the accumulator
+  //   group 1: k-steps of P_o H          -- after the last warp finished the tile's P_o tasks
+  //   group 2: k-steps of P_i H          -- after the last warp finished the tile's P_i tasks
+  // so the tensor core runs underneath the gather and only the last group's 6 MMAs are exposed at the end of a round.
+  auto issue_group = [&](int tl, int gm, int grp) {
     const uint32_t dcol = gm == 0 ? 64u * tl : 128u + 32u * tl;
-    uint32_t acc = 0;
+    const int ks0 = grp == 0 ? 0 : (grp == 1 ? 2 : 4);
 #pragma unroll
     for (int pass = 0; pass < 3; ++pass) {           // lo*hi, hi*lo, hi*hi (small terms first)
       const uint32_t ab = (pass == 0 ? a_lo_s : a_hi_s) + tl * (128 * 128);
       const uint32_t bb = (pass == 1 ? b_lo_s : b_hi_s) + (gm ? 64 * 128 : 0);
 #pragma unroll
-      for (int ks = 0; ks < 7; ++ks) {
+      for (int i = 0; i < 3; ++i) {
+        if (i == 2 && grp != 0) continue;
+        const int ks = i == 2 ? 6 : ks0 + i;
         const int panel = ks >> 2, kin = (ks & 3) * 16;
         umma_f16(tmem + dcol, umma_desc(ab + panel * TC_PANEL_A + kin * 2), umma_desc(bb + panel * TC_PANEL_B + kin * 2),
-                 gm == 0 ? ID64 : ID32, acc);
-        acc = 1;
+                 gm == 0 ? ID64 : ID32, (grp == 0 && pass == 0 && i == 0) ? 0u : 1u);
       }
     }
-    umma_commit(bar);
+    umma_commit(&bars[2 * gm + tl]);
+  };
+
+  // this warp's warp-tasks of segment `seg` = (MMA tile of the destination rows) * 2 + operator: results -> A panels as fp16 hi/lo
+  //   op 0 (P_o): panel 0 k 32..63        op 1 (P_i): panel 1 k 0..31
+  auto gather_segment = [&](int seg) {
+    const int ws = s_wstart[warp * 4 + seg], wc = s_wcount[warp * 4 + seg];
+    const int op = seg & 1;
+    unsigned char* dh = a_hi + (op ? TC_PANEL_A : 0);
+    unsigned char* dl = a_lo + (op ? TC_PANEL_A : 0);
+    const int kcol = (op ? 0 : 32) + 4 * j;
+    for (int i = 0; i < wc; ++i) {
+      const uint32_t d = s_wt[(ws + i) * 4 + quarter];
+      if (d != kImgNoTask) {
+        const float4 acc = gather_groups(Uj, s_idx, s_val, (int)(d >> 16), (int)((d >> 9) & 0x7f));
+        store_split4(dh, dl, (int)(d & 0xff), kcol, acc);
+      }
+    }
+  };
+  // a warp has written its share of segment `seg`: the last of the 16 warps to say so issues that segment's MMA group
+  auto segment_done = [&](int seg, int gm) {
+    fence_proxy_async();        // my generic-proxy stores to the A panels -> visible to the tensor core (async proxy)
+    __syncwarp();
+    if (lane == 0) {
+      const uint32_t old = atom_add_acq_rel_shared(&cnt[seg], 1u);
+      if (old + 1u == 16u * (rounds + 1u)) {
+        tc_fence_after();
+        const int tl = seg >> 1;
+        if (tl == 0 || two_tiles) issue_group(tl, gm, 1 + (seg & 1));
+      }
+      if (seg == 3) mbar_arrive(&bars[5]);     // my gathers of this round are complete (U is no longer read by me)
+    }
+    __syncwarp();
+  };
+  auto gather_round = [&](int gm) {
+    if (tid == 0) {             // (the block-wide barrier in front of every round ordered all operand stores)
+      issue_group(0, gm, 0);
+      if (two_tiles) issue_group(1, gm, 0);
+      tc_fence_before();
+    }
+#pragma unroll
+    for (int seg = 0; seg < 4; ++seg) {
+      if ((seg & 1) < p.n_ops) gather_segment(seg);
+      segment_done(seg, gm);
+    }
+    ++rounds;
   };
 
   auto x_base = [&](long long b) -> const float* { return p.x + (p.win_start ? p.win_start[b] * p.x_tstride : b * p.x_bstride); };
+  // [X_t | P_o X_t | P_i X_t] of my row -> k 32..43 of panel 1 (weights of absent channels / operators are zero, but the
+  // operand itself must be finite: everything not produced is written as 0 -- at store time, so the loads stay in flight)
+  auto load_x = [&](const float* xb, long long b, int t, float4& xv, float4& po, float4& pi) {
+    float xn[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int c = 0; c < CIN; ++c) xn[c] = __ldg(xb + t * p.x_tstride + row * CIN + c);
+    xv = make_float4(xn[0], xn[1], xn[2], xn[3]);
+    po = pi = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* sc = p.out + ((b * T + t) * (long long)N + row) * 32;   // parked there by the window prologue (plain loads:
+    if (p.n_ops >= 1) po = *reinterpret_cast<const float4*>(sc);         //  written by this CTA earlier in this launch)
+    if (p.n_ops >= 2) pi = *reinterpret_cast<const float4*>(sc + 4);
+  };
+  auto mask_c = [&](float4 v) {
+    if (CIN < 4) v.w = 0.f;
+    if (CIN < 3) v.z = 0.f;
+    if (CIN < 2) v.y = 0.f;
+    return v;
+  };
+  auto store_x = [&](const float4& xv, const float4& po, const float4& pi) {
+    store_split4(a_hi + TC_PANEL_A, a_lo + TC_PANEL_A, row, 32, xv);
+    store_split4(a_hi + TC_PANEL_A, a_lo + TC_PANEL_A, row, 36, mask_c(po));
+    store_split4(a_hi + TC_PANEL_A, a_lo + TC_PANEL_A, row, 40, mask_c(pi));
+  };
 
   for (long long b = blockIdx.x; b < p.B; b += gridDim.x) {
     const float* xb = x_base(b);
-    // ---- window prologue: H_0 and X_0 into U (fp32) and the A panels (fp16 hi/lo) -------------------------------
+    // ---- window prologue A: P_o X_t, P_i X_t for every step of the window, TCH steps per gather pass ------------------------
+    if (p.n_ops) {
+      constexpr int TCH = 32 / CIN;
+      for (int t0 = 0; t0 < T; t0 += TCH) {
+        const int tn = (T - t0) < TCH ? (T - t0) : TCH;
+        const int F = tn * CIN, NC = N * CIN;
+        for (int idx = tid; idx < tn * NC; idx += 512) {            // U[n][tt*CIN + c] = X[b, t0+tt, n, c]
+          const int tt = idx / NC, r = idx - tt * NC;
+          const int n = r / CIN, c = r - n * CIN;
+          U[n * TC_UP + tt * CIN + c] = __ldg(xb + (long long)(t0 + tt) * p.x_tstride + r);
+        }
+        __syncthreads();
+        for (int seg = 0; seg < 4; ++seg) {
+          const int ws = s_wstart[warp * 4 + seg], wc = s_wcount[warp * 4 + seg];
+          for (int i = 0; i < wc; ++i) {
+            const uint32_t d = s_wt[(ws + i) * 4 + quarter];
+            if (d != kImgNoTask && 4 * j < F) {
+              const float4 acc = gather_groups(Uj, s_idx, s_val, (int)(d >> 16), (int)((d >> 9) & 0x7f));
+              const float av[4] = {acc.x, acc.y, acc.z, acc.w};
+              const int drow = d & 0xff, op = (d >> 8) & 1;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const int f = 4 * j + k;
+                if (f < F) {
+                  const int tt = f / CIN, c = f - tt * CIN;
+                  p.out[((b * T + t0 + tt) * (long long)N + drow) * 32 + op * 4 + c] = av[k];
+                }
+              }
+            }
+          }
+        }
+        __syncthreads();
+      }
+    }
+    // ---- window prologue B: H_0 into U (fp32) and the A panels (fp16 hi/lo); the X k-step of step 0 ---------------------------
     float hreg[CW];
-    float xn[4] = {0.f, 0.f, 0.f, 0.f};
     if (live) {
 #pragma unroll
       for (int c = 0; c < CW / 4; ++c) {
@@ -306,33 +401,24 @@ __global__ void __launch_bounds__(256 * HALVES, 1) k_dcrnn_seq_tc(const TcParams
         st4(U + row * TC_UP + ch0 + 4 * c, h);
       }
       store_split_row<CW>(a_hi, a_lo, row, half, hreg);
-      if (half == 0) {
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-          if (c < CIN) xn[c] = __ldg(xb + row * CIN + c);
-        const float4 xv = make_float4(xn[0], xn[1], xn[2], xn[3]);
-        st4(U + row * TC_UP + 32, xv);
-        store_split4(a_hi + TC_PANEL_A, a_lo + TC_PANEL_A, row, 32, xv);
+      if (owner) {
+        float4 xv, po, pi;
+        load_x(xb, b, 0, xv, po, pi);
+        store_x(xv, po, pi);
       }
     }
+    fence_proxy_async();       // the first MMA group of step 0 is issued right behind this barrier
+    tc_fence_before();
     __syncthreads();
+    tc_fence_after();
 
     for (int t = 0; t < T; ++t) {
-      // prefetch X_{t+1} (consumed at the end of the step)
-      if (live && half == 0 && t + 1 < T) {
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-          if (c < CIN) xn[c] = __ldg(xb + (t + 1) * p.x_tstride + row * CIN + c);
-      }
-      // ---- round 1: diffuse [H | X_t] -----------------------------------------------------------------------
-      diffuse_tc<TC_NT>(U, gs, N, a_hi, a_lo, true, tid, 0, p.n_ops * N);
-      fence_proxy_async();
-      tc_fence_before();
-      __syncthreads();
-      tc_fence_after();
-      if (tid == 0) { issue(0, 0, &bars[0]); if (two_tiles) issue(1, 0, &bars[1]); }
-      // ---- epilogue 1: z, r gates; H*R ------------------------------------------------------------------------
+      // ---- round 1: diffuse H ------------------------------------------------------------------------------------------
+      gather_round(0);
+      // ---- epilogue 1: r gate; H*R ---------------------------------------------------------------------------------------
       if (tile == 0 || two_tiles) mbar_wait(&bars[tile], parity);   // tile 1 has no rows when N <= 128
+      mbar_wait(&bars[5], gpar);
+      gpar ^= 1u;
       tc_fence_after();
       const long long obase = (b * T + t) * (long long)N;
       {
@@ -364,15 +450,15 @@ __global__ void __launch_bounds__(256 * HALVES, 1) k_dcrnn_seq_tc(const TcParams
       tc_fence_before();
       __syncthreads();
       tc_fence_after();
-      // ---- round 2: re-diffuse the H*R columns -----------------------------------------------------------------
-      diffuse_tc<TC_NT>(U, gs, N, a_hi, a_lo, false, tid, 0, p.n_ops * N);
-      fence_proxy_async();
-      tc_fence_before();
-      __syncthreads();
-      tc_fence_after();
-      if (tid == 0) { issue(0, 1, &bars[2]); if (two_tiles) issue(1, 1, &bars[3]); }
-      // ---- epilogue 2: candidate, H_t ----------------------------------------------------------------------------
+      // ---- round 2: re-diffuse H*R ---------------------------------------------------------------------------------------
+      gather_round(1);
+      // ---- epilogue 2: candidate, H_t --------------------------------------------------------------------------------------
+      float4 xv, po, pi;
+      const bool feed_x = owner && t + 1 < T;
+      if (feed_x) load_x(xb, b, t + 1, xv, po, pi);      // in flight under the MMA wait
       if (tile == 0 || two_tiles) mbar_wait(&bars[2 + tile], parity);
+      mbar_wait(&bars[5], gpar);
+      gpar ^= 1u;
       tc_fence_after();
       {
         // Z is recomputed from its accumulator, which stays in TMEM until the next step's GEMM 1: cheaper than keeping
@@ -405,11 +491,7 @@ __global__ void __launch_bounds__(256 * HALVES, 1) k_dcrnn_seq_tc(const TcParams
               st4(sp + 2 * (long long)N * 32 + 4 * c, make_float4(ht[4 * c], ht[4 * c + 1], ht[4 * c + 2], ht[4 * c + 3]));
             }
           }
-          if (half == 0 && t + 1 < T) {
-            const float4 xv = make_float4(xn[0], xn[1], xn[2], xn[3]);
-            st4(U + row * TC_UP + 32, xv);
-            store_split4(a_hi + TC_PANEL_A, a_lo + TC_PANEL_A, row, 32, xv);
-          }
+          if (feed_x) store_x(xv, po, pi);
         }
       }
       parity ^= 1u;
@@ -425,16 +507,16 @@ __global__ void __launch_bounds__(256 * HALVES, 1) k_dcrnn_seq_tc(const TcParams
 
 inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
 
-bool tc_layout(const stmp_plan* plan, TcParams* p, int* smem_bytes) {
-  const int N = plan->n;
+// shared-memory layout for `n_ops` operators of `plan`
+bool tc_layout(const stmp_plan* plan, int n_ops, TcParams* p, int* smem_bytes) {
   int off = 0;
   p->off_A = off; off += 4 * TC_PANEL_A;
   p->off_B = off; off += 4 * TC_PANEL_B;
-  p->off_U = off; off += align_up(N * TC_UP * 4, 16);
-  p->off_gstart = off; off += align_up((2 * N + 1) * 4, 16);
-  p->off_order = off; off += align_up(2 * N * 4, 16);
-  const int nnz1 = plan->n_ops > 1 ? plan->fwd[1].nnz : 0;
-  p->off_ce = off; off += align_up((plan->fwd[0].nnz + nnz1 + 6 * N + 4) * 8, 16);
+  p->off_U = off; off += TC_UROWS * TC_UP * 4;
+  int nnz = 0;
+  for (int op = 0; op < n_ops; ++op) nnz += plan->fwd[op].nnz;
+  p->gl = graph_image_layout(n_ops * plan->n, nnz);
+  p->off_img = off; off += n_ops ? p->gl.bytes : 0;
   p->off_bias = off; off += 96 * 4;
   p->off_bar = off; off += 64;
   *smem_bytes = off;
@@ -443,23 +525,23 @@ bool tc_layout(const stmp_plan* plan, TcParams* p, int* smem_bytes) {
 
 }  // namespace
 
-bool gru_tc_supported(const stmp_plan* plan, long long cin) {
-  if (!plan || cin < 1 || cin > 4) return false;
-  if (plan->n > TC_AROWS - 1 || plan->n < 1) return false;
+static bool tc_fits(const stmp_plan* plan, int n_ops) {
+  if (!plan || plan->n > kImgMaxN || plan->n < 1) return false;
+  if (n_ops > 0 && !plan->gimg[n_ops]) return false;      // no image: graph too large / too dense for the 8-bit format
   TcParams p;
   int smem = 0;
-  p.N = plan->n;
-  return tc_layout(plan, &p, &smem);
+  return tc_layout(plan, n_ops, &p, &smem);
+}
+
+bool gru_tc_supported(const stmp_plan* plan, long long cin, int n_ops) {
+  if (!plan || cin < 1 || cin > 4 || n_ops < 0 || n_ops > 2 || n_ops > plan->n_ops) return false;
+  return tc_fits(plan, n_ops);
 }
 
 bool dcrnn_tc_supported(const stmp_plan* plan, long long cin, long long cout, long long K) {
   if (!plan || plan->flavor != STMP_FLAVOR_DCONV || plan->n_ops != 2) return false;
   if (K != 2 || cout != 32 || cin < 1 || cin > 4) return false;
-  if (plan->n > TC_AROWS - 1 || plan->n < 1) return false;
-  TcParams p;
-  int smem = 0;
-  p.N = plan->n;
-  return tc_layout(plan, &p, &smem);
+  return tc_fits(plan, 2);
 }
 
 static int tc_launch_params(const stmp_plan* plan, TcParams& p, cudaStream_t st);
@@ -493,29 +575,22 @@ int gru_tc_launch(const stmp_plan* plan, int n_ops, long long B, long long T, lo
 static int tc_launch_params(const stmp_plan* plan, TcParams& p, cudaStream_t st) {
   int smem = 0;
   const long long B = p.B;
-  if (!tc_layout(plan, &p, &smem)) return set_error(STMP_EUNSUPPORTED, "tcgen05 graph-GRU kernel needs %d B of shared memory", smem);
-  for (int op = 0; op < 2; ++op) {
-    const int src = op < plan->n_ops ? op : 0;
-    p.rowptr[op] = plan->fwd[src].rowptr; p.cv[op] = plan->fwd[src].cv;
-  }
-  p.gimg = (p.n_ops >= 1 && p.n_ops <= 2) ? plan->gimg[p.n_ops] : nullptr;
-  p.gimg_bytes = p.gimg ? plan->gimg_bytes[p.n_ops] : 0;
-  if (p.n_ops == 0) { p.gimg = nullptr; p.gimg_bytes = 0; }
+  if (!tc_layout(plan, p.n_ops, &p, &smem)) return set_error(STMP_EUNSUPPORTED, "tcgen05 graph-GRU kernel needs %d B of shared memory", smem);
+  p.gimg = p.n_ops ? plan->gimg[p.n_ops] : nullptr;
+  if (p.n_ops && !p.gimg) return set_error(STMP_EUNSUPPORTED, "tcgen05 graph-GRU kernel: the plan has no shared-memory graph image");
   int dev = 0, sms = 0;
   STMP_CUDA_OK(cudaGetDevice(&dev));
   STMP_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int grid = (int)(B < sms ? B : sms);
-  static int halves = -1;
-  if (halves < 0) {
-    const char* v = getenv("STMP_DCRNN_TC_HALVES");
-    halves = (v && atoi(v) == 1) ? 1 : 2;   // 2 (default): 16 warps, two channel halves per row; 1: 8 warps
-  }
-  if (halves == 2) {
-    STMP_CUDA_OK(cudaFuncSetAttribute(k_dcrnn_seq_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    k_dcrnn_seq_tc<2><<<grid, 512, smem, st>>>(p);
-  } else {
-    STMP_CUDA_OK(cudaFuncSetAttribute(k_dcrnn_seq_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    k_dcrnn_seq_tc<1><<<grid, 256, smem, st>>>(p);
+  switch (p.CIN) {
+#define STMP_TC_CASE(C)                                                                                              \
+  case C:                                                                                                            \
+    STMP_CUDA_OK(cudaFuncSetAttribute(k_dcrnn_seq_tc<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));        \
+    k_dcrnn_seq_tc<C><<<grid, 512, smem, st>>>(p);                                                                   \
+    break;
+    STMP_TC_CASE(1) STMP_TC_CASE(2) STMP_TC_CASE(3) STMP_TC_CASE(4)
+#undef STMP_TC_CASE
+    default: return set_error(STMP_EUNSUPPORTED, "tcgen05 graph-GRU kernel: cin=%d", p.CIN);
   }
   STMP_LAUNCH_OK("k_dcrnn_seq_tc");
   return STMP_OK;

@@ -17,6 +17,7 @@
 
 #include "common.cuh"
 #include "dcrnn_common.cuh"
+#include "graph_image.cuh"
 
 namespace stmp {
 
@@ -582,44 +583,149 @@ int build_gcn(Builder& b, stmp_plan* p, int n, int e, const int* row, const int*
   return 0;
 }
 
-// ---- shared-memory graph image for the fused tcgen05 kernel (see stmp_plan::gimg) -----------------------------------
-constexpr int kImgPitch = 36, kImgPad = 2, kImgMaxN = 207;
-
-__host__ __device__ inline int img_align16(int v) { return (v + 15) & ~15; }
-
-// One CTA stages the operators exactly like the kernel would (stage_graph) but into global memory.
-// header[0] = number of padded edge entries.
+// ---- shared-memory graph image for the fused tcgen05 kernel (graph_image.cuh) ---------------------------------------
+// One CTA.  Tasks (row, op) are rank-sorted per segment (destination row tile, operator) by descending group count, cut into
+// warp-tasks of four, and dealt longest-first to the least loaded of the 16 warps (loads carry over between the segments,
+// so the whole round is balanced, not each segment); then the padded edge groups are written.
 __global__ void __launch_bounds__(512) k_build_graph_image(const int* rp0, const int* rp1, const int2* cv0, const int2* cv1, int N,
-                                                           int n_ops, unsigned char* image, int* header) {
-  int* gstart = reinterpret_cast<int*>(image);
-  int* order = reinterpret_cast<int*>(image + img_align16((2 * N + 1) * 4));
-  int2* ce = reinterpret_cast<int2*>(image + img_align16((2 * N + 1) * 4) + img_align16(2 * N * 4));
-  stage_graph<512>(rp0, rp1, cv0, cv1, N, kImgPitch, ce, gstart, order, threadIdx.x, 1 << 30, n_ops, kImgPad);
+                                                           int n_ops, int nnz_total, unsigned char* image) {
+  __shared__ int s_ng[2 * kImgMaxN], s_g0[2 * kImgMaxN + 1], s_sorted[2 * kImgMaxN];
+  __shared__ unsigned char s_owner[2 * kImgMaxN / 4 + 8];
+  __shared__ int s_segcount[kImgSegs], s_valid;
+  const int NT = n_ops * N, tid = threadIdx.x;
+  const GraphImageLayout L = graph_image_layout(NT, nnz_total);
+  int* hdr = reinterpret_cast<int*>(image);
+  uint16_t* wstart = reinterpret_cast<uint16_t*>(image + L.off_wstart);
+  uint16_t* wcount = reinterpret_cast<uint16_t*>(image + L.off_wcount);
+  uint32_t* wt = reinterpret_cast<uint32_t*>(image + L.off_wt);
+  uint32_t* idx4 = reinterpret_cast<uint32_t*>(image + L.off_idx);
+  float4* val4 = reinterpret_cast<float4*>(image + L.off_val);
+  for (int task = tid; task < NT; task += blockDim.x) {
+    const int op = task >= N ? 1 : 0, i = task - op * N;
+    const int* rp = op ? rp1 : rp0;
+    s_ng[task] = (rp[i + 1] - rp[i] + 3) >> 2;
+  }
+  if (tid == 0) s_valid = 1;
   __syncthreads();
-  if (threadIdx.x == 0) header[0] = gstart[n_ops * N];
+  if (tid == 0) {
+    int run = 0, ok = (N <= kImgMaxN) ? 1 : 0;
+    for (int sg = 0; sg < kImgSegs; ++sg) s_segcount[sg] = 0;
+    for (int task = 0; task < NT; ++task) {
+      s_g0[task] = run;
+      run += s_ng[task];
+      if (s_ng[task] > 127) ok = 0;
+      const int op = task >= N ? 1 : 0;
+      ++s_segcount[((task - op * N) >= 128 ? 2 : 0) + op];
+    }
+    s_g0[NT] = run;
+    if (run > 65535 || run + 1 > L.cap_groups) ok = 0;
+    s_valid = ok;
+  }
+  __syncthreads();
+  // rank sort: (segment asc, group count desc, task id asc)
+  for (int task = tid; task < NT; task += blockDim.x) {
+    const int seg = ((task >= N ? task - N : task) >= 128 ? 2 : 0) + (task >= N ? 1 : 0), ng = s_ng[task];
+    int rank = 0;
+    for (int o = 0; o < NT; ++o) {
+      const int so = ((o >= N ? o - N : o) >= 128 ? 2 : 0) + (o >= N ? 1 : 0), no = s_ng[o];
+      rank += (so < seg) || (so == seg && (no > ng || (no == ng && o < task)));
+    }
+    s_sorted[rank] = task;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int load[kImgWarps], cntw[kImgWarps], pos[kImgWarps];
+    for (int w = 0; w < kImgWarps; ++w) load[w] = 0;
+    int nwt = 0;
+    int base = 0;
+    for (int seg = 0; seg < kImgSegs; base += s_segcount[seg], ++seg) {
+      const int cnt = s_segcount[seg], nw = (cnt + 3) >> 2;
+      for (int w = 0; w < kImgWarps; ++w) cntw[w] = 0;
+      for (int k = 0; k < nw; ++k) {                      // longest warp-task first onto the least loaded warp
+        int best = 0;
+        for (int w = 1; w < kImgWarps; ++w)
+          if (load[w] < load[best]) best = w;
+        s_owner[k] = (unsigned char)best;
+        load[best] += 2 * s_ng[s_sorted[base + 4 * k]] + 3;   // ~ issue slots: per group 6 loads + 8 FMA2, per task a split store
+        ++cntw[best];
+      }
+      int run = nwt;
+      for (int w = 0; w < kImgWarps; ++w) {
+        wstart[w * kImgSegs + seg] = (uint16_t)run;
+        wcount[w * kImgSegs + seg] = (uint16_t)cntw[w];
+        pos[w] = run;
+        run += cntw[w];
+      }
+      for (int k = 0; k < nw; ++k) {
+        const int slot = pos[s_owner[k]]++;
+        for (int qd = 0; qd < 4; ++qd) {
+          uint32_t d = kImgNoTask;
+          if (4 * k + qd < cnt) {
+            const int task = s_sorted[base + 4 * k + qd];
+            const int op = task >= N ? 1 : 0, i = task - op * N;
+            d = (uint32_t)i | ((uint32_t)op << 8) | ((uint32_t)s_ng[task] << 9) | ((uint32_t)s_g0[task] << 16);
+          }
+          wt[slot * 4 + qd] = d;
+        }
+      }
+      nwt = run;
+    }
+    hdr[0] = nwt;
+    hdr[1] = s_g0[NT];
+    hdr[2] = (s_valid && nwt <= L.cap_wt) ? 1 : 0;
+    hdr[3] = 0;
+  }
+  if (!s_valid) return;
+  // padded edge groups: pad entries read the all-zero row with value 0
+  for (int task = tid; task < NT; task += blockDim.x) {
+    const int op = task >= N ? 1 : 0, i = task - op * N;
+    const int* rp = op ? rp1 : rp0;
+    const int2* cv = op ? cv1 : cv0;
+    const int beg = rp[i], len = rp[i + 1] - beg;
+    for (int g = 0; g < s_ng[task]; ++g) {
+      uint32_t u = 0;
+      float v[4];
+      for (int e = 0; e < 4; ++e) {
+        const int k = 4 * g + e;
+        const int2 c = k < len ? cv[beg + k] : make_int2(kImgZeroRow, 0);
+        u |= ((uint32_t)c.x & 0xffu) << (8 * e);
+        v[e] = __int_as_float(c.y);
+      }
+      idx4[s_g0[task] + g] = u;
+      val4[s_g0[task] + g] = make_float4(v[0], v[1], v[2], v[3]);
+    }
+  }
+  if (tid == 0) {   // the spare group the gather loop prefetches past the last task
+    idx4[s_g0[NT]] = kImgZeroRow * 0x01010101u;
+    val4[s_g0[NT]] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
 }
 
 int build_graph_images(Builder& b, stmp_plan* p) {
   if (p->n > kImgMaxN) return 0;
   const int N = p->n;
-  int* d_hdr = b.talloc<int>(4);
-  if (!d_hdr) return b.rc;
+  int hdr[3][4] = {{0}};
   for (int n_ops = 1; n_ops <= p->n_ops; ++n_ops) {
     int nnz = 0;
     for (int op = 0; op < n_ops; ++op) nnz += p->fwd[op].nnz;
-    const int cap = img_align16((2 * N + 1) * 4) + img_align16(2 * N * 4) + (nnz + 2 * N * (kImgPad - 1) + 4) * 8;
-    STMP_CUDA_OK(cudaMalloc(&p->gimg[n_ops], (size_t)cap));
-    STMP_CUDA_OK(cudaMemsetAsync(p->gimg[n_ops], 0, (size_t)cap, b.st));
+    const GraphImageLayout L = graph_image_layout(n_ops * N, nnz);
+    if (L.bytes > 160 * 1024) continue;                       // cannot fit beside the operand panels anyway
+    STMP_CUDA_OK(cudaMalloc(&p->gimg[n_ops], (size_t)L.bytes));
+    STMP_CUDA_OK(cudaMemsetAsync(p->gimg[n_ops], 0, (size_t)L.bytes, b.st));
     const Csr& c1 = p->fwd[n_ops > 1 ? 1 : 0];
-    k_build_graph_image<<<1, 512, 0, b.st>>>(p->fwd[0].rowptr, c1.rowptr, p->fwd[0].cv, c1.cv, N, n_ops,
-                                             reinterpret_cast<unsigned char*>(p->gimg[n_ops]), d_hdr + n_ops);
+    k_build_graph_image<<<1, 512, 0, b.st>>>(p->fwd[0].rowptr, c1.rowptr, p->fwd[0].cv, c1.cv, N, n_ops, nnz,
+                                             reinterpret_cast<unsigned char*>(p->gimg[n_ops]));
     STMP_LAUNCH_OK("k_build_graph_image");
+    STMP_CUDA_OK(cudaMemcpyAsync(hdr[n_ops], p->gimg[n_ops], 16, cudaMemcpyDeviceToHost, b.st));
+    p->gimg_bytes[n_ops] = L.bytes;
   }
-  int h[4] = {0, 0, 0, 0};
-  STMP_CUDA_OK(cudaMemcpyAsync(h, d_hdr, sizeof(h), cudaMemcpyDeviceToHost, b.st));
   STMP_CUDA_OK(cudaStreamSynchronize(b.st));
   for (int n_ops = 1; n_ops <= p->n_ops; ++n_ops)
-    p->gimg_bytes[n_ops] = img_align16(img_align16((2 * N + 1) * 4) + img_align16(2 * N * 4) + h[n_ops] * 8);
+    if (p->gimg[n_ops] && !hdr[n_ops][2]) {                    // rows too long / too many groups for the compact format
+      cudaFree(p->gimg[n_ops]);
+      p->gimg[n_ops] = nullptr;
+      p->gimg_bytes[n_ops] = 0;
+    }
   return 0;
 }
 

@@ -4,9 +4,12 @@
 // metadata is one 64-bit load per edge, and E gathers are kept in flight (unroll 4) to cover L2 latency.
 // Deterministic: per destination the sum runs in the reference's scatter order with separate
 // multiply and add, which makes the result bit-identical to CPU index_select -> mul -> scatter_add_.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace stmp {
+int g_spmm_variant = -1;   // 0: k_spmm (broadcast entry loads, 4 deep); 1: k_spmm_pre<.,4>; 2: k_spmm_pre<.,8> (default)
 namespace {
 
 template <int VEC> struct VecT;
@@ -111,6 +114,67 @@ __global__ void __launch_bounds__(256) k_spmm(SpmmArgs a, int G, int log2G) {
   }
 }
 
+// The same product with the row's edge entries fetched ONCE by the group (lane l loads entry l: one coalesced 8-byte load per
+// lane instead of a dependent broadcast load in front of every batch of gathers) and handed out by shuffles, so that U
+// gathers are in flight per group and a row costs one entry-load latency + ceil(deg/U) gather latencies.  Same arithmetic
+// (CSR order, separate multiply and add) => bit-identical to k_spmm.  No attention operand (that path keeps k_spmm).
+template <int VEC, int U>
+__global__ void __launch_bounds__(256) k_spmm_pre(SpmmArgs a, int G, int log2G) {
+  const int l = threadIdx.x & (G - 1);
+  const long long group = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> log2G;
+  const long long total = a.batch * (long long)a.n;
+  // whole groups retire together (total groups is padded to the warp by the launch: lanes of absent groups idle but must shuffle)
+  const bool present = group < total;
+  const int i = present ? (int)(group % a.n) : 0;
+  const long long b = present ? group / a.n : 0;
+  const float* xb = a.x + b * a.bsx;
+  const int beg = present ? a.rowptr[i] : 0, end = present ? a.rowptr[i + 1] : 0;
+  const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) & ~(G - 1)));
+
+  for (int f0 = l * VEC; f0 < ((a.f + G * VEC - 1) / (G * VEC)) * (G * VEC); f0 += G * VEC) {
+    const bool fl = f0 < a.f;                       // lanes past the feature tail still take part in the shuffles
+    const float* xr = xb + f0;
+    const int ldx = (int)a.ldx;                     // host guarantees n * ldx < 2^31: 32-bit row offsets
+    float acc[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
+    for (int c0 = beg; c0 < end; c0 += G) {
+      const int2 mine = (c0 + l < end) ? __ldg(&a.cv[c0 + l]) : make_int2(0, 0);
+      const int nh = min(G, end - c0);
+      for (int u0 = 0; u0 < nh; u0 += U) {
+        float w[U];
+        float xv[U][VEC];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int col = __shfl_sync(gmask, mine.x, u0 + u, G);
+          w[u] = __int_as_float(__shfl_sync(gmask, mine.y, u0 + u, G));
+          if (u0 + u < nh && fl) ld_vec<VEC>(xr + col * ldx, xv[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if (u0 + u < nh) {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) acc[v] = __fadd_rn(acc[v], __fmul_rn(w[u], xv[u][v]));
+          }
+      }
+    }
+    if (present && fl) {
+      float o[VEC];
+      if (a.z) {
+        float zv[VEC];
+        ld_vec<VEC>(a.z + b * a.bsz + (long long)i * a.ldz + f0, zv);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) o[v] = __fadd_rn(__fmul_rn(a.alpha, acc[v]), __fmul_rn(a.beta, zv[v]));
+      } else {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) o[v] = (a.alpha == 1.0f) ? acc[v] : __fmul_rn(a.alpha, acc[v]);
+      }
+      st_vec<VEC>(a.y + b * a.bsy + (long long)i * a.ldy + f0, o);
+    }
+  }
+}
+
+
 // d(att)[b,i,c] += val * <gy[b,i,:], x[b,c,:]> : one warp per (b, entry); entries are unique (dst,src)
 // pairs except the doubled self loops of CHEB_ATT, hence atomicAdd.
 __global__ void __launch_bounds__(256) k_att_grad(const int* __restrict__ rowptr, const int2* __restrict__ cv, int n,
@@ -175,6 +239,23 @@ extern "C" int stmp_spmm(const stmp_plan* plan, int op, int transposed, int64_t 
   long long blocks = (threads + 255) / 256;
   STMP_REQUIRE(blocks < (1ll << 31), STMP_ESHAPE, "stmp_spmm: problem too large for one launch");
   cudaStream_t st = (cudaStream_t)stream;
+  if (g_spmm_variant < 0) {
+    const char* v = getenv("STMP_SPMM_VARIANT");
+    g_spmm_variant = v ? atoi(v) : 2;
+  }
+  if (!att && g_spmm_variant > 0 && (long long)c.n * ldx < (1ll << 31)) {
+    if (g_spmm_variant == 1) {
+      if (vec == 4) k_spmm_pre<4, 4><<<(unsigned)blocks, 256, 0, st>>>(a, G, lg);
+      else if (vec == 2) k_spmm_pre<2, 4><<<(unsigned)blocks, 256, 0, st>>>(a, G, lg);
+      else k_spmm_pre<1, 4><<<(unsigned)blocks, 256, 0, st>>>(a, G, lg);
+    } else {
+      if (vec == 4) k_spmm_pre<4, 8><<<(unsigned)blocks, 256, 0, st>>>(a, G, lg);
+      else if (vec == 2) k_spmm_pre<2, 8><<<(unsigned)blocks, 256, 0, st>>>(a, G, lg);
+      else k_spmm_pre<1, 8><<<(unsigned)blocks, 256, 0, st>>>(a, G, lg);
+    }
+    STMP_LAUNCH_OK("k_spmm_pre");
+    return STMP_OK;
+  }
   if (vec == 4) k_spmm<4><<<(unsigned)blocks, 256, 0, st>>>(a, G, lg);
   else if (vec == 2) k_spmm<2><<<(unsigned)blocks, 256, 0, st>>>(a, G, lg);
   else k_spmm<1><<<(unsigned)blocks, 256, 0, st>>>(a, G, lg);

@@ -14,6 +14,15 @@ class _A3Base(torch.nn.Module):
         _require_cuda(X, "X")
         base = self._base_tgcn
         P = X.shape[-1]
+        if base._attn_ok(X, H, P, self._attention):
+            # ONE launch: gather A^X for all periods per node, the GRU gates of every period and the softmax-weighted sum
+            N, F = X.shape[-3], X.shape[-2]
+            plan = base._plan(edge_index, edge_weight, N)
+            A, Bm, c = base._packed3()
+            probs = torch.nn.functional.softmax(self._attention.detach(), dim=0)
+            if X.dim() == 3:                                        # A3TGCN: (N,F,P), H (N,out)
+                return ops.tgcn_attn_fwd(plan, X.unsqueeze(0), A, Bm, c, probs, H, h_shared=True)[0]
+            return ops.tgcn_attn_fwd(plan, X, A, Bm, c, probs, H)   # A3TGCN2: (B,N,F,P), H (B,N,out)
         # (..., N, F, P) -> (P, ..., N, F): periods become the leading batch axis of the SpMM
         Xp = X.movedim(-1, 0).contiguous()
         lead = Xp.shape[:-2]

@@ -67,6 +67,38 @@ class TGCN(torch.nn.Module):
             return W, b, ops.gru_weight_image(W, b)
         return self._pack.get(list(self.parameters()), build)
 
+    def _packed3(self):
+        """The same folding for `stmp_tgcn_attn_fwd` (any graph size):  pre_g = (A^X) A[:, g] + H' Bm[:, g] + c[g]
+        with A = (L1 W)^T (in x out), Bm = L2^T (out x out), c = L1 b + l;  columns z | r | h."""
+        def build():
+            Ci, Co, dev = self.in_channels, self.out_channels, self.conv_z.lin.weight.device
+            A = torch.zeros(Ci, 96, device=dev)
+            Bm = torch.zeros(32, 96, device=dev)
+            c = torch.zeros(96, device=dev)
+            for gi, g in enumerate("zrh"):
+                conv, lin = getattr(self, f"conv_{g}"), getattr(self, f"linear_{g}")
+                L1, L2 = lin.weight[:, :Co], lin.weight[:, Co:]
+                r = slice(32 * gi, 32 * gi + Co)
+                A[:, r] = (L1 @ conv.lin.weight).t()
+                Bm[:Co, r] = L2.t()
+                c[r] = L1 @ conv.bias + lin.bias
+            return A, Bm, c
+        if not hasattr(self, "_pack3"):
+            self._pack3 = ops.PackCache()
+        return self._pack3.get(list(self.parameters()), build)
+
+    def _no_grad_needed(self, X, H, *extra):
+        if not torch.is_grad_enabled():
+            return True
+        ts = list(self.parameters()) + [X] + ([] if H is None else [H]) + list(extra)
+        return not any(t.requires_grad for t in ts)
+
+    def _attn_ok(self, X, H, periods, *extra):
+        """The fused temporal-attention + GCN kernel serves inference for out_channels == 32, in_channels <= 4 and
+        in_channels * periods <= 128 on graphs of any size."""
+        return (self.out_channels == 32 and self.in_channels <= 4 and self.in_channels * periods <= 128
+                and self._no_grad_needed(X, H, *extra))
+
     def _fused_ok(self, plan, X, H):
         if self.out_channels != 32:
             return False
@@ -78,9 +110,15 @@ class TGCN(torch.nn.Module):
     def forward(self, X: torch.FloatTensor, edge_index: torch.LongTensor, edge_weight: torch.FloatTensor = None,
                 H: torch.FloatTensor = None) -> torch.FloatTensor:
         _require_cuda(X, "X")
+        plan = self._plan(edge_index, edge_weight, X.size(-2))
+        if self._attn_ok(X, H, 1):       # one period, weight 1: the cell itself
+            A, Bm, c = self._packed3()
+            N, Ci = X.shape[-2], X.shape[-1]
+            h = None if H is None else H.reshape(-1, N, self.out_channels)
+            out = ops.tgcn_attn_fwd(plan, X.reshape(-1, N, Ci, 1), A, Bm, c, None, h)
+            return out.reshape(*X.shape[:-1], self.out_channels)
         if H is None:
             H = torch.zeros(*X.shape[:-1], self.out_channels, device=X.device, dtype=X.dtype)
-        plan = self._plan(edge_index, edge_weight, X.size(-2))
         if self._fused_ok(plan, X, H):   # every (batch) row is an independent 1-step window of the fused kernel
             W, b, img = self._packed()
             N, Ci = X.shape[-2], X.shape[-1]

@@ -151,6 +151,31 @@ def gru_seq_fwd(plan: GraphPlan, n_ops: int, x: torch.Tensor, wcat: torch.Tensor
     return out
 
 
+def tgcn_attn_fwd(plan: GraphPlan, x: torch.Tensor, A: torch.Tensor, Bm: torch.Tensor, c: torch.Tensor,
+                  probs: Optional[torch.Tensor] = None, h: Optional[torch.Tensor] = None, h_shared: bool = False) -> torch.Tensor:
+    """Fused A3TGCN(2) / TGCN(2) forward (stmp_tgcn_attn_fwd).  x (B,N,Fin,P) -> (B,N,32); h (B,N,32), or (N,32) with
+    h_shared=True (the same state for every batch row), or None (zeros)."""
+    x = _f32c(x, "X")
+    if x.dim() != 4 or x.size(1) != plan.num_nodes:
+        raise RuntimeError(f"X must be (B,{plan.num_nodes},Fin,P), got {tuple(x.shape)}")
+    B, N, fin, P = x.shape
+    A, Bm, c = _f32c(A, "A"), _f32c(Bm, "Bm"), _f32c(c, "c")
+    if A.shape != (fin, 96) or Bm.shape != (32, 96) or c.numel() != 96:
+        raise RuntimeError("folded weights must be A (Fin,96), Bm (32,96), c (96,)")
+    out = torch.empty((B, N, 32), dtype=torch.float32, device=x.device)
+    if B == 0:
+        return out
+    hc, hs = None, 0
+    if h is not None:
+        hc = _f32c(h, "H")
+        hs = 0 if h_shared else N * 32
+    pr = None if probs is None else _f32c(probs.detach(), "probs")
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().stmp_tgcn_attn_fwd(plan.handle, B, fin, P, _lib.ptr(x), _lib.ptr(hc), hs, _lib.ptr(A), _lib.ptr(Bm),
+                                                 _lib.ptr(c), _lib.ptr(pr), _lib.ptr(out), _lib.stream_ptr()))
+    return out
+
+
 def spmm_cols(plan: GraphPlan, op: int, buf: torch.Tensor, src_col: int, dst_col: int, width: int, alpha: float = 1.0,
               z_col: Optional[int] = None, beta: float = 0.0, transposed: bool = False):
     """In-place column-block product inside one basis buffer `buf` (..., N, LD):

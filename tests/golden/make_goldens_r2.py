@@ -44,7 +44,27 @@ def dcrnn_cfg2_grads():
          grads={k: p.grad.detach().clone() for k, p in m.named_parameters()}, K=2)
 
 
-GENERATORS = {"dcrnn_cfg2_grads": dcrnn_cfg2_grads}
+def a3tgcn2_cfg3():
+    at = refload.load("nn.recurrent.attentiontemporalgcn")
+    tg = refload.load("nn.recurrent.temporalgcn")
+    ei, ew, _ = synthetic.pems_bay_like(0, 16)
+    ei_t, ew_t = torch.from_numpy(ei), torch.from_numpy(ew)
+    torch.manual_seed(0)
+    m = at.A3TGCN2(2, 32, 12, 64)
+    g = torch.Generator().manual_seed(5)
+    X = torch.randn(8, 325, 2, 12, generator=g)
+    H = torch.randn(8, 325, 32, generator=g) * 0.5
+    m1 = at.A3TGCN(2, 32, 12)
+    c2 = tg.TGCN2(2, 32, 8)
+    with torch.no_grad():
+        out, outH = m(X, ei_t, ew_t), m(X, ei_t, ew_t, H)
+        out1, out1H = m1(X[0], ei_t, ew_t), m1(X[0], ei_t, ew_t, H[0])
+        cell, cellH = c2(X[..., 0], ei_t, ew_t), c2(X[..., 0], ei_t, ew_t, H)
+    save("a3tgcn2_cfg3", edge_index=ei_t, edge_weight=ew_t, X=X, H=H, state=sd(m), out=out, outH=outH,
+         state1=sd(m1), out1=out1, out1H=out1H, state_cell=sd(c2), cell=cell, cellH=cellH)
+
+
+GENERATORS = {"dcrnn_cfg2_grads": dcrnn_cfg2_grads, "a3tgcn2_cfg3": a3tgcn2_cfg3}
 
 
 if __name__ == "__main__":

@@ -109,16 +109,56 @@ def test_a3tgcn_goldens(golden_dir):
     _close(m1(g["X1"].to(DEV), ei, ew), g["out1"])
 
 
+def _ran(before, name):
+    return _lib.path_counters().get(name, 0) - before.get(name, 0)
+
+
 def test_a3tgcn2_config3_shape_vs_oracle():
-    """BASELINE config 3: A3TGCN2 on the PEMS-BAY shape (325 nodes, batch 64, 12 periods)."""
+    """BASELINE config 3: A3TGCN2 on the PEMS-BAY shape (325 nodes, batch 64, 12 periods) through the fused
+    temporal-attention + GCN kernel (stmp_tgcn_attn_fwd) -- ALL 64 rows against the oracle, with and without an incoming H."""
     ei, ew, _ = synthetic.pems_bay_like(0, 16)
     ei, ew = torch.from_numpy(ei), torch.from_numpy(ew)
     torch.manual_seed(0)
     m = A3TGCN2(2, 32, 12, 64)
-    X = torch.randn(8, 325, 2, 12)  # oracle on 8 of the 64 batch rows (seconds on CPU)
-    want = R.a3tgcn(m.state_dict(), X, ei, ew)
-    got = m.to(DEV)(X.to(DEV), ei.to(DEV), ew.to(DEV))
+    X = torch.randn(64, 325, 2, 12)
+    H = torch.randn(64, 325, 32) * 0.5
+    with torch.no_grad():
+        want = R.a3tgcn(m.state_dict(), X, ei, ew)
+        wantH = R.a3tgcn(m.state_dict(), X, ei, ew, H)
+        md = m.to(DEV)
+        c0 = _lib.path_counters()
+        got = md(X.to(DEV), ei.to(DEV), ew.to(DEV))
+        gotH = md(X.to(DEV), ei.to(DEV), ew.to(DEV), H.to(DEV))
+    assert _ran(c0, "k_tgcn_attn") == 2 and _ran(c0, "k_spmm") == 0 and _ran(c0, "k_spmm_pre") == 0     # the fused kernel served both calls
     _close(got, want)
+    _close(gotH, wantH)
+    # training still goes through the differentiable tiled path and agrees with the fused inference result
+    out_t = md(X[:4].to(DEV), ei.to(DEV), ew.to(DEV), H[:4].to(DEV))
+    assert out_t.requires_grad
+    _close(out_t, wantH[:4])
+
+
+def test_a3tgcn_family_config3_vs_reference_golden(golden_dir):
+    """The UNMODIFIED reference modules at the PEMS-BAY shape (tests/golden/make_goldens_r2.py): A3TGCN2, A3TGCN (one shared
+    state) and a TGCN2 cell (the one-period case of the same kernel)."""
+    from pytorch_geometric_temporal_b200.nn.recurrent import TGCN2
+    g = _load(golden_dir, "a3tgcn2_cfg3")
+    ei, ew, X, H = (g[k].to(DEV) for k in ("edge_index", "edge_weight", "X", "H"))
+    c0 = _lib.path_counters()
+    with torch.no_grad():
+        m = A3TGCN2(2, 32, 12, 64).to(DEV)
+        m.load_state_dict(g["state"])
+        _close(m(X, ei, ew), g["out"])
+        _close(m(X, ei, ew, H), g["outH"])
+        m1 = A3TGCN(2, 32, 12).to(DEV)
+        m1.load_state_dict(g["state1"])
+        _close(m1(X[0], ei, ew), g["out1"])
+        _close(m1(X[0], ei, ew, H[0]), g["out1H"])
+        c2 = TGCN2(2, 32, 8).to(DEV)
+        c2.load_state_dict(g["state_cell"])
+        _close(c2(X[..., 0], ei, ew), g["cell"])
+        _close(c2(X[..., 0], ei, ew, H), g["cellH"])
+    assert _ran(c0, "k_tgcn_attn") == 6
 
 
 def test_astgcn_goldens(golden_dir):

@@ -207,6 +207,37 @@ def test_tgcn_family_host_logic(golden_dir, dense_dconv_gcn_ops):
     _close(m1(g["X1"], g["edge_index"], g["edge_weight"]), g["out1"])
 
 
+def test_tgcn_attention_folding_host_logic_vs_reference_golden(golden_dir, dense_dconv_gcn_ops, monkeypatch):
+    """Host side of the fused temporal-attention + GCN kernel (stmp_tgcn_attn_fwd): the folded weights (A, Bm, c) of
+    `TGCN._packed3`, the period softmax and the call shapes, with the kernel replaced by a dense restatement of its
+    arithmetic -- against the UNMODIFIED reference modules at the PEMS-BAY shape (325 nodes)."""
+    def fake_kernel(plan, x, A, Bm, c, probs=None, h=None, h_shared=False):
+        B, N, Fi, P = x.shape
+        L = plan.mats[0]
+        H = torch.zeros(B, N, 32) if h is None else (h.expand(B, N, 32) if h_shared else h.reshape(B, N, 32))
+        out = torch.zeros(B, N, 32)
+        for t in range(P):
+            ax = torch.matmul(L, x[..., t])                                     # (B,N,Fi): A^ X_t
+            pre = lambda g, Hp: ax @ A[:, 32 * g:32 * g + 32] + Hp @ Bm[:, 32 * g:32 * g + 32] + c[32 * g:32 * g + 32]
+            Z, Rg = torch.sigmoid(pre(0, H)), torch.sigmoid(pre(1, H))
+            Hn = Z * H + (1 - Z) * torch.tanh(pre(2, H * Rg))
+            out = out + (Hn if probs is None else probs[t] * Hn)
+        return out
+    monkeypatch.setattr(ops, "tgcn_attn_fwd", fake_kernel)
+    g = _load(golden_dir, "a3tgcn2_cfg3")
+    ei, ew, X, H = g["edge_index"], g["edge_weight"], g["X"], g["H"]
+    with torch.no_grad():
+        m = A3TGCN2(2, 32, 12, 64)
+        m.load_state_dict(g["state"])
+        _close(m(X, ei, ew), g["out"]); _close(m(X, ei, ew, H), g["outH"])
+        m1 = A3TGCN(2, 32, 12)
+        m1.load_state_dict(g["state1"])
+        _close(m1(X[0], ei, ew), g["out1"]); _close(m1(X[0], ei, ew, H[0]), g["out1H"])
+        c2 = TGCN2(2, 32, 8)
+        c2.load_state_dict(g["state_cell"])
+        _close(c2(X[..., 0], ei, ew), g["cell"]); _close(c2(X[..., 0], ei, ew, H), g["cellH"])
+
+
 # ---- ASTGCN: attention-weighted first hop, timesteps folded into the feature axis, fp32 time convolutions ---------------
 import pytorch_geometric_temporal_b200.nn.attention.astgcn as astgcn_mod  # noqa: E402
 from oracle import attention as OA  # noqa: E402
