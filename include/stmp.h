@@ -109,6 +109,12 @@ int stmp_spmm(const stmp_plan* plan, int op, int transposed, int64_t batch, int6
               float alpha, const float* z, int64_t ldz, int64_t bsz, float beta,
               const float* att, void* stream);
 
+/* The forward product with the attention handed in TRANSPOSED and row-padded: entry (dst, src) uses attT[b, src, dst], rows att_ld
+ * floats apart (the layout stmp_spatial_attention_fwd writes: softmax over dim 1 of S is a row softmax of S^T). */
+int stmp_spmm_att_t(const stmp_plan* plan, int op, int64_t batch, int64_t f, const float* x, int64_t ldx, int64_t bsx, float* y,
+                   int64_t ldy, int64_t bsy, float alpha, const float* z, int64_t ldz, int64_t bsz, float beta, const float* attT,
+                   int64_t att_ld, void* stream);
+
 /* d(att)[b,dst,src] += val * <gy[b,dst,:], x[b,src,:]> for every entry of `op` (backward of the
  * attention-weighted first hop, astgcn.py:156-170).  datt must be zero-initialised by the caller. */
 int stmp_spmm_att_grad(const stmp_plan* plan, int op, int64_t batch, int64_t f, const float* gy,
@@ -257,6 +263,26 @@ int stmp_gemm_lstm_f32(const float* A, int64_t lda, int64_t M, int64_t K, int64_
                        const float* conv_bias, const float* cell, const float* wci, const float* wcf, const float* wco,
                        const float* bi, const float* bf, const float* bc, const float* bo, float* h_out, float* c_out,
                        void* stream);
+
+/* ---- ASTGCN block (nn/attention/astgcn.py:408-481): the dense products on tcgen05 with their operand gathers and pointwise tails fused
+ * stmp_gemm_blocks_f32:  C[m, 0:ncols] = epilogue( sum_i A_i[m + shift_i, 0:width_i] @ W_i + bias )
+ *   the A operand is a list of nblk (<= 12) K-blocks of <= 64 columns: blk_ptr[i] (device pointer, HOST array), row stride blk_ld[i],
+ *   valid columns blk_width[i], row shift blk_shift[i] inside sequences of `seq` consecutive rows (rows shifted out of their sequence read
+ *   as zero).  packed = stmp_gemm_prepack of the stacked weight [nblk*64][N] (rows of a block beyond its width are zero), N % 16 == 0,
+ *   N <= 320.  epilogue 0: + bias; 1: + bias, ReLU; 2: + bias, ReLU, LayerNorm(gamma, beta, eps) over the row (N == ncols == 64).
+ *   With channels-last activations (B, nodes, T, F) this is: the Chebyshev contraction sum_k T_k W_k + ReLU (astgcn.py:166-178,448) with
+ *   blocks T_0|T_1|T_2; time convolution (1x3, padding 1) + residual 1x1 convolution + ReLU + LayerNorm (:473-480) with blocks
+ *   X^[t-1] | X^[t] | X^[t+1] | X[t], seq = T; the final (1 x F) convolution (:604-610) with the T blocks of a row.
+ * stmp_spatial_attention_fwd:  S = softmax_dim1(Vs @ sigmoid(LHS @ RHS + bs)) (astgcn.py:245-262), written TRANSPOSED:
+ *   st_out[b, j, i] = S[b, i, j], rows ld_out (>= nodes rounded up to 64, % 4 == 0) floats apart, padding columns zero.
+ *   lhs [B][nodes][T] = (X~ W1) W2, rhs [B][T][nodes] = (W3 X~)^T, bsT [nodes][nodes] = bs^T, vsT_packed = stmp_gemm_prepack of Vs^T
+ *   zero-padded to [P][P], P = nodes rounded up to 64 (<= 320).  The N x N sigmoid is generated inside the GEMM's operand stage and the
+ *   softmax is the GEMM epilogue: neither ever reaches HBM.  nodes <= 320, T <= 16. */
+int stmp_gemm_blocks_f32(int64_t M, int64_t N, int64_t ncols, int64_t nblk, const float* const* blk_ptr, const int64_t* blk_ld,
+                         const int32_t* blk_width, const int32_t* blk_shift, int64_t seq, const void* packed, const float* bias,
+                         int epilogue, const float* gamma, const float* beta, float eps, float* C, int64_t ldc, void* stream);
+int stmp_spatial_attention_fwd(int64_t B, int64_t n_nodes, int64_t n_steps, const float* lhs, const float* rhs, const float* bsT,
+                               const void* vsT_packed, float* st_out, int64_t ld_out, void* stream);
 
 /* ---- K8: index-batching window gather -----------------------------------------------------------
  * x[b] = series[start[b] : start[b]+h], y[b] = series[start[b]+h : start[b]+2h]   (index_dataset.py:49-57

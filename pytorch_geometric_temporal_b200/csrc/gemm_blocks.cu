@@ -1,0 +1,406 @@
+// gemm_blocks.cu -- the dense products of an ASTGCN block (nn/attention/astgcn.py) on the 5th-gen tensor cores, fp32 in / fp32 out,
+// with the operand GATHER and the pointwise tail of each product fused into one kernel:
+//
+//   C[m, :] = epilogue( sum_blocks  A_blk[row(m) + shift_blk, 0:width_blk] @ W_blk  + bias )
+//
+// * the A operand is a list of up to 12 K-blocks (<= 64 columns each) that may come from DIFFERENT tensors and may be SHIFTED by
+//   whole rows inside sequences of `seq` rows (out-of-sequence rows read as zero).  With activations kept channels-last
+//   (B, N, T, F) this expresses, without any im2col / cat / permute in HBM:
+//     - the Chebyshev contraction  sum_k T_k W_k            (astgcn.py:166-178)      blocks = T_0 | T_1 | T_2, epilogue ReLU (:448)
+//     - time convolution (1x3, pad 1) + residual 1x1 convolution + ReLU + LayerNorm   (:473-480)
+//                                                            blocks = X^[t-1] | X^[t] | X^[t+1] | X[t], epilogue ReLU + LayerNorm
+//     - the final (1 x F_t) convolution over (T, F_t)        (:604-610)               blocks = the T*F_t columns of a row
+// * MODE_SPATT generates the A operand instead of loading it: spatial attention (astgcn.py:245-262)
+//     S = softmax_dim1( Vs @ sigmoid(LHS @ RHS + bs) )   is computed TRANSPOSED,  S^T[b] = sigmoid(...)^T @ Vs^T, rows (b, j):
+//     A[(b,j)][k] = sigmoid( sum_t LHS[b,k,t] RHS[b,t,j] + bs[k][j] )  is formed on the fly from the two (B,N,T) factors, and the
+//     softmax over dim 1 of S becomes a softmax over the COLUMNS of each output row -- thread-local in the epilogue (TMEM lane ==
+//     row).  2 B N^3 FLOPs, the one GEMM of the model SURVEY calls a tensor-core target, never materialises the N x N sigmoid.
+// * fp32-class accuracy from fp16 tensor cores: operands split into hi = fp16(v), lo = fp16(v - hi), three tcgen05.mma.kind::f16
+//   passes lo*hi + hi*lo + hi*hi into the fp32 TMEM accumulator (as gemm_tc.cu / dcrnn_seq_tc.cu; tools/tc_probe.cu).
+// One CTA = 128 rows x all N (<= 320) columns; N > 256 runs as two MMA column halves.  2-stage pipeline: the tile of k-block i+1 is
+// loaded / generated / converted while the MMAs of k-block i run.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace stmp {
+namespace {
+
+constexpr int GB_NT = 256;
+constexpr int GB_BM = 128;
+constexpr int GB_A_BYTES = GB_BM * 128;   // one K-block of A (hi or lo): 128 rows x 64 fp16
+constexpr int GB_MAXBLK = 12;
+
+enum { EPI_BIAS = 0, EPI_RELU = 1, EPI_RELU_LN = 2, EPI_SOFTMAX = 3 };
+
+struct KBlock {
+  const float* ptr;
+  long long ld;     // row stride (floats)
+  int width;        // valid columns (<= 64); the rest of the k-block is zero
+  int shift;        // row shift inside a sequence of `seq` rows
+};
+
+struct GbParams {
+  KBlock blk[GB_MAXBLK];
+  int nblk;
+  int M, N;                 // N % 16 == 0, N <= 320
+  int seq;                  // rows per sequence for shifted blocks (>= 1)
+  const __half* w_hi;       // [N][nblk*64]
+  const __half* w_lo;
+  const float* bias;        // [N] or null
+  float* C; long long ldc;
+  int ncols;                // columns written (<= N)
+  // EPI_RELU_LN (N == 64): LayerNorm over the row
+  const float* gamma; const float* beta; float eps;
+  // MODE_SPATT
+  int spatt;                // 1: generate A
+  int Nn, Tn;               // nodes, timesteps
+  const float* lhs;         // [B][Nn][Tn]
+  const float* rhs;         // [B][Tn][Nn]
+  const float* bsT;         // [Nn][Nn]  bs transposed: bsT[j][k] = bs[k][j]
+};
+
+__device__ __forceinline__ float sigmoid_g(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+
+template <int EPI>
+__global__ void __launch_bounds__(GB_NT, 1) k_gemm_blocks(const GbParams p) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int N = p.N;
+  const int b_bytes = N * 128;                       // one K-block of B (hi or lo)
+  const int stage_bytes = 2 * GB_A_BYTES + 2 * b_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * stage_bytes);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  float* red = reinterpret_cast<float*>(bars + 4);     // [2][128] epilogue exchange (EPI_SOFTMAX)
+
+  const int tm_cols = N > 256 ? 512 : 256;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tm_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    fence_mbar_init();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const long long m0 = (long long)blockIdx.x * GB_BM;
+  const int nkb = p.nblk, Kpad = p.nblk * 64;
+  const int nh = N > 256 ? 2 : 1, Nh = N / nh;        // MMA column halves
+  const uint32_t idesc = umma_idesc_f16(128, Nh);
+
+  // MODE_SPATT per-thread constants: my row (b, j) and its RHS column
+  float rj[16];
+  int sp_b = 0, sp_j = 0;
+  const int sp_r = tid & 127, sp_kh = tid >> 7;
+  if (p.spatt) {
+    const long long m = m0 + sp_r;
+    const long long mm = m < p.M ? m : p.M - 1;
+    sp_b = (int)(mm / p.Nn);
+    sp_j = (int)(mm - (long long)sp_b * p.Nn);
+#pragma unroll
+    for (int t = 0; t < 16; ++t) rj[t] = t < p.Tn ? __ldg(p.rhs + ((long long)sp_b * p.Tn + t) * p.Nn + sp_j) : 0.f;
+  }
+
+  for (int kb = 0; kb < nkb; ++kb) {
+    const int s = kb & 1;
+    unsigned char* a_hi = smem + s * stage_bytes;
+    unsigned char* a_lo = a_hi + GB_A_BYTES;
+    unsigned char* b_hi = a_lo + GB_A_BYTES;
+    unsigned char* b_lo = b_hi + b_bytes;
+    if (kb >= 2) {  // the MMAs of k-block kb-2 must have drained this stage
+      mbar_wait(&bars[s], (uint32_t)((kb >> 1) - 1) & 1u);
+      tc_fence_after();
+    }
+    const int k0 = kb * 64;
+    if (!p.spatt) {
+      // A: 128 x 64 fp32 of block kb (row-shifted, zero outside the sequence / beyond `width`) -> hi/lo fp16, swizzled.
+      const KBlock blk = p.blk[kb];
+      const bool vec = (blk.width % 4 == 0) && (blk.ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(blk.ptr) & 15) == 0);
+      float4 v[8];
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        const int idx = tid + jj * GB_NT;
+        const int r = idx >> 4, c4 = idx & 15;
+        const long long row = m0 + r;
+        const int k = 4 * c4;
+        v[jj] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row < p.M && k < blk.width) {
+          const int tt = (int)(row % p.seq) + blk.shift;
+          if (tt >= 0 && tt < p.seq) {
+            const float* src = blk.ptr + (row + blk.shift) * blk.ld + k;
+            if (vec) {
+              v[jj] = __ldg(reinterpret_cast<const float4*>(src));
+            } else {
+              v[jj].x = __ldg(src);
+              if (k + 1 < blk.width) v[jj].y = __ldg(src + 1);
+              if (k + 2 < blk.width) v[jj].z = __ldg(src + 2);
+              if (k + 3 < blk.width) v[jj].w = __ldg(src + 3);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        const int idx = tid + jj * GB_NT;
+        store_split4(a_hi, a_lo, idx >> 4, 4 * (idx & 15), v[jj]);
+      }
+    } else {
+      // A generated: A[(b,j)][k] = sigmoid(sum_t LHS[b,k,t] RHS[b,t,j] + bsT[j][k]); thread = (row, k half of 32).  LHS rows are
+      // warp-uniform addresses (all rows of a warp share b except across one batch boundary): broadcast loads out of L1.
+      const int Tn = p.Tn;
+      const float* lb = p.lhs + (long long)sp_b * p.Nn * Tn;
+      const float* bsr = p.bsT + (long long)sp_j * p.Nn;
+#pragma unroll 2
+      for (int g = 0; g < 8; ++g) {
+        const int kk = sp_kh * 32 + 4 * g;
+        float o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int k = k0 + kk + e;
+          float acc = 0.f;
+          if (k < p.Nn) {
+            const float* lk = lb + (long long)k * Tn;
+#pragma unroll
+            for (int t = 0; t < 16; ++t)
+              if (t < Tn) acc = fmaf(__ldg(lk + t), rj[t], acc);
+            acc = sigmoid_g(acc + __ldg(bsr + k));
+          }
+          o[e] = acc;
+        }
+        store_split4(a_hi, a_lo, sp_r, kk, make_float4(o[0], o[1], o[2], o[3]));
+      }
+    }
+    // B: N x 64 fp16 (already split, L2-resident) -> swizzled; 4 x (hi, lo) 128-bit loads in flight per thread
+    for (int base = 0; base < N * 8; base += 4 * GB_NT) {
+      uint4 h[4], l[4];
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int idx = base + tid + jj * GB_NT;
+        if (idx < N * 8) {
+          const long long g = (long long)(idx >> 3) * Kpad + k0 + 8 * (idx & 7);
+          h[jj] = __ldg(reinterpret_cast<const uint4*>(p.w_hi + g));
+          l[jj] = __ldg(reinterpret_cast<const uint4*>(p.w_lo + g));
+        }
+      }
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int idx = base + tid + jj * GB_NT;
+        if (idx < N * 8) {
+          const int n = idx >> 3, c = idx & 7;
+          const int off = n * 128 + ((c ^ (n & 7)) << 4);
+          *reinterpret_cast<uint4*>(b_hi + off) = h[jj];
+          *reinterpret_cast<uint4*>(b_lo + off) = l[jj];
+        }
+      }
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (tid == 0) {
+      const uint32_t ah = smem_u32(a_hi), al = smem_u32(a_lo), bh = smem_u32(b_hi), bl = smem_u32(b_lo);
+      for (int hh = 0; hh < nh; ++hh) {
+#pragma unroll
+        for (int pass = 0; pass < 3; ++pass) {          // lo*hi, hi*lo, hi*hi
+          const uint32_t ab = pass == 0 ? al : ah, bb = (pass == 1 ? bl : bh) + hh * Nh * 128;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            umma_f16(tmem + hh * Nh, umma_desc(ab + ks * 32), umma_desc(bb + ks * 32), idesc, (kb | pass | ks) ? 1u : 0u);
+        }
+      }
+      umma_commit(&bars[s]);
+    }
+  }
+  {  // all MMAs complete in order: waiting for the last commit is enough
+    const int last = nkb - 1;
+    mbar_wait(&bars[last & 1], (uint32_t)(last >> 1) & 1u);
+    tc_fence_after();
+  }
+
+  // ---- epilogue: TMEM lane == row ----------------------------------------------------------------------------------------
+  const int q = warp & 3, half = warp >> 2;
+  const long long row = m0 + q * 32 + lane;
+  const bool live = row < p.M;
+  const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
+  if (EPI == EPI_BIAS || EPI == EPI_RELU) {
+    // warps 0-3 / 4-7 split the 16-column chunks
+    const int nchunk = N / 16;
+    for (int ch = half; ch < nchunk; ch += 2) {
+      const int c0 = ch * 16;
+      uint32_t v[16];
+      tmem_ld16(trow + c0, v);
+      tmem_ld_wait();
+      if (live) {
+#pragma unroll
+        for (int jj = 0; jj < 16; ++jj) {
+          const int c = c0 + jj;
+          if (c < p.ncols) {
+            float o = __uint_as_float(v[jj]) + (p.bias ? __ldg(p.bias + c) : 0.f);
+            if (EPI == EPI_RELU) o = fmaxf(o, 0.f);
+            v[jj] = __float_as_uint(o);
+          }
+        }
+        float* dst = p.C + row * p.ldc + c0;
+        if (c0 + 16 <= p.ncols && (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0)) {
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj)
+            *reinterpret_cast<float4*>(dst + 4 * jj) = make_float4(__uint_as_float(v[4 * jj]), __uint_as_float(v[4 * jj + 1]),
+                                                                   __uint_as_float(v[4 * jj + 2]), __uint_as_float(v[4 * jj + 3]));
+        } else {
+#pragma unroll
+          for (int jj = 0; jj < 16; ++jj)
+            if (c0 + jj < p.ncols) dst[jj] = __uint_as_float(v[jj]);
+        }
+      }
+    }
+  } else if (EPI == EPI_RELU_LN) {
+    // y = LayerNorm(relu(acc + bias)) over the row's 64 columns (torch: biased variance, eps inside the sqrt); warps 0-3 own the rows
+    if (half == 0) {
+      float x[64];
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+        uint32_t v[16];
+        tmem_ld16(trow + 16 * ch, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int jj = 0; jj < 16; ++jj) x[16 * ch + jj] = fmaxf(__uint_as_float(v[jj]) + (p.bias ? __ldg(p.bias + 16 * ch + jj) : 0.f), 0.f);
+      }
+      float mean = 0.f;
+#pragma unroll
+      for (int c = 0; c < 64; ++c) mean += x[c];
+      mean *= (1.0f / 64.0f);
+      float var = 0.f;
+#pragma unroll
+      for (int c = 0; c < 64; ++c) { const float d = x[c] - mean; var = fmaf(d, d, var); }
+      const float rstd = rsqrtf(var * (1.0f / 64.0f) + p.eps);
+      if (live) {
+        float* dst = p.C + row * p.ldc;
+#pragma unroll
+        for (int c = 0; c < 64; c += 4) {
+          float4 o;
+          o.x = (x[c] - mean) * rstd * __ldg(p.gamma + c) + __ldg(p.beta + c);
+          o.y = (x[c + 1] - mean) * rstd * __ldg(p.gamma + c + 1) + __ldg(p.beta + c + 1);
+          o.z = (x[c + 2] - mean) * rstd * __ldg(p.gamma + c + 2) + __ldg(p.beta + c + 2);
+          o.w = (x[c + 3] - mean) * rstd * __ldg(p.gamma + c + 3) + __ldg(p.beta + c + 3);
+          *reinterpret_cast<float4*>(dst + c) = o;
+        }
+      }
+    }
+  } else {
+    // softmax over the first ncols columns of the row (= softmax over dim 1 of S for the transposed product); the two warp halves
+    // take alternate 16-column chunks and exchange their partial max / sum through shared memory
+    const int nchunk = N / 16, r128 = q * 32 + lane;
+    float mx = -INFINITY;
+    for (int ch = half; ch < nchunk; ch += 2) {
+      uint32_t v[16];
+      tmem_ld16(trow + 16 * ch, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int jj = 0; jj < 16; ++jj)
+        if (16 * ch + jj < p.ncols) mx = fmaxf(mx, __uint_as_float(v[jj]));
+    }
+    red[half * 128 + r128] = mx;
+    __syncthreads();
+    mx = fmaxf(red[r128], red[128 + r128]);
+    __syncthreads();
+    float sum = 0.f;
+    for (int ch = half; ch < nchunk; ch += 2) {
+      uint32_t v[16];
+      tmem_ld16(trow + 16 * ch, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int jj = 0; jj < 16; ++jj)
+        if (16 * ch + jj < p.ncols) sum += __expf(__uint_as_float(v[jj]) - mx);
+    }
+    red[half * 128 + r128] = sum;
+    __syncthreads();
+    const float inv = 1.0f / (red[r128] + red[128 + r128]);
+    for (int ch = half; ch < nchunk; ch += 2) {
+      uint32_t v[16];
+      tmem_ld16(trow + 16 * ch, v);
+      tmem_ld_wait();
+      if (live) {
+        float* dst = p.C + row * p.ldc + 16 * ch;      // ldc % 4 == 0, C 16-byte aligned (checked on the host)
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          float o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) o[e] = (16 * ch + 4 * jj + e < p.ncols) ? __expf(__uint_as_float(v[4 * jj + e]) - mx) * inv : 0.f;
+          if (16 * ch + 4 * jj < p.ldc) *reinterpret_cast<float4*>(dst + 4 * jj) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(tm_cols));
+}
+
+template <int EPI>
+int gb_launch(GbParams& p, cudaStream_t st) {
+  const int smem = 2 * (2 * GB_A_BYTES + 2 * p.N * 128) + 32 + 256 * 4;
+  if (smem > 232448) return set_error(STMP_EUNSUPPORTED, "blocked GEMM: N=%d needs %d B of shared memory", p.N, smem);
+  STMP_CUDA_OK(cudaFuncSetAttribute(k_gemm_blocks<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const unsigned grid = (unsigned)((p.M + GB_BM - 1) / GB_BM);
+  k_gemm_blocks<EPI><<<grid, GB_NT, smem, st>>>(p);
+  STMP_LAUNCH_OK("k_gemm_blocks");
+  return STMP_OK;
+}
+
+int gb_dispatch(GbParams& p, int epi, cudaStream_t st) {
+  switch (epi) {
+    case EPI_BIAS: return gb_launch<EPI_BIAS>(p, st);
+    case EPI_RELU: return gb_launch<EPI_RELU>(p, st);
+    case EPI_RELU_LN: return gb_launch<EPI_RELU_LN>(p, st);
+    case EPI_SOFTMAX: return gb_launch<EPI_SOFTMAX>(p, st);
+  }
+  return set_error(STMP_EINVAL, "blocked GEMM: unknown epilogue %d", epi);
+}
+
+}  // namespace
+}  // namespace stmp
+
+using namespace stmp;
+
+extern "C" int stmp_gemm_blocks_f32(int64_t M, int64_t N, int64_t ncols, int64_t nblk, const float* const* blk_ptr, const int64_t* blk_ld,
+                                    const int32_t* blk_width, const int32_t* blk_shift, int64_t seq, const void* packed, const float* bias,
+                                    int epilogue, const float* gamma, const float* beta, float eps, float* C, int64_t ldc, void* stream) {
+  STMP_REQUIRE(blk_ptr && blk_ld && blk_width && blk_shift && packed && C, STMP_EINVAL, "stmp_gemm_blocks_f32: NULL pointer");
+  STMP_REQUIRE(M >= 0 && nblk >= 1 && seq >= 1, STMP_EINVAL, "stmp_gemm_blocks_f32: bad sizes");
+  if (nblk > GB_MAXBLK || N > 320 || N % 16 != 0 || N < 16 || ncols > N || ncols < 1 || M >= (1ll << 31) - 128)
+    return set_error(STMP_EUNSUPPORTED, "blocked GEMM takes <= %d k-blocks, N <= 320, N %% 16 == 0 (nblk=%lld N=%lld)", GB_MAXBLK,
+                     (long long)nblk, (long long)N);
+  if (epilogue == EPI_RELU_LN && (N != 64 || ncols != 64 || !gamma || !beta || ldc % 4 != 0 || (reinterpret_cast<uintptr_t>(C) & 15)))
+    return set_error(STMP_EUNSUPPORTED, "blocked GEMM: the LayerNorm epilogue needs N == 64, gamma/beta and 16-byte aligned rows");
+  if (epilogue == EPI_SOFTMAX) return set_error(STMP_EINVAL, "blocked GEMM: the softmax epilogue belongs to stmp_spatial_attention_fwd");
+  if (M == 0) return STMP_OK;
+  GbParams p = {};
+  for (int i = 0; i < nblk; ++i) {
+    STMP_REQUIRE(blk_ptr[i] != nullptr && blk_width[i] >= 1 && blk_width[i] <= 64, STMP_EINVAL, "stmp_gemm_blocks_f32: bad block %d", i);
+    p.blk[i].ptr = blk_ptr[i]; p.blk[i].ld = blk_ld[i]; p.blk[i].width = blk_width[i]; p.blk[i].shift = blk_shift[i];
+  }
+  p.nblk = (int)nblk; p.M = (int)M; p.N = (int)N; p.seq = (int)seq; p.ncols = (int)ncols;
+  p.w_hi = reinterpret_cast<const __half*>(packed); p.w_lo = p.w_hi + N * nblk * 64;
+  p.bias = bias; p.C = C; p.ldc = ldc; p.gamma = gamma; p.beta = beta; p.eps = eps;
+  return gb_dispatch(p, epilogue, (cudaStream_t)stream);
+}
+
+extern "C" int stmp_spatial_attention_fwd(int64_t B, int64_t n_nodes, int64_t n_steps, const float* lhs, const float* rhs, const float* bsT,
+                                          const void* vsT_packed, float* st_out, int64_t ld_out, void* stream) {
+  STMP_REQUIRE(lhs && rhs && bsT && vsT_packed && st_out, STMP_EINVAL, "stmp_spatial_attention_fwd: NULL pointer");
+  STMP_REQUIRE(B >= 0 && n_nodes >= 1 && n_steps >= 1, STMP_EINVAL, "stmp_spatial_attention_fwd: bad sizes");
+  const int64_t Npad = (n_nodes + 63) / 64 * 64;
+  if (Npad > 320 || n_steps > 16 || ld_out < Npad || ld_out % 4 != 0 || (reinterpret_cast<uintptr_t>(st_out) & 15))
+    return set_error(STMP_EUNSUPPORTED, "fused spatial attention takes <= 320 nodes, <= 16 timesteps and 16-byte aligned rows of >= %lld floats "
+                                        "(nodes=%lld steps=%lld ld=%lld)", (long long)Npad, (long long)n_nodes, (long long)n_steps, (long long)ld_out);
+  if (B == 0) return STMP_OK;
+  GbParams p = {};
+  p.nblk = (int)(Npad / 64); p.M = (int)(B * n_nodes); p.N = (int)Npad; p.seq = 1; p.ncols = (int)n_nodes;
+  p.w_hi = reinterpret_cast<const __half*>(vsT_packed); p.w_lo = p.w_hi + Npad * Npad;
+  p.bias = nullptr; p.C = st_out; p.ldc = ld_out;
+  p.spatt = 1; p.Nn = (int)n_nodes; p.Tn = (int)n_steps; p.lhs = lhs; p.rhs = rhs; p.bsT = bsT;
+  return gb_dispatch(p, EPI_SOFTMAX, (cudaStream_t)stream);
+}

@@ -45,8 +45,9 @@ struct SpmmArgs {
   float* y; long long ldy, bsy;
   const float* z; long long ldz, bsz;
   float alpha, beta;
-  const float* att;  // [batch, n, n] or null
-  int att_transposed; // entry (dst=i, src=c): forward uses att[b,i,c]; transposed product uses att[b,c,i]
+  const float* att;  // [batch, n, att_ld] or null
+  long long att_ld;  // row stride of att (n unless the attention is handed in padded)
+  int att_transposed; // entry (dst=i, src=c): forward uses att[b,i,c]; transposed product / transposed attention uses att[b,c,i]
 };
 
 // G lanes per row (power of two, <=32).  blockDim.x = 256.
@@ -59,7 +60,7 @@ __global__ void __launch_bounds__(256) k_spmm(SpmmArgs a, int G, int log2G) {
   const int i = (int)(group % a.n);
   const long long b = group / a.n;
   const float* xb = a.x + b * a.bsx;
-  const float* attb = a.att ? a.att + b * (long long)a.n * a.n : nullptr;
+  const float* attb = a.att ? a.att + b * (long long)a.n * a.att_ld : nullptr;
   const int beg = a.rowptr[i], end = a.rowptr[i + 1];
 
   for (int f0 = lane_in_group * VEC; f0 < a.f; f0 += G * VEC) {
@@ -79,7 +80,7 @@ __global__ void __launch_bounds__(256) k_spmm(SpmmArgs a, int G, int log2G) {
       for (int u = 0; u < 4; ++u) {
         w[u] = __int_as_float(e[u].y);
         if (attb) {
-          float s = a.att_transposed ? __ldg(&attb[(long long)e[u].x * a.n + i]) : __ldg(&attb[(long long)i * a.n + e[u].x]);
+          float s = a.att_transposed ? __ldg(&attb[(long long)e[u].x * a.att_ld + i]) : __ldg(&attb[(long long)i * a.att_ld + e[u].x]);
           w[u] = __fmul_rn(w[u], s);
         }
       }
@@ -94,7 +95,7 @@ __global__ void __launch_bounds__(256) k_spmm(SpmmArgs a, int G, int log2G) {
       ld_vec<VEC>(xb + (long long)e.x * a.ldx + f0, xv);
       float w = __int_as_float(e.y);
       if (attb) {
-        float s = a.att_transposed ? __ldg(&attb[(long long)e.x * a.n + i]) : __ldg(&attb[(long long)i * a.n + e.x]);
+        float s = a.att_transposed ? __ldg(&attb[(long long)e.x * a.att_ld + i]) : __ldg(&attb[(long long)i * a.att_ld + e.x]);
         w = __fmul_rn(w, s);
       }
 #pragma unroll
@@ -206,9 +207,27 @@ inline bool aligned(const void* p, int bytes) { return (reinterpret_cast<uintptr
 
 using namespace stmp;
 
+static int spmm_impl(const stmp_plan* plan, int op, int transposed, int64_t batch, int64_t f, const float* x,
+                     int64_t ldx, int64_t bsx, float* y, int64_t ldy, int64_t bsy, float alpha, const float* z,
+                     int64_t ldz, int64_t bsz, float beta, const float* att, int64_t att_ld, int att_is_transposed, void* stream);
+
 extern "C" int stmp_spmm(const stmp_plan* plan, int op, int transposed, int64_t batch, int64_t f, const float* x,
                          int64_t ldx, int64_t bsx, float* y, int64_t ldy, int64_t bsy, float alpha, const float* z,
                          int64_t ldz, int64_t bsz, float beta, const float* att, void* stream) {
+  return spmm_impl(plan, op, transposed, batch, f, x, ldx, bsx, y, ldy, bsy, alpha, z, ldz, bsz, beta, att, plan ? plan->n : 0, 0, stream);
+}
+
+extern "C" int stmp_spmm_att_t(const stmp_plan* plan, int op, int64_t batch, int64_t f, const float* x, int64_t ldx, int64_t bsx,
+                              float* y, int64_t ldy, int64_t bsy, float alpha, const float* z, int64_t ldz, int64_t bsz, float beta,
+                              const float* attT, int64_t att_ld, void* stream) {
+  STMP_REQUIRE(attT != nullptr, STMP_EINVAL, "stmp_spmm_att_t: attT is NULL");
+  STMP_REQUIRE(plan == nullptr || att_ld >= plan->n, STMP_ESHAPE, "stmp_spmm_att_t: att_ld smaller than the node count");
+  return spmm_impl(plan, op, 0, batch, f, x, ldx, bsx, y, ldy, bsy, alpha, z, ldz, bsz, beta, attT, att_ld, 1, stream);
+}
+
+static int spmm_impl(const stmp_plan* plan, int op, int transposed, int64_t batch, int64_t f, const float* x,
+                     int64_t ldx, int64_t bsx, float* y, int64_t ldy, int64_t bsy, float alpha, const float* z,
+                     int64_t ldz, int64_t bsz, float beta, const float* att, int64_t att_ld, int att_is_transposed, void* stream) {
   STMP_REQUIRE(plan != nullptr, STMP_EINVAL, "stmp_spmm: plan is NULL");
   STMP_REQUIRE(op >= 0 && op < plan->n_ops, STMP_EINVAL, "stmp_spmm: op %d out of range", op);
   STMP_REQUIRE(x && y, STMP_EINVAL, "stmp_spmm: x/y is NULL");
@@ -221,7 +240,7 @@ extern "C" int stmp_spmm(const stmp_plan* plan, int op, int transposed, int64_t 
   a.rowptr = c.rowptr; a.cv = c.cv; a.n = c.n; a.batch = batch; a.f = (int)f;
   a.x = x; a.ldx = ldx; a.bsx = bsx; a.y = y; a.ldy = ldy; a.bsy = bsy;
   a.z = z; a.ldz = z ? ldz : 0; a.bsz = z ? bsz : 0; a.alpha = alpha; a.beta = beta;
-  a.att = att; a.att_transposed = transposed ? 1 : 0;
+  a.att = att; a.att_ld = att_ld; a.att_transposed = (transposed ? 1 : 0) ^ (att_is_transposed ? 1 : 0);
   // widest vector the shapes/alignments allow
   auto ok = [&](int v) {
     int bytes = 4 * v;

@@ -11,8 +11,14 @@ What runs where
   (:442-450) is folded into the feature axis (the attention matrix is shared by all T timesteps), so one
   launch per hop covers every timestep; the dense `(I*S)^T @ x` used for a diagonal scale (:160-165) is
   a broadcast multiply;
-* dense attention products / convolutions / LayerNorm are true dense GEMM-class work and stay on
-  cuBLAS/cuDNN through torch.
+* inference on a static graph (N <= 320, T <= 12, 64 time filters, stride 1) keeps the activations channels-last
+  (B, N, T, F) between blocks and runs every large product on tcgen05 with its neighbours fused (csrc/gemm_blocks.cu):
+  spatial attention `softmax(Vs @ sigmoid(LHS @ RHS + bs))` in ONE kernel (the N x N sigmoid is generated in the operand
+  stage, the softmax is the epilogue; the result is kept transposed and consumed so by `stmp_spmm_att_t`); the Chebyshev
+  contraction + ReLU; time convolution + residual convolution + ReLU + LayerNorm; the final convolution.  No im2col, cat
+  or permute of activations in HBM.  Only the T x T temporal attention and the (B,N,T) attention factors stay on torch;
+* training (autograd) and the per-timestep edge_index list path use the op-for-op torch formulation around `stmp_spmm`
+  (dense products on cuBLAS through torch).
 * lambda_max for normalization != "sym": the reference calls scipy ARPACK on the host in EVERY block
   forward (:437-438); here it is computed once per static graph and cached.
 """
@@ -164,6 +170,12 @@ def _conv_1xk(conv: nn.Conv2d, x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def _needs_grad(module, *tensors):
+    if not torch.is_grad_enabled():
+        return False
+    return any(p.requires_grad for p in module.parameters()) or any(t.requires_grad for t in tensors)
+
+
 def _reset(module):
     """xavier_uniform for dim>1, uniform(0,1) otherwise -- applied to EVERY parameter (astgcn.py:401-406)."""
     for p in module.parameters():
@@ -201,8 +213,68 @@ class ASTGCNBlock(nn.Module):
             self._lam_cache[key] = hit
         return hit[0]
 
+    # ---- native inference path: channels-last activations, fused tcgen05 products ------------------------------------
+    def _native_ok(self, N, Fi, T):
+        tc, rc = self._time_convolution, self._residual_convolution
+        K = self._chebconv_attention._weight.size(0)
+        return (N <= 320 and T <= 16 and Fi <= 64 and K <= 12 and tc.out_channels == 64 and tc.in_channels == 64
+                and tc.stride[1] == 1 and rc.stride[1] == 1 and tc.kernel_size == (1, 3) and tc.padding == (0, 1))
+
+    def _native_packs(self):
+        def build():
+            ta, sa, cc = self._temporal_attention, self._spatial_attention, self._chebconv_attention
+            tc, rc = self._time_convolution, self._residual_convolution
+            K = cc._weight.size(0)
+            return dict(
+                vsT=ops.spatial_attention_prepack(sa._Vs), bsT=sa._bs[0].t().contiguous(),
+                cheb=ops.gemm_blocks_prepack([cc._weight[k] for k in range(K)]),                       # (Fi, Fc) per hop
+                # time conv taps t-1, t, t+1: W[o, c, 0, tap] -> (c, o); residual 1x1: W[o, c, 0, 0] -> (c, o)
+                tconv=ops.gemm_blocks_prepack([tc.weight[:, :, 0, j].t().contiguous() for j in range(3)]
+                                              + [rc.weight[:, :, 0, 0].t().contiguous()]),
+                tbias=(tc.bias + rc.bias).contiguous())
+        if not hasattr(self, "_npack"):
+            self._npack = ops.PackCache()
+        return self._npack.get(list(self.parameters()), build)
+
+    def forward_channels_last(self, Xc: torch.Tensor, edge_index: torch.Tensor) -> torch.Tensor:
+        """Xc (B, N, T, Fi) contiguous -> (B, N, T, Ft) contiguous; inference only (no autograd)."""
+        B, N, T, Fi = Xc.shape
+        ta, sa, cc = self._temporal_attention, self._spatial_attention, self._chebconv_attention
+        pk = self._native_packs()
+        # temporal attention (astgcn.py:311-328): T x T per batch row -- tiny, stays on torch
+        lhs = torch.matmul(torch.einsum("bntf,n->btf", Xc, ta._U1), ta._U2)                # (B,T,N)
+        rhs = torch.einsum("bntf,f->bnt", Xc, ta._U3)                                       # (B,N,T)
+        E = F.softmax(torch.matmul(ta._Ve, torch.sigmoid(torch.matmul(lhs, rhs) + ta._be)), dim=1)
+        Xt = torch.einsum("bntf,btu->bnuf", Xc, E)                                          # X~ channels-last (:427-430)
+        # spatial attention factors (:245-256), then the fused N x N kernel; ST[b, j, i] = S[b, i, j]
+        lhs_s = torch.matmul(torch.einsum("bnuf,u->bnf", Xt, sa._W1), sa._W2)               # (B,N,T)
+        rhs_s = torch.einsum("bnuf,f->bun", Xt, sa._W3).contiguous()                        # (B,T,N)
+        ST = ops.spatial_attention(lhs_s, rhs_s, pk["bsT"], pk["vsT"])
+        # ChebConvAttention over all T timesteps at once (:141-183): T_0 = diag(S) x, T_1 = (norm * S) T_0, T_k = 2 L T_{k-1} - T_{k-2}
+        lam = self._lambda_max(edge_index, N)
+        if cc._normalization != "sym" and lam is None:
+            raise ValueError("You need to pass `lambda_max` to `forward() in`case the normalization is non-symmetric.")
+        plan = cc._plan(edge_index, None, N, lam)
+        K = cc._weight.size(0)
+        x2 = Xc.reshape(B, N, T * Fi)
+        Ts = [torch.diagonal(ST, dim1=1, dim2=2)[:, :N].unsqueeze(-1) * x2]
+        if K > 1:
+            Ts.append(ops.spmm_attT(plan, 0, Ts[0], ST))
+        for _ in range(2, K):
+            Ts.append(ops.spmm_raw(plan, 0, Ts[-1], alpha=2.0, z=Ts[-2], beta=-1.0))
+        Fc = cc._weight.size(2)
+        Xh = ops.gemm_blocks([(t.reshape(B * N * T, Fi), Fi, 0) for t in Ts], pk["cheb"], 64, Fc, cc._bias, ops.EPI_RELU)   # (BNT, Fc)
+        # time conv (1x3, pad 1) + residual 1x1 conv + ReLU + LayerNorm (:473-480) in one launch
+        Xf = Xc.reshape(B * N * T, Fi)
+        ln = self._layer_norm
+        Y = ops.gemm_blocks([(Xh, Fc, -1), (Xh, Fc, 0), (Xh, Fc, 1), (Xf, Fi, 0)], pk["tconv"], 64, 64, pk["tbias"], ops.EPI_RELU_LN,
+                            ln.weight, ln.bias, ln.eps, seq=T)
+        return Y.view(B, N, T, 64)
+
     def forward(self, X: torch.FloatTensor, edge_index: Union[torch.LongTensor, List[torch.LongTensor]]) -> torch.FloatTensor:
         B, N, Fi, T = X.shape
+        if (not isinstance(edge_index, list)) and self._native_ok(N, Fi, T) and not _needs_grad(self, X):
+            return self.forward_channels_last(X.permute(0, 1, 3, 2).contiguous(), edge_index).permute(0, 1, 3, 2)
         E = self._temporal_attention(X)
         X_tilde = torch.matmul(X.reshape(B, -1, T), E).reshape(B, N, Fi, T)
         S = self._spatial_attention(X_tilde)
@@ -235,8 +307,34 @@ class ASTGCN(nn.Module):
         self._final_conv = nn.Conv2d(int(len_input / time_strides), num_for_predict, kernel_size=(1, nb_time_filter))
         _reset(self)
 
+    def _final_pack(self):
+        def build():
+            w = self._final_conv.weight                                      # (P, T', 1, Ft)
+            blocks = [w[:, t, 0, :].t().contiguous() for t in range(w.size(1))]   # per timestep (Ft, P)
+            P = w.size(0)
+            P16 = (P + 15) // 16 * 16
+            blocks = [F.pad(b, (0, P16 - P)) for b in blocks]
+            bias = F.pad(self._final_conv.bias, (0, P16 - P))
+            return ops.gemm_blocks_prepack(blocks), bias.contiguous(), P16
+        if not hasattr(self, "_fpack"):
+            self._fpack = ops.PackCache()
+        return self._fpack.get(list(self._final_conv.parameters()), build)
+
     def forward(self, X: torch.FloatTensor, edge_index: torch.LongTensor) -> torch.FloatTensor:
         _require_cuda(X, "X")
+        B, N, Fi, T = X.shape
+        fc = self._final_conv
+        if (not isinstance(edge_index, list) and not _needs_grad(self, X) and fc.in_channels <= 12 and fc.kernel_size[1] == 64
+                and all(b._native_ok(N, Fi if i == 0 else 64, T) for i, b in enumerate(self._blocklist))):
+            # inference: channels-last (B,N,T,F) all the way, one layout change at the input
+            Xc = X.permute(0, 1, 3, 2).contiguous()
+            for block in self._blocklist:
+                Xc = block.forward_channels_last(Xc, edge_index)
+            packed, bias, P16 = self._final_pack()
+            Tn = Xc.size(2)
+            rows = Xc.reshape(B * N, Tn * 64)
+            out = ops.gemm_blocks([(rows[:, 64 * t:64 * t + 64], 64, 0) for t in range(Tn)], packed, P16, fc.out_channels, bias, ops.EPI_BIAS)
+            return out.view(B, N, fc.out_channels)
         for block in self._blocklist:
             X = block(X, edge_index)
         X = _conv_1xk(self._final_conv, X.permute(0, 3, 1, 2))     # kernel (1, F_t) over the feature axis

@@ -218,6 +218,79 @@ def gemm(A: torch.Tensor, packed: torch.Tensor, K: int, N: int, bias: Optional[t
     return C
 
 
+EPI_BIAS, EPI_RELU, EPI_RELU_LN = 0, 1, 2
+
+
+def gemm_blocks_prepack(blocks) -> torch.Tensor:
+    """Pack the per-block weights [(width_i, N) fp32 ...] of a blocked GEMM: every block is zero-padded to 64 rows, the stack
+    (nblk*64, N) is split into fp16 hi/lo by stmp_gemm_prepack."""
+    N = blocks[0].size(1)
+    W = torch.zeros(64 * len(blocks), N, device=blocks[0].device, dtype=torch.float32)
+    for i, w in enumerate(blocks):
+        if w.size(0) > 64 or w.size(1) != N:
+            raise RuntimeError("blocked GEMM: weight blocks must be (<=64, N)")
+        W[64 * i:64 * i + w.size(0)] = w
+    return gemm_prepack(W)
+
+
+def gemm_blocks(blocks, packed: torch.Tensor, N: int, ncols: int, bias: Optional[torch.Tensor] = None, epilogue: int = EPI_BIAS,
+                gamma=None, beta=None, eps: float = 1e-5, seq: int = 1, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """C[m, :ncols] = epilogue(sum_i A_i[m + shift_i, :width_i] @ W_i + bias)  (stmp_gemm_blocks_f32).
+    blocks: list of (tensor, width, shift): `tensor` is a 2-D fp32 CUDA view (M, >=width) with unit column stride."""
+    M = blocks[0][0].size(0)
+    dev = blocks[0][0].device
+    n = len(blocks)
+    ptrs = (ctypes.c_void_p * n)()
+    lds = (ctypes.c_int64 * n)()
+    widths = (ctypes.c_int32 * n)()
+    shifts = (ctypes.c_int32 * n)()
+    for i, (t, width, shift) in enumerate(blocks):
+        _require_cuda(t, "block")
+        if t.dtype != torch.float32 or t.dim() != 2 or t.size(0) != M or (t.size(1) > 1 and t.stride(1) != 1) or t.size(1) < width:
+            raise RuntimeError("blocked GEMM: every block must be a float32 (M, >=width) view with unit column stride")
+        ptrs[i], lds[i], widths[i], shifts[i] = t.data_ptr(), t.stride(0), width, shift
+    C = torch.empty((M, ncols), dtype=torch.float32, device=dev) if out is None else out
+    v = [None if t is None else _f32c(t.detach(), "param") for t in (bias, gamma, beta)]
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().stmp_gemm_blocks_f32(M, N, ncols, n, ctypes.cast(ptrs, ctypes.c_void_p), ctypes.cast(lds, ctypes.c_void_p),
+                                                   ctypes.cast(widths, ctypes.c_void_p), ctypes.cast(shifts, ctypes.c_void_p), seq,
+                                                   _lib.ptr(packed), _lib.ptr(v[0]), epilogue, _lib.ptr(v[1]), _lib.ptr(v[2]), eps,
+                                                   _lib.ptr(C), C.stride(0), _lib.stream_ptr()))
+    return C
+
+
+def spatial_attention_prepack(Vs: torch.Tensor) -> torch.Tensor:
+    """Vs (N,N) -> packed fp16 hi/lo of Vs^T zero-padded to (P,P), P = N rounded up to 64."""
+    n = Vs.size(0)
+    P = (n + 63) // 64 * 64
+    W = torch.zeros(P, P, device=Vs.device, dtype=torch.float32)
+    W[:n, :n] = Vs.detach().t()
+    return gemm_prepack(W)
+
+
+def spatial_attention(lhs: torch.Tensor, rhs: torch.Tensor, bsT: torch.Tensor, vsT_packed: torch.Tensor) -> torch.Tensor:
+    """ST (B, N, P) with ST[b, j, i] = softmax_dim1(Vs @ sigmoid(lhs @ rhs + bs))[b, i, j]; columns >= N are zero."""
+    lhs, rhs, bsT = _f32c(lhs, "lhs"), _f32c(rhs, "rhs"), _f32c(bsT, "bsT")
+    B, n, T = lhs.shape
+    P = (n + 63) // 64 * 64
+    st = torch.empty((B, n, P), dtype=torch.float32, device=lhs.device)
+    with torch.cuda.device(lhs.device):
+        _lib.check(_lib.lib().stmp_spatial_attention_fwd(B, n, T, _lib.ptr(lhs), _lib.ptr(rhs), _lib.ptr(bsT), _lib.ptr(vsT_packed),
+                                                         _lib.ptr(st), P, _lib.stream_ptr()))
+    return st
+
+
+def spmm_attT(plan: GraphPlan, op: int, x: torch.Tensor, attT: torch.Tensor, alpha: float = 1.0) -> torch.Tensor:
+    """y = alpha * (A_op * att) x with the attention given transposed / row-padded (B, N, ld) as `spatial_attention` writes it."""
+    x = _f32c(x, "x")
+    B, N, F = x.shape
+    y = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().stmp_spmm_att_t(plan.handle, op, B, F, _lib.ptr(x), F, N * F, _lib.ptr(y), F, N * F, alpha, None, F, N * F, 0.0,
+                                             _lib.ptr(attT), attT.stride(1), _lib.stream_ptr()))
+    return y
+
+
 def gemm_lstm(A: torch.Tensor, packed: torch.Tensor, K: int, cout: int, conv_bias, cell, wci, wcf, wco, bi, bf, bc, bo):
     """(H', C') = peephole-LSTM gates of (A @ W + conv_bias), fused in the GEMM epilogue (stmp_gemm_lstm_f32)."""
     A, cell = _f32c(A, "A"), _f32c(cell, "C")

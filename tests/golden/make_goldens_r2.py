@@ -64,7 +64,29 @@ def a3tgcn2_cfg3():
          state1=sd(m1), out1=out1, out1H=out1H, state_cell=sd(c2), cell=cell, cellH=cellH)
 
 
-GENERATORS = {"dcrnn_cfg2_grads": dcrnn_cfg2_grads, "a3tgcn2_cfg3": a3tgcn2_cfg3}
+def astgcn_cfg4():
+    """BASELINE configs[3]: ASTGCN(3 blocks, K=3, 64 Chebyshev / 64 time filters, stride 1, 12 -> 12) on the PeMS04 shape (307 nodes,
+    340 undirected links), batch 32, normalization "sym"; plus normalization None (lambda_max by scipy) on 8 rows."""
+    mod = refload.load("nn.attention.astgcn")
+    eiu = torch.from_numpy(synthetic.pems04_like(0))
+    cases = {}
+    for norm, B in (("sym", 32), (None, 8)):
+        torch.manual_seed(0)
+        m = mod.ASTGCN(3, 1, 3, 64, 64, 1, 12, 12, 307, normalization=norm)
+        g = torch.Generator().manual_seed(11)
+        X = torch.randn(B, 307, 1, 12, generator=g)
+        with torch.no_grad():
+            out = m(X, eiu)
+        # Vs / bs are 3 x 2 x 307 x 307 floats: regenerate them from the seed at test time instead of storing them
+        cases[str(norm)] = dict(normalization=norm, X=X, out=out, seed=0)
+        small = {k: v.detach().clone() for k, v in m.state_dict().items()}
+        cases[str(norm)]["state_checksum"] = float(sum(v.double().abs().sum() for v in small.values()))
+    save("astgcn_cfg4", edge_index=eiu, cases=cases,
+         ctor=dict(nb_block=3, in_channels=1, K=3, nb_chev_filter=64, nb_time_filter=64, time_strides=1, num_for_predict=12,
+                   len_input=12, num_of_vertices=307))
+
+
+GENERATORS = {"dcrnn_cfg2_grads": dcrnn_cfg2_grads, "a3tgcn2_cfg3": a3tgcn2_cfg3, "astgcn_cfg4": astgcn_cfg4}
 
 
 if __name__ == "__main__":

@@ -178,6 +178,72 @@ def test_astgcn_goldens(golden_dir):
         _close(out_l, c["out"], rtol=2e-4, atol=2e-5)
 
 
+def test_astgcn_config4_shape_vs_reference_golden(golden_dir):
+    """BASELINE configs[3] AT SHAPE: ASTGCN(3 blocks, K=3, 64/64 filters) on 307 nodes, batch 32 (and normalization None on 8
+    rows), against the UNMODIFIED reference (tests/golden/make_goldens_r2.py) at the STRICT tolerance rtol 1e-4 / atol 1e-5,
+    through the native channels-last path: fused spatial attention, blocked tcgen05 GEMMs (k_gemm_blocks), attention SpMM."""
+    g = _load(golden_dir, "astgcn_cfg4")
+    ei = g["edge_index"].to(DEV)
+    for c in g["cases"].values():
+        torch.manual_seed(c["seed"])                     # the reference module was built under this seed: same init stream
+        m = ASTGCN(**g["ctor"], normalization=c["normalization"])
+        chk = float(sum(v.double().abs().sum() for v in m.state_dict().values()))
+        assert abs(chk - c["state_checksum"]) <= 1e-6 * c["state_checksum"], "parameter init stream differs from the reference module's"
+        m = m.to(DEV)
+        c0 = _lib.path_counters()
+        with torch.no_grad():
+            out = m(c["X"].to(DEV), ei)
+        assert _ran(c0, "k_gemm_blocks") == 3 * 3 + 1       # per block: spatial attention, Chebyshev contraction, time conv; + final conv
+        assert _ran(c0, "k_spmm") == 3 and _ran(c0, "k_spmm_pre") == 3     # per block: attention-weighted hop + plain hop
+        _close(out, c["out"])
+        # the op-for-op torch path (what training uses) agrees as well
+        out_t = m(c["X"][:4].to(DEV).requires_grad_(True), ei)
+        _close(out_t, c["out"][:4], rtol=2e-4, atol=2e-5)
+
+
+def test_spatial_attention_kernel_vs_fp64():
+    """stmp_spatial_attention_fwd alone: softmax_dim1(Vs @ sigmoid(LHS @ RHS + bs)) for 307 / 200 / 64 nodes against float64."""
+    from pytorch_geometric_temporal_b200 import ops
+    for n, B, T in ((307, 5, 12), (200, 3, 7), (64, 2, 16)):
+        g = torch.Generator().manual_seed(n)
+        lhs, rhs = torch.randn(B, n, T, generator=g) * 0.5, torch.randn(B, T, n, generator=g) * 0.5
+        bs, Vs = torch.randn(n, n, generator=g) * 0.3, torch.randn(n, n, generator=g) * (1.5 / n ** 0.5)
+        S = torch.softmax(Vs.double() @ torch.sigmoid(lhs.double() @ rhs.double() + bs.double()), dim=1)
+        S32 = torch.softmax(Vs @ torch.sigmoid(lhs @ rhs + bs), dim=1)
+        ST = ops.spatial_attention(lhs.to(DEV), rhs.to(DEV), bs.t().contiguous().to(DEV), ops.spatial_attention_prepack(Vs.to(DEV)))
+        got = ST[:, :, :n].transpose(1, 2).cpu()
+        err, err32 = (got.double() - S).abs().max().item(), (S32.double() - S).abs().max().item()
+        assert err < 4 * err32 + 1e-7, (n, err, err32)
+        assert torch.all(ST[:, :, n:] == 0)
+
+
+def test_gemm_blocks_shift_ln_epilogues_vs_torch():
+    """stmp_gemm_blocks_f32: row-shifted blocks inside sequences (a 1x3 convolution without im2col), ragged widths, the
+    ReLU + LayerNorm epilogue and a 12-column output -- against torch fp32 / fp64."""
+    from pytorch_geometric_temporal_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    B, T, C = 37, 12, 64                                  # 444 rows: not a multiple of the 128-row tile
+    Xh, X1 = torch.randn(B, T, C, generator=g), torch.randn(B, T, 1, generator=g)
+    Wt, Wr = torch.randn(C, C, 3, generator=g) * 0.1, torch.randn(C, 1, generator=g)
+    bias, gamma, beta = torch.randn(C, generator=g), torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g)
+    conv = torch.nn.functional.conv1d(Xh.transpose(1, 2), Wt, padding=1).transpose(1, 2) + X1 @ Wr.t() + bias
+    want = torch.nn.functional.layer_norm(torch.relu(conv), (C,), gamma, beta, 1e-5)
+    packed = ops.gemm_blocks_prepack([Wt[:, :, j].t().contiguous().to(DEV) for j in range(3)] + [Wr.t().contiguous().to(DEV)])
+    xh, x1 = Xh.to(DEV).reshape(B * T, C), X1.to(DEV).reshape(B * T, 1)
+    got = ops.gemm_blocks([(xh, C, -1), (xh, C, 0), (xh, C, 1), (x1, 1, 0)], packed, 64, 64, bias.to(DEV), ops.EPI_RELU_LN,
+                          gamma.to(DEV), beta.to(DEV), 1e-5, seq=T)
+    _close(got, want.reshape(B * T, C), rtol=1e-4, atol=2e-5)
+    # plain / ReLU epilogues with a narrow output (final convolution: 12 columns of a 16-column product)
+    W = torch.randn(3 * C, 16, generator=g) * 0.1
+    packed = ops.gemm_blocks_prepack([W[C * i:C * i + C].to(DEV) for i in range(3)])
+    rows = torch.randn(200, 3 * C, generator=g)
+    rd = rows.to(DEV)
+    b16 = torch.randn(16, generator=g)
+    blocks = [(rd[:, C * i:C * i + C], C, 0) for i in range(3)]
+    _close(ops.gemm_blocks(blocks, packed, 16, 12, b16.to(DEV), ops.EPI_BIAS), (rows @ W + b16)[:, :12], rtol=1e-4, atol=2e-5)
+    _close(ops.gemm_blocks(blocks, packed, 16, 16, b16.to(DEV), ops.EPI_RELU), torch.relu(rows @ W + b16), rtol=1e-4, atol=2e-5)
+
+
 def test_chebconv_attention_errors_and_repr():
     conv = ChebConvAttention(2, 3, 3, None).to(DEV)
     assert repr(conv) == "ChebConvAttention(2, 3, K=3, normalization=None)"   # test/attention_test.py:197
