@@ -194,6 +194,13 @@ int stmp_lstm_ifc(int64_t rows, int64_t cout, const float* pi, const float* pf, 
 int stmp_lstm_oh(int64_t rows, int64_t cout, const float* po, const float* cnew, const float* wco,
                  const float* bo, float* o, float* hnew, void* stream);
 
+/* Backward of the peephole-LSTM gate chain (what autograd records for gconv_lstm.py:168-202): pre [rows][4*cout] = i|f|c|o pre-activations
+ * of the contraction incl. the ChebConv biases, c_old / c_new [rows][cout], gh = dL/dH', gc = dL/dC' (either may be NULL = zeros)
+ * -> dpre [rows][4*cout], dc_old [rows][cout].  The gates are recomputed from `pre` (nothing but S, C_{t-1}, C_t is kept by the forward). */
+int stmp_lstm_gate_bwd(int64_t rows, int64_t cout, const float* pre, const float* c_old, const float* c_new, const float* gh,
+                       const float* gc, const float* wci, const float* wcf, const float* wco, const float* bi, const float* bf,
+                       const float* bc, const float* bo, float* dpre, float* dc_old, void* stream);
+
 /* ---- backward of the fused DCRNN sequence (what autograd replays for dcrnn.py:429-475 / :172-219), small graphs ----
  * Served when stmp_dcrnn_bwd_supported(plan, cin, cout, K) != 0 (DCONV plan, K = 2, cout = 32, cin <= 4, graph + tiles
  * fit one SM's shared memory: N <= ~235); otherwise callers use the per-step path (stmp_gru_bwd_* + stmp_spmm).

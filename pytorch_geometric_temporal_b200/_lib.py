@@ -63,6 +63,7 @@ _SIGNATURES = {
     "stmp_gru_bwd_carry": (c_int, [c_int64] * 5 + [_P, _P, _P, _P, _P, _P, c_int64, _P, c_int64, _P, _P, c_int64, _P, _P, _P, _P]),
     "stmp_gru_bwd_zr": (c_int, [c_int64] * 5 + [_P, _P, c_int64, _P, _P, _P, c_int64, _P, _P, _P]),
     "stmp_lstm_ifc": (c_int, [c_int64, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "stmp_lstm_gate_bwd": (c_int, [c_int64, c_int64] + [_P] * 15),
     "stmp_lstm_oh": (c_int, [c_int64, c_int64, _P, _P, _P, _P, _P, _P, _P]),
     "stmp_gemm_packed_elems": (c_int64, [c_int64, c_int64]),
     "stmp_gemm_prepack": (c_int, [_P, c_int64, c_int64, c_int64, _P, _P]),

@@ -63,6 +63,42 @@ __global__ void __launch_bounds__(kT) k_lstm_oh(long long n, int cout, const flo
   }
 }
 
+// Gate derivatives of the peephole LSTM cell (hand-written backward of gconv_lstm.py:168-202), one thread per (row, channel).
+//   pre [rows][4*Co] = pre-activations i|f|c|o of the contraction INCLUDING the ChebConv biases (recomputed by the backward GEMM),
+//   c_old / c_new [rows][Co], gh = dL/dH' , gc = dL/dC' arriving from later steps (nullable);
+//   dpre [rows][4*Co] = dL/d pre, dc_old [rows][Co] = dL/dC_{t-1}.
+__global__ void __launch_bounds__(kT) k_lstm_gate_bwd(long long n, int cout, const float* __restrict__ pre, const float* __restrict__ c_old,
+                                                      const float* __restrict__ c_new, const float* __restrict__ gh,
+                                                      const float* __restrict__ gc, const float* __restrict__ wci,
+                                                      const float* __restrict__ wcf, const float* __restrict__ wco,
+                                                      const float* __restrict__ bi, const float* __restrict__ bf,
+                                                      const float* __restrict__ bc, const float* __restrict__ bo,
+                                                      float* __restrict__ dpre, float* __restrict__ dc_old) {
+  for (long long i = blockIdx.x * (long long)kT + threadIdx.x; i < n; i += (long long)gridDim.x * kT) {
+    const long long row = i / cout;
+    const int ch = (int)(i - row * cout);
+    const float* pr = pre + row * 4 * cout;
+    const float co = c_old[i], cn = c_new[i];
+    const float iv = sigmoidf_acc(__fadd_rn(__fadd_rn(pr[ch], __fmul_rn(wci[ch], co)), bi[ch]));
+    const float fv = sigmoidf_acc(__fadd_rn(__fadd_rn(pr[cout + ch], __fmul_rn(wcf[ch], co)), bf[ch]));
+    const float tv = tanhf(__fadd_rn(pr[2 * cout + ch], bc[ch]));
+    const float ov = sigmoidf_acc(__fadd_rn(__fadd_rn(pr[3 * cout + ch], __fmul_rn(wco[ch], cn)), bo[ch]));
+    const float tc = tanhf(cn);
+    const float g = gh ? gh[i] : 0.f;
+    const float dpo = g * tc * ov * (1.0f - ov);
+    const float dcn = (gc ? gc[i] : 0.f) + g * ov * (1.0f - tc * tc) + dpo * wco[ch];
+    const float dpi = dcn * tv * iv * (1.0f - iv);
+    const float dpf = dcn * co * fv * (1.0f - fv);
+    const float dpc = dcn * iv * (1.0f - tv * tv);
+    float* dp = dpre + row * 4 * cout;
+    dp[ch] = dpi;
+    dp[cout + ch] = dpf;
+    dp[2 * cout + ch] = dpc;
+    dp[3 * cout + ch] = dpo;
+    dc_old[i] = dcn * fv + dpi * wci[ch] + dpf * wcf[ch];
+  }
+}
+
 // x[b, t, :] = series[start[b] + t, :]  for t in [0,h);  y[b, t, :] = series[start[b] + h + t, :]
 template <typename V>
 __global__ void __launch_bounds__(kT) k_window_gather(const V* __restrict__ series, long long row_v, const long long* __restrict__ start,
@@ -230,6 +266,18 @@ extern "C" int stmp_lstm_oh(int64_t rows, int64_t cout, const float* po, const f
   STMP_LAUNCH_OK("k_lstm_oh");
   return STMP_OK;
 }
+extern "C" int stmp_lstm_gate_bwd(int64_t rows, int64_t cout, const float* pre, const float* c_old, const float* c_new, const float* gh,
+                                  const float* gc, const float* wci, const float* wcf, const float* wco, const float* bi, const float* bf,
+                                  const float* bc, const float* bo, float* dpre, float* dc_old, void* stream) {
+  STMP_REQUIRE(rows >= 0 && cout > 0, STMP_EINVAL, "stmp_lstm_gate_bwd: bad size");
+  STMP_REQUIRE(pre && c_old && c_new && wci && wcf && wco && bi && bf && bc && bo && dpre && dc_old, STMP_EINVAL, "stmp_lstm_gate_bwd: NULL tensor");
+  if (rows == 0) return STMP_OK;
+  k_lstm_gate_bwd<<<grid_for(rows * cout), kT, 0, (cudaStream_t)stream>>>(rows * cout, (int)cout, pre, c_old, c_new, gh, gc, wci, wcf, wco, bi,
+                                                                        bf, bc, bo, dpre, dc_old);
+  STMP_LAUNCH_OK("k_lstm_gate_bwd");
+  return STMP_OK;
+}
+
 extern "C" int stmp_window_gather(const float* series, int64_t t_total, int64_t row_elems, const int64_t* start, int64_t B,
                                   int64_t horizon, float* x, float* y, void* stream) {
   STMP_REQUIRE(series && start && x, STMP_EINVAL, "stmp_window_gather: NULL pointer");

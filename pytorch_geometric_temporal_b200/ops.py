@@ -207,14 +207,23 @@ def gemm_prepack(W: torch.Tensor) -> torch.Tensor:
     return packed
 
 
-def gemm(A: torch.Tensor, packed: torch.Tensor, K: int, N: int, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """C = A @ W + bias on tcgen05 with the fp16 hi/lo operand split (fp32-class accuracy).  A (..., K) contiguous."""
+def gemm(A: torch.Tensor, packed: torch.Tensor, K: int, N: int, bias: Optional[torch.Tensor] = None,
+         out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """C = A @ W + bias on tcgen05 with the fp16 hi/lo operand split (fp32-class accuracy).  A (..., K) contiguous.
+    `out`: a 2-D (M, N) view with unit column stride (e.g. a column block of a wider buffer) to write into."""
     A = _f32c(A, "A")
     M = A.numel() // K
-    C = torch.empty(*A.shape[:-1], N, dtype=torch.float32, device=A.device)
+    if out is None:
+        C = torch.empty(*A.shape[:-1], N, dtype=torch.float32, device=A.device)
+        ldc = N
+    else:
+        C = out
+        if C.dim() != 2 or C.size(0) != M or C.size(1) != N or C.stride(1) != 1 or C.dtype != torch.float32:
+            raise RuntimeError("gemm: `out` must be a float32 (M, N) view with unit column stride")
+        ldc = C.stride(0)
     b = None if bias is None else _f32c(bias.detach(), "bias")
     with torch.cuda.device(A.device):
-        _lib.check(_lib.lib().stmp_gemm_f32(_lib.ptr(A), K, M, K, N, _lib.ptr(packed), _lib.ptr(b), _lib.ptr(C), N, _lib.stream_ptr()))
+        _lib.check(_lib.lib().stmp_gemm_f32(_lib.ptr(A), K, M, K, N, _lib.ptr(packed), _lib.ptr(b), _lib.ptr(C), ldc, _lib.stream_ptr()))
     return C
 
 
@@ -491,6 +500,22 @@ def lstm_oh(po, cnew, wco, bo):
         _lib.check(_lib.lib().stmp_lstm_oh(rows, cout, _lib.ptr(po), _lib.ptr(cnew), _lib.ptr(v[0]), _lib.ptr(v[1]), None,
                                            _lib.ptr(hn), _lib.stream_ptr()))
     return hn
+
+
+def lstm_gate_bwd(pre, c_old, c_new, gh, gc, wci, wcf, wco, bi, bf, bc, bo):
+    """(dpre (rows,4Co), dC_old (rows,Co)) of the peephole-LSTM gate chain (stmp_lstm_gate_bwd); gh / gc may be None."""
+    pre, c_old, c_new = _f32c(pre, "pre"), _f32c(c_old, "c_old"), _f32c(c_new, "c_new")
+    cout = c_old.size(-1)
+    rows = c_old.numel() // cout
+    dpre = torch.empty_like(pre)
+    dco = torch.empty_like(c_old)
+    gh = None if gh is None else _f32c(gh, "gh")
+    gc = None if gc is None else _f32c(gc, "gc")
+    v = [_f32c(t.detach().reshape(-1), "param") for t in (wci, wcf, wco, bi, bf, bc, bo)]
+    with torch.cuda.device(pre.device):
+        _lib.check(_lib.lib().stmp_lstm_gate_bwd(rows, cout, _lib.ptr(pre), _lib.ptr(c_old), _lib.ptr(c_new), _lib.ptr(gh), _lib.ptr(gc),
+                                                 *[_lib.ptr(t) for t in v], _lib.ptr(dpre), _lib.ptr(dco), _lib.stream_ptr()))
+    return dpre, dco
 
 
 def window_gather(series: torch.Tensor, start: torch.Tensor, horizon: int, with_target: bool = True):

@@ -86,7 +86,31 @@ def astgcn_cfg4():
                    len_input=12, num_of_vertices=307))
 
 
-GENERATORS = {"dcrnn_cfg2_grads": dcrnn_cfg2_grads, "a3tgcn2_cfg3": a3tgcn2_cfg3, "astgcn_cfg4": astgcn_cfg4}
+def gconv_lstm_cfg5seq():
+    """GConvLSTM(64,64,K=3) (the cfg5 cell) unrolled over 6 steps on a 600-node / 6000-edge random graph (CPU-tractable slice of the
+    10k/100k shape): final H, C and the autograd gradients of every parameter and of X from the UNMODIFIED reference module."""
+    gl = refload.load("nn.recurrent.gconv_lstm")
+    ei, ew = synthetic.large_graph(600, 6000, 1)
+    ei_t, ew_t = torch.from_numpy(ei), torch.from_numpy(ew)
+    torch.manual_seed(3)
+    m = gl.GConvLSTM(64, 64, 3)
+    for n_, p in m.named_parameters():                 # non-zero biases / peepholes so their gradients are exercised
+        if n_.startswith("b_") or n_.endswith(".bias"):
+            torch.nn.init.normal_(p, std=0.1)
+    g = torch.Generator().manual_seed(9)
+    X = (torch.randn(6, 600, 64, generator=g) * 0.5).requires_grad_(True)
+    H = C = None
+    loss = 0
+    for t in range(6):
+        H, C = m(X[t], ei_t, ew_t, H, C)
+        loss = loss + (H * torch.linspace(-1, 1, H.numel()).view_as(H)).sum() + 0.3 * C.square().sum()
+    loss.backward()
+    save("gconv_lstm_cfg5seq", edge_index=ei_t, edge_weight=ew_t, X=X.detach(), state=sd(m), H=H.detach(), C=C.detach(),
+         gX=X.grad.clone(), grads={k: p.grad.detach().clone() for k, p in m.named_parameters()})
+
+
+GENERATORS = {"dcrnn_cfg2_grads": dcrnn_cfg2_grads, "a3tgcn2_cfg3": a3tgcn2_cfg3, "astgcn_cfg4": astgcn_cfg4,
+              "gconv_lstm_cfg5seq": gconv_lstm_cfg5seq}
 
 
 if __name__ == "__main__":

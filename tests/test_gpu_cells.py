@@ -97,6 +97,32 @@ def test_tgcn_goldens(golden_dir):
         _close(m2(c["X2"].to(DEV), ei, ew, c["H2"].to(DEV)), c["out2"])
 
 
+@pytest.mark.parametrize("fused", [True, False])
+def test_gconv_lstm_cfg5_cell_sequence_gradients_vs_reference_golden(golden_dir, fused):
+    """GConvLSTM(64,64,K=3) unrolled over 6 steps: final state AND every gradient against the UNMODIFIED reference's autograd
+    (tests/golden/make_goldens_r2.py) -- through the hand-written cell backward (_LstmCellFn: tcgen05 GEMM + LSTM epilogue forward,
+    recompute + stmp_lstm_gate_bwd + transposed SpMM backward) and through the op-for-op autograd path."""
+    g = _load(golden_dir, "gconv_lstm_cfg5seq")
+    ei, ew = g["edge_index"].to(DEV), g["edge_weight"].to(DEV)
+    m = GConvLSTM(64, 64, 3).to(DEV)
+    m.load_state_dict(g["state"])
+    m.fused_training = fused
+    X = g["X"].to(DEV).requires_grad_(True)
+    c0 = _lib.path_counters()
+    H = C = None
+    loss = 0
+    for t in range(6):
+        H, C = m(X[t], ei, ew, H, C)
+        loss = loss + (H * torch.linspace(-1, 1, H.numel(), device=DEV).view_as(H)).sum() + 0.3 * C.square().sum()
+    loss.backward()
+    assert (_ran(c0, "k_lstm_gate_bwd") == 6) == fused
+    _close(H, g["H"]); _close(C, g["C"])
+    _close(X.grad, g["gX"], 1e-3, 1e-3 * g["gX"].abs().max().item())
+    for k, p in m.named_parameters():
+        ref = g["grads"][k]
+        _close(p.grad, ref, 1e-3, 1e-3 * ref.abs().max().item() + 1e-7)
+
+
 def test_a3tgcn_goldens(golden_dir):
     g = _load(golden_dir, "a3tgcn_small")
     ei, ew = g["edge_index"].to(DEV), g["edge_weight"].to(DEV)

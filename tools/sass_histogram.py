@@ -15,10 +15,11 @@ for line in out.splitlines():
     m = re.search(r"Function : (\S+)", line)
     if m:
         name = subprocess.run(["c++filt", m.group(1)], capture_output=True, text=True).stdout.strip()
-        kern = re.sub(r"\(.*", "", name).replace("stmp::(anonymous namespace)::", "")
-        hist[kern] = collections.Counter()
+        name = name.replace("(anonymous namespace)::", "").replace("void ", "")
+        kern = re.sub(r"\(.*", "", name)
+        hist.setdefault(kern, collections.Counter())
         continue
-    m = re.match(r"\s+/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_]+(?:\.[A-Z0-9_]+)*)", line)
+    m = re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_]+(?:\.[A-Z0-9_]+)*)", line)
     if m and kern:
         hist[kern][m.group(1).split(".")[0]] += 1
 KEY = ("UTCHMMA", "UTCQMMA", "UTCBAR", "LDTM", "STTM", "UBLKCP", "UTMALDG", "UTMASTG", "SYNCS", "HMMA", "LDGSTS", "FFMA2", "ATOMS", "REDUX")
@@ -26,7 +27,7 @@ print(f"# {os.path.relpath(lib, ROOT)}: SASS opcode counts per kernel (cuobjdump
 for k in sorted(hist):
     h = hist[k]
     tot = sum(h.values())
-    if tot == 0:
+    if tot == 0 or "cub::" in k:
         continue
     key = " ".join(f"{o}={h[o]}" for o in KEY if h[o])
     top = " ".join(f"{o}:{c}" for o, c in h.most_common(8))
