@@ -152,22 +152,15 @@ __device__ __forceinline__ float4 gather_groups(const float* __restrict__ Uj, co
   return acc;
 }
 
-__device__ __forceinline__ uint32_t atom_add_acq_rel_shared(uint32_t* p, uint32_t v) {
-  uint32_t old;
-  asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(p)), "r"(v) : "memory");
-  return old;
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
 // Step anatomy (all 16 warps; T_k = MMA row tile k = rows [128k, 128k+128)):
-//   round 1  gather [P_o H | P_i H] of T_0's rows -> A panels;  the LAST warp to finish issues GEMM1(T_0) (z|r pre-activations)
-//            gather T_1's rows                                   last warp issues GEMM1(T_1); every warp arrives on `gdone`
-//   epi 1    wait GEMM1(own tile) + gdone (nobody reads U any more): R, H*R -> U, A panel               __syncthreads
+//   round 1  tid 0 issues the H | X k-steps of GEMM1 for both tiles; all warps gather [P_o H | P_i H] of T_0's rows -> A panels
+//            barrier; tid 0 issues T_0's P_o / P_i k-steps + commit -- the tensor core works on T_0 while the LSU gathers T_1's rows
+//            barrier; tid 0 issues T_1's k-steps + commit
+//   epi 1    wait GEMM1(own tile): R, H*R -> U, A panel                                                          barrier
 //   round 2  same gathers over H*R, GEMM2 (candidate)
-//   epi 2    wait GEMM2(own tile) + gdone: Z (recomputed from TMEM), H~, H_t -> U, A panel, HBM;  X_{t+1} k-step  __syncthreads
-// so the tensor core works on T_0 while the LSU still gathers T_1, and a step has two block-wide barriers instead of four.
+//   epi 2    wait GEMM2(own tile): Z (recomputed from TMEM), H~, H_t -> U, A panel, HBM;  X_{t+1} k-step           barrier
+// The task lists of the gather are balanced over the warps when the plan is built (graph_image.cuh), which is what makes the extra
+// barriers cheap (round 1 profile: 25 % of all warp time was barrier wait behind the warp that always drew the longest rows).
 // X is never gathered per step: P_o X_t, P_i X_t of ALL steps of a window are produced by one gather pass over rows of
 // T*Cin floats in the window prologue and parked in the window's own (not yet written) output rows out[b, t, :, 0:8].
 template <int CIN>
@@ -188,9 +181,8 @@ __global__ void __launch_bounds__(512, 1) k_dcrnn_seq_tc(const TcParams p) {
   const uint32_t* s_idx = reinterpret_cast<const uint32_t*>(img + p.gl.off_idx);
   const float4* s_val = reinterpret_cast<const float4*>(img + p.gl.off_val);
   float* Bs = reinterpret_cast<float*>(smem + p.off_bias);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.off_bar);   // [0..3] MMA done (gemm*2+tile; 3 commits each), [4] prologue TMA, [5] gather done
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.off_bar);   // [0..3] MMA done (gemm*2+tile), [4] prologue TMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
-  uint32_t* cnt = tmem_slot + 1;                                    // [4] warps that finished segment (tile*2+op) (monotonic)
 
   if (blockIdx.x >= p.B) return;
 
@@ -200,10 +192,7 @@ __global__ void __launch_bounds__(512, 1) k_dcrnn_seq_tc(const TcParams p) {
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   if (tid == 0) {
-    for (int i = 0; i < 4; ++i) mbar_init(&bars[i], 3);
-    mbar_init(&bars[4], 1);
-    mbar_init(&bars[5], 16);
-    cnt[0] = cnt[1] = cnt[2] = cnt[3] = 0;
+    for (int i = 0; i < 5; ++i) mbar_init(&bars[i], 1);
     fence_mbar_init();
     const uint32_t tx = (p.n_ops ? (uint32_t)p.gl.bytes : 0u) + (p.wimage ? (uint32_t)TC_WIMAGE_BYTES : 0u);
     if (tx) {   // graph image and weight image arrive by TMA bulk copies while the CTA zeroes its panels
@@ -255,7 +244,7 @@ __global__ void __launch_bounds__(512, 1) k_dcrnn_seq_tc(const TcParams p) {
   const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
   const uint32_t a_hi_s = smem_u32(a_hi), a_lo_s = smem_u32(a_lo), b_hi_s = smem_u32(b_hi), b_lo_s = smem_u32(b_lo);
   constexpr uint32_t ID64 = umma_idesc_f16(128, 64), ID32 = umma_idesc_f16(128, 32);
-  uint32_t parity = 0, gpar = 0, rounds = 0;
+  uint32_t parity = 0;
   const bool two_tiles = N > 128;
   const int j = lane & 7, quarter = lane >> 3;
   const float* Uj = U + 4 * j;
@@ -282,7 +271,6 @@ __global__ void __launch_bounds__(512, 1) k_dcrnn_seq_tc(const TcParams p) {
                  gm == 0 ? ID64 : ID32, (grp == 0 && pass == 0 && i == 0) ? 0u : 1u);
       }
     }
-    umma_commit(&bars[2 * gm + tl]);
   };
 
   // this warp's warp-tasks of segment `seg` = (MMA tile of the destination rows) * 2 + operator: results -> A panels as fp16 hi/lo
@@ -301,33 +289,40 @@ __global__ void __launch_bounds__(512, 1) k_dcrnn_seq_tc(const TcParams p) {
       }
     }
   };
-  // a warp has written its share of segment `seg`: the last of the 16 warps to say so issues that segment's MMA group
-  auto segment_done = [&](int seg, int gm) {
-    fence_proxy_async();        // my generic-proxy stores to the A panels -> visible to the tensor core (async proxy)
-    __syncwarp();
-    if (lane == 0) {
-      const uint32_t old = atom_add_acq_rel_shared(&cnt[seg], 1u);
-      if (old + 1u == 16u * (rounds + 1u)) {
-        tc_fence_after();
-        const int tl = seg >> 1;
-        if (tl == 0 || two_tiles) issue_group(tl, gm, 1 + (seg & 1));
-      }
-      if (seg == 3) mbar_arrive(&bars[5]);     // my gathers of this round are complete (U is no longer read by me)
-    }
-    __syncwarp();
-  };
+  // One gather round.  tid 0 issues every MMA: the static group (H | X k-steps) of both tiles right away (the block barrier in front of
+  // the round ordered those operand stores), tile 0's P_o / P_i groups behind the barrier that closes tile 0's tasks -- they run on the
+  // tensor core while the LSU gathers tile 1 -- and tile 1's groups behind the closing barrier.  One commit per tile covers all of
+  // that tile's MMAs (same issuing thread => in order).  The task lists are balanced (graph_image.cuh), so the two barriers are cheap;
+  // the closing one also tells the epilogue that nobody reads U any more.
   auto gather_round = [&](int gm) {
-    if (tid == 0) {             // (the block-wide barrier in front of every round ordered all operand stores)
+    if (tid == 0) {
       issue_group(0, gm, 0);
       if (two_tiles) issue_group(1, gm, 0);
-      tc_fence_before();
     }
-#pragma unroll
-    for (int seg = 0; seg < 4; ++seg) {
-      if ((seg & 1) < p.n_ops) gather_segment(seg);
-      segment_done(seg, gm);
+    if (p.n_ops > 0) gather_segment(0);
+    if (p.n_ops > 1) gather_segment(1);
+    fence_proxy_async();        // my generic-proxy stores to the A panels -> visible to the tensor core (async proxy)
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (tid == 0) {
+      issue_group(0, gm, 1);
+      issue_group(0, gm, 2);
+      umma_commit(&bars[2 * gm]);
     }
-    ++rounds;
+    if (two_tiles) {
+      if (p.n_ops > 0) gather_segment(2);
+      if (p.n_ops > 1) gather_segment(3);
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (tid == 0 && two_tiles) {
+      issue_group(1, gm, 1);
+      issue_group(1, gm, 2);
+      umma_commit(&bars[2 * gm + 1]);
+    }
   };
 
   auto x_base = [&](long long b) -> const float* { return p.x + (p.win_start ? p.win_start[b] * p.x_tstride : b * p.x_bstride); };
@@ -363,10 +358,27 @@ __global__ void __launch_bounds__(512, 1) k_dcrnn_seq_tc(const TcParams p) {
       for (int t0 = 0; t0 < T; t0 += TCH) {
         const int tn = (T - t0) < TCH ? (T - t0) : TCH;
         const int F = tn * CIN, NC = N * CIN;
-        for (int idx = tid; idx < tn * NC; idx += 512) {            // U[n][tt*CIN + c] = X[b, t0+tt, n, c]
-          const int tt = idx / NC, r = idx - tt * NC;
-          const int n = r / CIN, c = r - n * CIN;
-          U[n * TC_UP + tt * CIN + c] = __ldg(xb + (long long)(t0 + tt) * p.x_tstride + r);
+        // U[n][tt*CIN + c] = X[b, t0+tt, n, c]: all loads of a thread are issued before the first store (one HBM/L2 latency)
+        for (int base = 0; base < tn * NC; base += 512 * 8) {
+          float xv8[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int idx = base + u * 512 + tid;
+            xv8[u] = 0.f;
+            if (idx < tn * NC) {
+              const int tt = idx / NC, r = idx - tt * NC;
+              xv8[u] = __ldg(xb + (long long)(t0 + tt) * p.x_tstride + r);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int idx = base + u * 512 + tid;
+            if (idx < tn * NC) {
+              const int tt = idx / NC, r = idx - tt * NC;
+              const int n = r / CIN, c = r - n * CIN;
+              U[n * TC_UP + tt * CIN + c] = xv8[u];
+            }
+          }
         }
         __syncthreads();
         for (int seg = 0; seg < 4; ++seg) {
@@ -377,12 +389,21 @@ __global__ void __launch_bounds__(512, 1) k_dcrnn_seq_tc(const TcParams p) {
               const float4 acc = gather_groups(Uj, s_idx, s_val, (int)(d >> 16), (int)((d >> 9) & 0x7f));
               const float av[4] = {acc.x, acc.y, acc.z, acc.w};
               const int drow = d & 0xff, op = (d >> 8) & 1;
+              float* orow = p.out + ((b * T + t0) * (long long)N + drow) * 32 + op * 4;
+              const long long tstep = (long long)N * 32;
+              if (CIN == 2) {           // floats 4j..4j+3 = (t, c) = (2j,0) (2j,1) (2j+1,0) (2j+1,1): two 8-byte stores
+                *reinterpret_cast<float2*>(orow + (2 * j) * tstep) = make_float2(av[0], av[1]);
+                if (4 * j + 2 < F) *reinterpret_cast<float2*>(orow + (2 * j + 1) * tstep) = make_float2(av[2], av[3]);
+              } else if (CIN == 4) {    // one timestep per lane: a 16-byte store
+                *reinterpret_cast<float4*>(orow + j * tstep) = acc;
+              } else {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const int f = 4 * j + k;
-                if (f < F) {
-                  const int tt = f / CIN, c = f - tt * CIN;
-                  p.out[((b * T + t0 + tt) * (long long)N + drow) * 32 + op * 4 + c] = av[k];
+                for (int k = 0; k < 4; ++k) {
+                  const int f = 4 * j + k;
+                  if (f < F) {
+                    const int tt = f / CIN, c = f - tt * CIN;
+                    orow[tt * tstep + c] = av[k];
+                  }
                 }
               }
             }
@@ -417,8 +438,6 @@ __global__ void __launch_bounds__(512, 1) k_dcrnn_seq_tc(const TcParams p) {
       gather_round(0);
       // ---- epilogue 1: r gate; H*R ---------------------------------------------------------------------------------------
       if (tile == 0 || two_tiles) mbar_wait(&bars[tile], parity);   // tile 1 has no rows when N <= 128
-      mbar_wait(&bars[5], gpar);
-      gpar ^= 1u;
       tc_fence_after();
       const long long obase = (b * T + t) * (long long)N;
       {
@@ -457,8 +476,6 @@ __global__ void __launch_bounds__(512, 1) k_dcrnn_seq_tc(const TcParams p) {
       const bool feed_x = owner && t + 1 < T;
       if (feed_x) load_x(xb, b, t + 1, xv, po, pi);      // in flight under the MMA wait
       if (tile == 0 || two_tiles) mbar_wait(&bars[2 + tile], parity);
-      mbar_wait(&bars[5], gpar);
-      gpar ^= 1u;
       tc_fence_after();
       {
         // Z is recomputed from its accumulator, which stays in TMEM until the next step's GEMM 1: cheaper than keeping

@@ -636,6 +636,7 @@ __global__ void __launch_bounds__(512) k_build_graph_image(const int* rp0, const
   if (tid == 0) {
     int load[kImgWarps], cntw[kImgWarps], pos[kImgWarps];
     for (int w = 0; w < kImgWarps; ++w) load[w] = 0;
+    load[0] = 24;                                        // warp 0 also issues the round's MMAs (~42 x 8 issue slots)
     int nwt = 0;
     int base = 0;
     for (int seg = 0; seg < kImgSegs; base += s_segcount[seg], ++seg) {

@@ -115,6 +115,135 @@ __global__ void __launch_bounds__(256) k_spmm(SpmmArgs a, int G, int log2G) {
   }
 }
 
+// Variant with NO scalar tail: every batch of U entries is predicated, so a row of degree d costs ceil(d/U) dependent
+// (entry load -> gather) round trips instead of floor(d/4) + d%4 (degree 11: 3 or 2 instead of 5).  Same arithmetic order.
+template <int VEC, int U>
+__global__ void __launch_bounds__(256) k_spmm_masked(SpmmArgs a, int G, int log2G) {
+  const int lane_in_group = threadIdx.x & (G - 1);
+  const long long group = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> log2G;
+  const long long total = a.batch * (long long)a.n;
+  if (group >= total) return;
+  const int i = (int)(group % a.n);
+  const long long b = group / a.n;
+  const float* xb = a.x + b * a.bsx;
+  const float* attb = a.att ? a.att + b * (long long)a.n * a.att_ld : nullptr;
+  const int beg = a.rowptr[i], end = a.rowptr[i + 1];
+  for (int f0 = lane_in_group * VEC; f0 < a.f; f0 += G * VEC) {
+    float acc[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
+    for (int k = beg; k < end; k += U) {
+      int2 e[U];
+      float xv[U][VEC];
+      float w[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) e[u] = (k + u < end) ? __ldg(&a.cv[k + u]) : make_int2(i, 0);
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (k + u < end) ld_vec<VEC>(xb + (long long)e[u].x * a.ldx + f0, xv[u]);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        w[u] = __int_as_float(e[u].y);
+        if (attb && k + u < end) {
+          float s = a.att_transposed ? __ldg(&attb[(long long)e[u].x * a.att_ld + i]) : __ldg(&attb[(long long)i * a.att_ld + e[u].x]);
+          w[u] = __fmul_rn(w[u], s);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (k + u < end) {
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) acc[v] = __fadd_rn(acc[v], __fmul_rn(w[u], xv[u][v]));
+        }
+    }
+    float o[VEC];
+    if (a.z) {
+      float zv[VEC];
+      ld_vec<VEC>(a.z + b * a.bsz + (long long)i * a.ldz + f0, zv);
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) o[v] = __fadd_rn(__fmul_rn(a.alpha, acc[v]), __fmul_rn(a.beta, zv[v]));
+    } else {
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) o[v] = (a.alpha == 1.0f) ? acc[v] : __fmul_rn(a.alpha, acc[v]);
+    }
+    st_vec<VEC>(a.y + b * a.bsy + (long long)i * a.ldy + f0, o);
+  }
+}
+
+// ---- TMA-staged gather ---------------------------------------------------------------------------------------------------------
+// One warp per (batch, destination) row, persistent over rows.  The source rows of the destination's CSR row are fetched by TMA bulk
+// copies (cp.async.bulk global -> shared, one per edge, 4*f bytes each, completion on the warp's mbarrier) into the warp's slots in
+// shared memory, up to SLOTS rows per batch -- the loads in flight are bounded by shared memory (SLOTS x 4f bytes per warp), not by
+// the L1's outstanding-load tracking that caps the register gather (k_spmm: ~64 KB per SM in flight whatever the unroll depth:
+// tests/perf/spmm_variants.py).  Lanes then read their float4 of every staged row (conflict-free) and accumulate in CSR order with
+// separate multiply and add -- bit-identical to k_spmm.  Needs f % 4 == 0, 16-byte aligned rows, f <= 32 * 4 * JMAX, no attention.
+template <int SLOTS, int JMAX>
+__global__ void __launch_bounds__(256) k_spmm_tma(SpmmArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rowbytes = a.f * 4;
+  float* slots = reinterpret_cast<float*>(smem_raw) + (size_t)warp * SLOTS * a.f;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)8 * SLOTS * rowbytes) + warp;
+  if (lane == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  __syncwarp();
+  const long long total = a.batch * (long long)a.n;
+  uint32_t parity = 0;
+  for (long long group = (long long)blockIdx.x * 8 + warp; group < total; group += (long long)gridDim.x * 8) {
+    const int i = (int)(group % a.n);
+    const long long b = group / a.n;
+    const float* xb = a.x + b * a.bsx;
+    const int beg = __ldg(a.rowptr + i), end = __ldg(a.rowptr + i + 1);
+    float acc[JMAX][4];
+#pragma unroll
+    for (int j = 0; j < JMAX; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+    for (int c0 = beg; c0 < end; c0 += SLOTS) {
+      const int nh = min(SLOTS, end - c0);
+      const int2 mine = lane < nh ? __ldg(a.cv + c0 + lane) : make_int2(0, 0);
+      if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)(nh * rowbytes));
+      __syncwarp();
+      if (lane < nh) tma_bulk_g2s(slots + (size_t)lane * a.f, xb + (long long)mine.x * a.ldx, (uint32_t)rowbytes, bar);
+      mbar_wait(bar, parity);
+      parity ^= 1u;
+      for (int u = 0; u < nh; ++u) {
+        const float w = __int_as_float(__shfl_sync(0xffffffffu, mine.y, u));
+#pragma unroll
+        for (int j = 0; j < JMAX; ++j) {
+          const int f0 = (j * 32 + lane) * 4;
+          if (f0 < a.f) {
+            const float4 xv = *reinterpret_cast<const float4*>(slots + (size_t)u * a.f + f0);
+            acc[j][0] = __fadd_rn(acc[j][0], __fmul_rn(w, xv.x));
+            acc[j][1] = __fadd_rn(acc[j][1], __fmul_rn(w, xv.y));
+            acc[j][2] = __fadd_rn(acc[j][2], __fmul_rn(w, xv.z));
+            acc[j][3] = __fadd_rn(acc[j][3], __fmul_rn(w, xv.w));
+          }
+        }
+      }
+      __syncwarp();          // every lane is done with the slots before the next batch of copies overwrites them
+    }
+#pragma unroll
+    for (int j = 0; j < JMAX; ++j) {
+      const int f0 = (j * 32 + lane) * 4;
+      if (f0 < a.f) {
+        float o[4];
+        if (a.z) {
+          const float4 zv = __ldg(reinterpret_cast<const float4*>(a.z + b * a.bsz + (long long)i * a.ldz + f0));
+          o[0] = __fadd_rn(__fmul_rn(a.alpha, acc[j][0]), __fmul_rn(a.beta, zv.x));
+          o[1] = __fadd_rn(__fmul_rn(a.alpha, acc[j][1]), __fmul_rn(a.beta, zv.y));
+          o[2] = __fadd_rn(__fmul_rn(a.alpha, acc[j][2]), __fmul_rn(a.beta, zv.z));
+          o[3] = __fadd_rn(__fmul_rn(a.alpha, acc[j][3]), __fmul_rn(a.beta, zv.w));
+        } else {
+#pragma unroll
+          for (int v = 0; v < 4; ++v) o[v] = (a.alpha == 1.0f) ? acc[j][v] : __fmul_rn(a.alpha, acc[j][v]);
+        }
+        *reinterpret_cast<float4*>(a.y + b * a.bsy + (long long)i * a.ldy + f0) = make_float4(o[0], o[1], o[2], o[3]);
+      }
+    }
+  }
+}
+
 // The same product with the row's edge entries fetched ONCE by the group (lane l loads entry l: one coalesced 8-byte load per
 // lane instead of a dependent broadcast load in front of every batch of gathers) and handed out by shuffles, so that U
 // gathers are in flight per group and a row costs one entry-load latency + ceil(deg/U) gather latencies.  Same arithmetic
@@ -260,9 +389,51 @@ static int spmm_impl(const stmp_plan* plan, int op, int transposed, int64_t batc
   cudaStream_t st = (cudaStream_t)stream;
   if (g_spmm_variant < 0) {
     const char* v = getenv("STMP_SPMM_VARIANT");
-    g_spmm_variant = v ? atoi(v) : 2;
+    g_spmm_variant = v ? atoi(v) : 0;   // measured (tests/perf/spmm_variants.py, cfg5 probe): v0 1487 GB/s, v1 1364, v2 1064
   }
-  if (!att && g_spmm_variant > 0 && (long long)c.n * ldx < (1ll << 31)) {
+  if ((g_spmm_variant == 5 || g_spmm_variant == 6) && !att && vec == 4 && f <= 512 && (long long)groups >= 8) {
+    // TMA-staged gather: SLOTS x 4f bytes of shared memory per warp
+    const int slots = g_spmm_variant == 5 ? 8 : 16;
+    const size_t smem = (size_t)8 * slots * f * 4 + 8 * 8;
+    if (smem <= 200 * 1024) {
+      int dev = 0, sms = 0;
+      STMP_CUDA_OK(cudaGetDevice(&dev));
+      STMP_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+      int per_sm = (int)((220 * 1024) / (smem + 1024));
+      if (per_sm > 8) per_sm = 8;
+      if (per_sm < 1) per_sm = 1;
+      long long want = (groups + 7) / 8;
+      unsigned grid = (unsigned)(want < (long long)sms * per_sm ? want : (long long)sms * per_sm);
+      const int jm = (int)((f + 127) / 128);
+#define STMP_TMA_LAUNCH(S, J)                                                                                          \
+  do {                                                                                                                 \
+    STMP_CUDA_OK(cudaFuncSetAttribute(k_spmm_tma<S, J>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
+    k_spmm_tma<S, J><<<grid, 256, smem, st>>>(a);                                                                      \
+  } while (0)
+      if (slots == 8) {
+        if (jm == 1) STMP_TMA_LAUNCH(8, 1); else if (jm == 2) STMP_TMA_LAUNCH(8, 2); else STMP_TMA_LAUNCH(8, 4);
+      } else {
+        if (jm == 1) STMP_TMA_LAUNCH(16, 1); else if (jm == 2) STMP_TMA_LAUNCH(16, 2); else STMP_TMA_LAUNCH(16, 4);
+      }
+#undef STMP_TMA_LAUNCH
+      STMP_LAUNCH_OK("k_spmm_tma");
+      return STMP_OK;
+    }
+  }
+  if (g_spmm_variant == 3 || g_spmm_variant == 4) {
+    if (g_spmm_variant == 3) {
+      if (vec == 4) k_spmm_masked<4, 4><<<(unsigned)blocks, 256, 0, st>>>(a, G, lg);
+      else if (vec == 2) k_spmm_masked<2, 4><<<(unsigned)blocks, 256, 0, st>>>(a, G, lg);
+      else k_spmm_masked<1, 4><<<(unsigned)blocks, 256, 0, st>>>(a, G, lg);
+    } else {
+      if (vec == 4) k_spmm_masked<4, 8><<<(unsigned)blocks, 256, 0, st>>>(a, G, lg);
+      else if (vec == 2) k_spmm_masked<2, 8><<<(unsigned)blocks, 256, 0, st>>>(a, G, lg);
+      else k_spmm_masked<1, 8><<<(unsigned)blocks, 256, 0, st>>>(a, G, lg);
+    }
+    STMP_LAUNCH_OK("k_spmm_masked");
+    return STMP_OK;
+  }
+  if (!att && (g_spmm_variant == 1 || g_spmm_variant == 2) && (long long)c.n * ldx < (1ll << 31)) {
     if (g_spmm_variant == 1) {
       if (vec == 4) k_spmm_pre<4, 4><<<(unsigned)blocks, 256, 0, st>>>(a, G, lg);
       else if (vec == 2) k_spmm_pre<2, 4><<<(unsigned)blocks, 256, 0, st>>>(a, G, lg);
