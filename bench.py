@@ -192,8 +192,11 @@ def spmm_probe(dev, pk):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
     gbs = bytes_alg / (ms * 1e-3) / 1e9
+    gather = 4 * nnz * F * B                       # source rows delivered L2 -> SM (every entry reads a 4F-byte row); not HBM traffic
     return {"workload": "SpMM N=10000 nnz=%d F=128 batch=32 (in 164 MB + out 164 MB > L2)" % nnz, "ms": ms,
-            "algorithmic_bytes": bytes_alg, "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"]}
+            "algorithmic_bytes": bytes_alg, "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
+            "l2_gather_bytes": gather, "l2_to_sm_gbs": (gather + bytes_alg) / (ms * 1e-3) / 1e9,
+            "note": "random graph: bound by the L2->SM delivery of the gathered rows (5.5x the algorithmic bytes), see DESIGN.md section 3"}
 
 
 class EpochFeeder(object):

@@ -284,12 +284,18 @@ int stmp_gemm_lstm_f32(const float* A, int64_t lda, int64_t M, int64_t K, int64_
  *   st_out[b, j, i] = S[b, i, j], rows ld_out (>= nodes rounded up to 64, % 4 == 0) floats apart, padding columns zero.
  *   lhs [B][nodes][T] = (X~ W1) W2, rhs [B][T][nodes] = (W3 X~)^T, bsT [nodes][nodes] = bs^T, vsT_packed = stmp_gemm_prepack of Vs^T
  *   zero-padded to [P][P], P = nodes rounded up to 64 (<= 320).  The N x N sigmoid is generated inside the GEMM's operand stage and the
- *   softmax is the GEMM epilogue: neither ever reaches HBM.  nodes <= 320, T <= 16. */
+ *   softmax is the GEMM epilogue: neither ever reaches HBM.
+ *   nodes <= 320, T <= 12.
+ * Optional weight IMAGE (both entries; NULL = the kernel swizzles the packed weights itself): stmp_gemm_blocks_image rewrites a packed weight
+ * into the per-k-block shared-memory image (hi | lo tile, SWIZZLE_128B) of stmp_gemm_blocks_image_bytes(N, nblk) bytes, which every CTA then
+ * fetches with ONE TMA bulk copy per k-block while it loads / generates its A tile. */
 int stmp_gemm_blocks_f32(int64_t M, int64_t N, int64_t ncols, int64_t nblk, const float* const* blk_ptr, const int64_t* blk_ld,
-                         const int32_t* blk_width, const int32_t* blk_shift, int64_t seq, const void* packed, const float* bias,
-                         int epilogue, const float* gamma, const float* beta, float eps, float* C, int64_t ldc, void* stream);
+                         const int32_t* blk_width, const int32_t* blk_shift, int64_t seq, const void* packed, const void* image,
+                         const float* bias, int epilogue, const float* gamma, const float* beta, float eps, float* C, int64_t ldc, void* stream);
 int stmp_spatial_attention_fwd(int64_t B, int64_t n_nodes, int64_t n_steps, const float* lhs, const float* rhs, const float* bsT,
-                               const void* vsT_packed, float* st_out, int64_t ld_out, void* stream);
+                               const void* vsT_packed, const void* vsT_image, float* st_out, int64_t ld_out, void* stream);
+int64_t stmp_gemm_blocks_image_bytes(int64_t N, int64_t nblk);
+int stmp_gemm_blocks_image(const void* packed, int64_t N, int64_t nblk, void* image, void* stream);
 
 /* ---- K8: index-batching window gather -----------------------------------------------------------
  * x[b] = series[start[b] : start[b]+h], y[b] = series[start[b]+h : start[b]+2h]   (index_dataset.py:49-57

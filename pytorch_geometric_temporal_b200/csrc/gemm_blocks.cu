@@ -46,6 +46,7 @@ struct GbParams {
   int seq;                  // rows per sequence for shifted blocks (>= 1)
   const __half* w_hi;       // [N][nblk*64]
   const __half* w_lo;
+  const unsigned char* w_img;   // optional: per k-block the B tile exactly as it sits in shared memory (hi | lo, swizzled): one TMA bulk copy
   const float* bias;        // [N] or null
   float* C; long long ldc;
   int ncols;                // columns written (<= N)
@@ -68,9 +69,9 @@ __global__ void __launch_bounds__(GB_NT, 1) k_gemm_blocks(const GbParams p) {
   const int N = p.N;
   const int b_bytes = N * 128;                       // one K-block of B (hi or lo)
   const int stage_bytes = 2 * GB_A_BYTES + 2 * b_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * stage_bytes);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
-  float* red = reinterpret_cast<float*>(bars + 4);     // [2][128] epilogue exchange (EPI_SOFTMAX)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * stage_bytes);   // [0,1] MMAs of a stage drained; [2,3] B tile of a stage landed (TMA)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  float* red = reinterpret_cast<float*>(bars + 6);     // [2][128] epilogue exchange (EPI_SOFTMAX)
 
   const int tm_cols = N > 256 ? 512 : 256;
   if (warp == 0) {
@@ -78,8 +79,7 @@ __global__ void __launch_bounds__(GB_NT, 1) k_gemm_blocks(const GbParams p) {
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   if (tid == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&bars[i], 1);
     fence_mbar_init();
   }
   tc_fence_before();
@@ -91,17 +91,21 @@ __global__ void __launch_bounds__(GB_NT, 1) k_gemm_blocks(const GbParams p) {
   const int nh = N > 256 ? 2 : 1, Nh = N / nh;        // MMA column halves
   const uint32_t idesc = umma_idesc_f16(128, Nh);
 
-  // MODE_SPATT per-thread constants: my row (b, j) and its RHS column
-  float rj[16];
-  int sp_b = 0, sp_j = 0;
-  const int sp_r = tid & 127, sp_kh = tid >> 7;
+  // MODE_SPATT register tile: thread = 4 consecutive rows (b, j..j+3) x 8 k of every k-block.  RHS columns of my rows live in
+  // registers for the whole tile; LHS rows are warp-uniform addresses (a warp shares k): broadcast 16-byte loads out of L1.
+  float rj[4][12];
+  int sp_b[4], sp_j[4];
+  const int sp_r0 = (tid & 31) * 4, sp_k8 = (tid >> 5) * 8;
   if (p.spatt) {
-    const long long m = m0 + sp_r;
-    const long long mm = m < p.M ? m : p.M - 1;
-    sp_b = (int)(mm / p.Nn);
-    sp_j = (int)(mm - (long long)sp_b * p.Nn);
 #pragma unroll
-    for (int t = 0; t < 16; ++t) rj[t] = t < p.Tn ? __ldg(p.rhs + ((long long)sp_b * p.Tn + t) * p.Nn + sp_j) : 0.f;
+    for (int r = 0; r < 4; ++r) {
+      const long long m = m0 + sp_r0 + r;
+      const long long mm = m < p.M ? m : p.M - 1;
+      sp_b[r] = (int)(mm / p.Nn);
+      sp_j[r] = (int)(mm - (long long)sp_b[r] * p.Nn);
+#pragma unroll
+      for (int t = 0; t < 12; ++t) rj[r][t] = t < p.Tn ? __ldg(p.rhs + ((long long)sp_b[r] * p.Tn + t) * p.Nn + sp_j[r]) : 0.f;
+    }
   }
 
   for (int kb = 0; kb < nkb; ++kb) {
@@ -115,6 +119,10 @@ __global__ void __launch_bounds__(GB_NT, 1) k_gemm_blocks(const GbParams p) {
       tc_fence_after();
     }
     const int k0 = kb * 64;
+    if (p.w_img && tid == 0) {
+      mbar_arrive_expect_tx(&bars[2 + s], 2u * (uint32_t)b_bytes);
+      tma_bulk_g2s(b_hi, p.w_img + (size_t)kb * 2 * b_bytes, 2u * (uint32_t)b_bytes, &bars[2 + s]);
+    }
     if (!p.spatt) {
       // A: 128 x 64 fp32 of block kb (row-shifted, zero outside the sequence / beyond `width`) -> hi/lo fp16, swizzled.
       const KBlock blk = p.blk[kb];
@@ -148,33 +156,65 @@ __global__ void __launch_bounds__(GB_NT, 1) k_gemm_blocks(const GbParams p) {
         store_split4(a_hi, a_lo, idx >> 4, 4 * (idx & 15), v[jj]);
       }
     } else {
-      // A generated: A[(b,j)][k] = sigmoid(sum_t LHS[b,k,t] RHS[b,t,j] + bsT[j][k]); thread = (row, k half of 32).  LHS rows are
-      // warp-uniform addresses (all rows of a warp share b except across one batch boundary): broadcast loads out of L1.
+      // A generated: A[(b,j)][k] = sigmoid(sum_t LHS[b,k,t] RHS[b,t,j] + bsT[j][k])
       const int Tn = p.Tn;
-      const float* lb = p.lhs + (long long)sp_b * p.Nn * Tn;
-      const float* bsr = p.bsT + (long long)sp_j * p.Nn;
-#pragma unroll 2
-      for (int g = 0; g < 8; ++g) {
-        const int kk = sp_kh * 32 + 4 * g;
-        float o[4];
+      float o[4][8];
+      const bool uni = sp_b[0] == sp_b[3];             // all four rows in one batch element (always, except across a batch boundary)
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int k = k0 + kk + e;
-          float acc = 0.f;
-          if (k < p.Nn) {
-            const float* lk = lb + (long long)k * Tn;
+      for (int e = 0; e < 8; ++e) {
+        const int k = k0 + sp_k8 + e;
+        const bool kv = k < p.Nn;
+        if (uni) {
+          float l[12];
 #pragma unroll
-            for (int t = 0; t < 16; ++t)
-              if (t < Tn) acc = fmaf(__ldg(lk + t), rj[t], acc);
-            acc = sigmoid_g(acc + __ldg(bsr + k));
+          for (int t = 0; t < 12; ++t) l[t] = 0.f;
+          if (kv) {
+            const float* lk = p.lhs + ((long long)sp_b[0] * p.Nn + k) * Tn;
+            if (Tn == 12) {                              // 48-byte rows: three 16-byte broadcast loads
+#pragma unroll
+              for (int q4 = 0; q4 < 3; ++q4) {
+                const float4 v4 = __ldg(reinterpret_cast<const float4*>(lk) + q4);
+                l[4 * q4] = v4.x; l[4 * q4 + 1] = v4.y; l[4 * q4 + 2] = v4.z; l[4 * q4 + 3] = v4.w;
+              }
+            } else {
+#pragma unroll
+              for (int t = 0; t < 12; ++t)
+                if (t < Tn) l[t] = __ldg(lk + t);
+            }
           }
-          o[e] = acc;
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            float acc = 0.f;
+#pragma unroll
+            for (int t = 0; t < 12; ++t) acc = fmaf(l[t], rj[r][t], acc);
+            o[r][e] = acc;
+          }
+        } else {
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            float acc = 0.f;
+            if (kv) {
+              const float* lk = p.lhs + ((long long)sp_b[r] * p.Nn + k) * Tn;
+#pragma unroll
+              for (int t = 0; t < 12; ++t)
+                if (t < Tn) acc = fmaf(__ldg(lk + t), rj[r][t], acc);
+            }
+            o[r][e] = acc;
+          }
         }
-        store_split4(a_hi, a_lo, sp_r, kk, make_float4(o[0], o[1], o[2], o[3]));
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const float* bsr = p.bsT + (long long)sp_j[r] * p.Nn + k0 + sp_k8;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[r][e] = (k0 + sp_k8 + e < p.Nn) ? sigmoid_g(o[r][e] + __ldg(bsr + e)) : 0.f;
+        store_split4(a_hi, a_lo, sp_r0 + r, sp_k8, make_float4(o[r][0], o[r][1], o[r][2], o[r][3]));
+        store_split4(a_hi, a_lo, sp_r0 + r, sp_k8 + 4, make_float4(o[r][4], o[r][5], o[r][6], o[r][7]));
       }
     }
-    // B: N x 64 fp16 (already split, L2-resident) -> swizzled; 4 x (hi, lo) 128-bit loads in flight per thread
-    for (int base = 0; base < N * 8; base += 4 * GB_NT) {
+    // B: the k-block's tile.  With a pre-swizzled image it is ONE TMA bulk copy issued before the A tile is formed (it lands while the
+    // threads load / generate A); otherwise N x 64 fp16 (already split, L2-resident) -> swizzled by hand.
+    for (int base = 0; base < (p.w_img ? 0 : N * 8); base += 4 * GB_NT) {
       uint4 h[4], l[4];
 #pragma unroll
       for (int jj = 0; jj < 4; ++jj) {
@@ -201,6 +241,7 @@ __global__ void __launch_bounds__(GB_NT, 1) k_gemm_blocks(const GbParams p) {
     __syncthreads();
     tc_fence_after();
     if (tid == 0) {
+      if (p.w_img) mbar_wait(&bars[2 + s], (uint32_t)(kb >> 1) & 1u);
       const uint32_t ah = smem_u32(a_hi), al = smem_u32(a_lo), bh = smem_u32(b_hi), bl = smem_u32(b_lo);
       for (int hh = 0; hh < nh; ++hh) {
 #pragma unroll
@@ -339,9 +380,24 @@ __global__ void __launch_bounds__(GB_NT, 1) k_gemm_blocks(const GbParams p) {
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(tm_cols));
 }
 
+// packed [N][Kpad] hi | lo  ->  per k-block [hi tile | lo tile], each N x 128 B in the SWIZZLE_128B layout of the kernel's B stage
+__global__ void k_gb_weight_image(const __half* __restrict__ hi, const __half* __restrict__ lo, int N, int nblk, unsigned char* __restrict__ img) {
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;     // one 16-byte chunk
+  const long long per = (long long)N * 8;
+  if (idx >= per * nblk * 2) return;
+  const int kb = (int)(idx / (2 * per));
+  const long long rem = idx - (long long)kb * 2 * per;
+  const int half = (int)(rem / per);
+  const int r = (int)(rem - half * per);
+  const int n = r >> 3, c = r & 7;
+  const __half* src = (half ? lo : hi) + (long long)n * nblk * 64 + kb * 64 + 8 * c;
+  const uint4 v = *reinterpret_cast<const uint4*>(src);
+  *reinterpret_cast<uint4*>(img + ((size_t)kb * 2 + half) * N * 128 + n * 128 + ((c ^ (n & 7)) << 4)) = v;
+}
+
 template <int EPI>
 int gb_launch(GbParams& p, cudaStream_t st) {
-  const int smem = 2 * (2 * GB_A_BYTES + 2 * p.N * 128) + 32 + 256 * 4;
+  const int smem = 2 * (2 * GB_A_BYTES + 2 * p.N * 128) + 48 + 256 * 4;
   if (smem > 232448) return set_error(STMP_EUNSUPPORTED, "blocked GEMM: N=%d needs %d B of shared memory", p.N, smem);
   STMP_CUDA_OK(cudaFuncSetAttribute(k_gemm_blocks<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const unsigned grid = (unsigned)((p.M + GB_BM - 1) / GB_BM);
@@ -366,8 +422,8 @@ int gb_dispatch(GbParams& p, int epi, cudaStream_t st) {
 using namespace stmp;
 
 extern "C" int stmp_gemm_blocks_f32(int64_t M, int64_t N, int64_t ncols, int64_t nblk, const float* const* blk_ptr, const int64_t* blk_ld,
-                                    const int32_t* blk_width, const int32_t* blk_shift, int64_t seq, const void* packed, const float* bias,
-                                    int epilogue, const float* gamma, const float* beta, float eps, float* C, int64_t ldc, void* stream) {
+                                    const int32_t* blk_width, const int32_t* blk_shift, int64_t seq, const void* packed, const void* image,
+                                    const float* bias, int epilogue, const float* gamma, const float* beta, float eps, float* C, int64_t ldc, void* stream) {
   STMP_REQUIRE(blk_ptr && blk_ld && blk_width && blk_shift && packed && C, STMP_EINVAL, "stmp_gemm_blocks_f32: NULL pointer");
   STMP_REQUIRE(M >= 0 && nblk >= 1 && seq >= 1, STMP_EINVAL, "stmp_gemm_blocks_f32: bad sizes");
   if (nblk > GB_MAXBLK || N > 320 || N % 16 != 0 || N < 16 || ncols > N || ncols < 1 || M >= (1ll << 31) - 128)
@@ -384,22 +440,36 @@ extern "C" int stmp_gemm_blocks_f32(int64_t M, int64_t N, int64_t ncols, int64_t
   }
   p.nblk = (int)nblk; p.M = (int)M; p.N = (int)N; p.seq = (int)seq; p.ncols = (int)ncols;
   p.w_hi = reinterpret_cast<const __half*>(packed); p.w_lo = p.w_hi + N * nblk * 64;
+  p.w_img = reinterpret_cast<const unsigned char*>(image);
   p.bias = bias; p.C = C; p.ldc = ldc; p.gamma = gamma; p.beta = beta; p.eps = eps;
   return gb_dispatch(p, epilogue, (cudaStream_t)stream);
 }
 
+extern "C" int64_t stmp_gemm_blocks_image_bytes(int64_t N, int64_t nblk) { return nblk * 2 * N * 128; }
+
+extern "C" int stmp_gemm_blocks_image(const void* packed, int64_t N, int64_t nblk, void* image, void* stream) {
+  STMP_REQUIRE(packed && image && N > 0 && nblk > 0, STMP_EINVAL, "stmp_gemm_blocks_image: bad argument");
+  const __half* hi = reinterpret_cast<const __half*>(packed);
+  const long long total = (long long)N * 8 * nblk * 2;
+  k_gb_weight_image<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(hi, hi + N * nblk * 64, (int)N, (int)nblk,
+                                                                                      reinterpret_cast<unsigned char*>(image));
+  STMP_LAUNCH_OK("k_gb_weight_image");
+  return STMP_OK;
+}
+
 extern "C" int stmp_spatial_attention_fwd(int64_t B, int64_t n_nodes, int64_t n_steps, const float* lhs, const float* rhs, const float* bsT,
-                                          const void* vsT_packed, float* st_out, int64_t ld_out, void* stream) {
+                                          const void* vsT_packed, const void* vsT_image, float* st_out, int64_t ld_out, void* stream) {
   STMP_REQUIRE(lhs && rhs && bsT && vsT_packed && st_out, STMP_EINVAL, "stmp_spatial_attention_fwd: NULL pointer");
   STMP_REQUIRE(B >= 0 && n_nodes >= 1 && n_steps >= 1, STMP_EINVAL, "stmp_spatial_attention_fwd: bad sizes");
   const int64_t Npad = (n_nodes + 63) / 64 * 64;
-  if (Npad > 320 || n_steps > 16 || ld_out < Npad || ld_out % 4 != 0 || (reinterpret_cast<uintptr_t>(st_out) & 15))
-    return set_error(STMP_EUNSUPPORTED, "fused spatial attention takes <= 320 nodes, <= 16 timesteps and 16-byte aligned rows of >= %lld floats "
+  if (Npad > 320 || n_steps > 12 || ld_out < Npad || ld_out % 4 != 0 || (reinterpret_cast<uintptr_t>(st_out) & 15))
+    return set_error(STMP_EUNSUPPORTED, "fused spatial attention takes <= 320 nodes, <= 12 timesteps and 16-byte aligned rows of >= %lld floats "
                                         "(nodes=%lld steps=%lld ld=%lld)", (long long)Npad, (long long)n_nodes, (long long)n_steps, (long long)ld_out);
   if (B == 0) return STMP_OK;
   GbParams p = {};
   p.nblk = (int)(Npad / 64); p.M = (int)(B * n_nodes); p.N = (int)Npad; p.seq = 1; p.ncols = (int)n_nodes;
   p.w_hi = reinterpret_cast<const __half*>(vsT_packed); p.w_lo = p.w_hi + Npad * Npad;
+  p.w_img = reinterpret_cast<const unsigned char*>(vsT_image);
   p.bias = nullptr; p.C = st_out; p.ldc = ld_out;
   p.spatt = 1; p.Nn = (int)n_nodes; p.Tn = (int)n_steps; p.lhs = lhs; p.rhs = rhs; p.bsT = bsT;
   return gb_dispatch(p, EPI_SOFTMAX, (cudaStream_t)stream);

@@ -1,7 +1,11 @@
 // spmm.cu -- K1/K3: gather of source-node rows -> edge-weighted accumulate per destination, with the
-// Chebyshev/diffusion axpby fused into the epilogue.  HBM/L2-bandwidth bound: one group of G lanes owns
-// one (batch, destination) row, lanes are vectorised along the feature axis (float4/float2/float), edge
-// metadata is one 64-bit load per edge, and E gathers are kept in flight (unroll 4) to cover L2 latency.
+// Chebyshev/diffusion axpby fused into the epilogue.  One group of G lanes owns one (batch, destination) row, lanes are
+// vectorised along the feature axis (float4/float2/float), edge metadata is one 64-bit load per edge, 4 gathers in flight.
+// Bound (cfg5 probe, random 10^4-node graph): the L2 -> SM delivery of the gathered rows -- 4*nnz*F*B = 1.8 GB per launch
+// on top of the 0.33 GB of compulsory HBM traffic, ~8.2 TB/s through the crossbar.  Measured dead ends, all bit-identical and all
+// at or below this kernel (tests/perf/spmm_variants.py, profiles/r02_spmm_variants_*.json): entries preloaded once + shuffles
+// with 4 / 8 gathers in flight (0.92x / 0.72x), predicated batches without a scalar tail (0.98x / 0.58x), and TMA-staged
+// source rows (k_spmm_tma below, kept selectable: 0.90x / 0.95x) -- more bytes in flight do not move the delivery rate.
 // Deterministic: per destination the sum runs in the reference's scatter order with separate
 // multiply and add, which makes the result bit-identical to CPU index_select -> mul -> scatter_add_.
 #include <cstdlib>
@@ -9,7 +13,7 @@
 #include "common.cuh"
 
 namespace stmp {
-int g_spmm_variant = -1;   // 0: k_spmm (broadcast entry loads, 4 deep); 1: k_spmm_pre<.,4>; 2: k_spmm_pre<.,8> (default)
+int g_spmm_variant = -1;   // 0 (default): k_spmm register gather; 1 / 2: k_spmm_tma with 8 / 16 staged rows per warp
 namespace {
 
 template <int VEC> struct VecT;
@@ -115,61 +119,6 @@ __global__ void __launch_bounds__(256) k_spmm(SpmmArgs a, int G, int log2G) {
   }
 }
 
-// Variant with NO scalar tail: every batch of U entries is predicated, so a row of degree d costs ceil(d/U) dependent
-// (entry load -> gather) round trips instead of floor(d/4) + d%4 (degree 11: 3 or 2 instead of 5).  Same arithmetic order.
-template <int VEC, int U>
-__global__ void __launch_bounds__(256) k_spmm_masked(SpmmArgs a, int G, int log2G) {
-  const int lane_in_group = threadIdx.x & (G - 1);
-  const long long group = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> log2G;
-  const long long total = a.batch * (long long)a.n;
-  if (group >= total) return;
-  const int i = (int)(group % a.n);
-  const long long b = group / a.n;
-  const float* xb = a.x + b * a.bsx;
-  const float* attb = a.att ? a.att + b * (long long)a.n * a.att_ld : nullptr;
-  const int beg = a.rowptr[i], end = a.rowptr[i + 1];
-  for (int f0 = lane_in_group * VEC; f0 < a.f; f0 += G * VEC) {
-    float acc[VEC];
-#pragma unroll
-    for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
-    for (int k = beg; k < end; k += U) {
-      int2 e[U];
-      float xv[U][VEC];
-      float w[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) e[u] = (k + u < end) ? __ldg(&a.cv[k + u]) : make_int2(i, 0);
-#pragma unroll
-      for (int u = 0; u < U; ++u)
-        if (k + u < end) ld_vec<VEC>(xb + (long long)e[u].x * a.ldx + f0, xv[u]);
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        w[u] = __int_as_float(e[u].y);
-        if (attb && k + u < end) {
-          float s = a.att_transposed ? __ldg(&attb[(long long)e[u].x * a.att_ld + i]) : __ldg(&attb[(long long)i * a.att_ld + e[u].x]);
-          w[u] = __fmul_rn(w[u], s);
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u)
-        if (k + u < end) {
-#pragma unroll
-          for (int v = 0; v < VEC; ++v) acc[v] = __fadd_rn(acc[v], __fmul_rn(w[u], xv[u][v]));
-        }
-    }
-    float o[VEC];
-    if (a.z) {
-      float zv[VEC];
-      ld_vec<VEC>(a.z + b * a.bsz + (long long)i * a.ldz + f0, zv);
-#pragma unroll
-      for (int v = 0; v < VEC; ++v) o[v] = __fadd_rn(__fmul_rn(a.alpha, acc[v]), __fmul_rn(a.beta, zv[v]));
-    } else {
-#pragma unroll
-      for (int v = 0; v < VEC; ++v) o[v] = (a.alpha == 1.0f) ? acc[v] : __fmul_rn(a.alpha, acc[v]);
-    }
-    st_vec<VEC>(a.y + b * a.bsy + (long long)i * a.ldy + f0, o);
-  }
-}
-
 // ---- TMA-staged gather ---------------------------------------------------------------------------------------------------------
 // One warp per (batch, destination) row, persistent over rows.  The source rows of the destination's CSR row are fetched by TMA bulk
 // copies (cp.async.bulk global -> shared, one per edge, 4*f bytes each, completion on the warp's mbarrier) into the warp's slots in
@@ -243,67 +192,6 @@ __global__ void __launch_bounds__(256) k_spmm_tma(SpmmArgs a) {
     }
   }
 }
-
-// The same product with the row's edge entries fetched ONCE by the group (lane l loads entry l: one coalesced 8-byte load per
-// lane instead of a dependent broadcast load in front of every batch of gathers) and handed out by shuffles, so that U
-// gathers are in flight per group and a row costs one entry-load latency + ceil(deg/U) gather latencies.  Same arithmetic
-// (CSR order, separate multiply and add) => bit-identical to k_spmm.  No attention operand (that path keeps k_spmm).
-template <int VEC, int U>
-__global__ void __launch_bounds__(256) k_spmm_pre(SpmmArgs a, int G, int log2G) {
-  const int l = threadIdx.x & (G - 1);
-  const long long group = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> log2G;
-  const long long total = a.batch * (long long)a.n;
-  // whole groups retire together (total groups is padded to the warp by the launch: lanes of absent groups idle but must shuffle)
-  const bool present = group < total;
-  const int i = present ? (int)(group % a.n) : 0;
-  const long long b = present ? group / a.n : 0;
-  const float* xb = a.x + b * a.bsx;
-  const int beg = present ? a.rowptr[i] : 0, end = present ? a.rowptr[i + 1] : 0;
-  const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) & ~(G - 1)));
-
-  for (int f0 = l * VEC; f0 < ((a.f + G * VEC - 1) / (G * VEC)) * (G * VEC); f0 += G * VEC) {
-    const bool fl = f0 < a.f;                       // lanes past the feature tail still take part in the shuffles
-    const float* xr = xb + f0;
-    const int ldx = (int)a.ldx;                     // host guarantees n * ldx < 2^31: 32-bit row offsets
-    float acc[VEC];
-#pragma unroll
-    for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
-    for (int c0 = beg; c0 < end; c0 += G) {
-      const int2 mine = (c0 + l < end) ? __ldg(&a.cv[c0 + l]) : make_int2(0, 0);
-      const int nh = min(G, end - c0);
-      for (int u0 = 0; u0 < nh; u0 += U) {
-        float w[U];
-        float xv[U][VEC];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int col = __shfl_sync(gmask, mine.x, u0 + u, G);
-          w[u] = __int_as_float(__shfl_sync(gmask, mine.y, u0 + u, G));
-          if (u0 + u < nh && fl) ld_vec<VEC>(xr + col * ldx, xv[u]);
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-          if (u0 + u < nh) {
-#pragma unroll
-            for (int v = 0; v < VEC; ++v) acc[v] = __fadd_rn(acc[v], __fmul_rn(w[u], xv[u][v]));
-          }
-      }
-    }
-    if (present && fl) {
-      float o[VEC];
-      if (a.z) {
-        float zv[VEC];
-        ld_vec<VEC>(a.z + b * a.bsz + (long long)i * a.ldz + f0, zv);
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) o[v] = __fadd_rn(__fmul_rn(a.alpha, acc[v]), __fmul_rn(a.beta, zv[v]));
-      } else {
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) o[v] = (a.alpha == 1.0f) ? acc[v] : __fmul_rn(a.alpha, acc[v]);
-      }
-      st_vec<VEC>(a.y + b * a.bsy + (long long)i * a.ldy + f0, o);
-    }
-  }
-}
-
 
 // d(att)[b,i,c] += val * <gy[b,i,:], x[b,c,:]> : one warp per (b, entry); entries are unique (dst,src)
 // pairs except the doubled self loops of CHEB_ATT, hence atomicAdd.
@@ -389,11 +277,11 @@ static int spmm_impl(const stmp_plan* plan, int op, int transposed, int64_t batc
   cudaStream_t st = (cudaStream_t)stream;
   if (g_spmm_variant < 0) {
     const char* v = getenv("STMP_SPMM_VARIANT");
-    g_spmm_variant = v ? atoi(v) : 0;   // measured (tests/perf/spmm_variants.py, cfg5 probe): v0 1487 GB/s, v1 1364, v2 1064
+    g_spmm_variant = v ? atoi(v) : 0;
   }
-  if ((g_spmm_variant == 5 || g_spmm_variant == 6) && !att && vec == 4 && f <= 512 && (long long)groups >= 8) {
+  if ((g_spmm_variant == 1 || g_spmm_variant == 2) && !att && vec == 4 && f <= 512 && (long long)groups >= 8) {
     // TMA-staged gather: SLOTS x 4f bytes of shared memory per warp
-    const int slots = g_spmm_variant == 5 ? 8 : 16;
+    const int slots = g_spmm_variant == 1 ? 8 : 16;
     const size_t smem = (size_t)8 * slots * f * 4 + 8 * 8;
     if (smem <= 200 * 1024) {
       int dev = 0, sms = 0;
@@ -419,32 +307,6 @@ static int spmm_impl(const stmp_plan* plan, int op, int transposed, int64_t batc
       STMP_LAUNCH_OK("k_spmm_tma");
       return STMP_OK;
     }
-  }
-  if (g_spmm_variant == 3 || g_spmm_variant == 4) {
-    if (g_spmm_variant == 3) {
-      if (vec == 4) k_spmm_masked<4, 4><<<(unsigned)blocks, 256, 0, st>>>(a, G, lg);
-      else if (vec == 2) k_spmm_masked<2, 4><<<(unsigned)blocks, 256, 0, st>>>(a, G, lg);
-      else k_spmm_masked<1, 4><<<(unsigned)blocks, 256, 0, st>>>(a, G, lg);
-    } else {
-      if (vec == 4) k_spmm_masked<4, 8><<<(unsigned)blocks, 256, 0, st>>>(a, G, lg);
-      else if (vec == 2) k_spmm_masked<2, 8><<<(unsigned)blocks, 256, 0, st>>>(a, G, lg);
-      else k_spmm_masked<1, 8><<<(unsigned)blocks, 256, 0, st>>>(a, G, lg);
-    }
-    STMP_LAUNCH_OK("k_spmm_masked");
-    return STMP_OK;
-  }
-  if (!att && (g_spmm_variant == 1 || g_spmm_variant == 2) && (long long)c.n * ldx < (1ll << 31)) {
-    if (g_spmm_variant == 1) {
-      if (vec == 4) k_spmm_pre<4, 4><<<(unsigned)blocks, 256, 0, st>>>(a, G, lg);
-      else if (vec == 2) k_spmm_pre<2, 4><<<(unsigned)blocks, 256, 0, st>>>(a, G, lg);
-      else k_spmm_pre<1, 4><<<(unsigned)blocks, 256, 0, st>>>(a, G, lg);
-    } else {
-      if (vec == 4) k_spmm_pre<4, 8><<<(unsigned)blocks, 256, 0, st>>>(a, G, lg);
-      else if (vec == 2) k_spmm_pre<2, 8><<<(unsigned)blocks, 256, 0, st>>>(a, G, lg);
-      else k_spmm_pre<1, 8><<<(unsigned)blocks, 256, 0, st>>>(a, G, lg);
-    }
-    STMP_LAUNCH_OK("k_spmm_pre");
-    return STMP_OK;
   }
   if (vec == 4) k_spmm<4><<<(unsigned)blocks, 256, 0, st>>>(a, G, lg);
   else if (vec == 2) k_spmm<2><<<(unsigned)blocks, 256, 0, st>>>(a, G, lg);

@@ -217,7 +217,7 @@ class ASTGCNBlock(nn.Module):
     def _native_ok(self, N, Fi, T):
         tc, rc = self._time_convolution, self._residual_convolution
         K = self._chebconv_attention._weight.size(0)
-        return (N <= 320 and T <= 16 and Fi <= 64 and K <= 12 and tc.out_channels == 64 and tc.in_channels == 64
+        return (N <= 320 and T <= 12 and Fi <= 64 and K <= 12 and tc.out_channels == 64 and tc.in_channels == 64
                 and tc.stride[1] == 1 and rc.stride[1] == 1 and tc.kernel_size == (1, 3) and tc.padding == (0, 1))
 
     def _native_packs(self):

@@ -230,16 +230,25 @@ def gemm(A: torch.Tensor, packed: torch.Tensor, K: int, N: int, bias: Optional[t
 EPI_BIAS, EPI_RELU, EPI_RELU_LN = 0, 1, 2
 
 
-def gemm_blocks_prepack(blocks) -> torch.Tensor:
+def _weight_image(packed: torch.Tensor, N: int, nblk: int) -> torch.Tensor:
+    img = torch.empty(int(_lib.lib().stmp_gemm_blocks_image_bytes(N, nblk)), dtype=torch.uint8, device=packed.device)
+    with torch.cuda.device(packed.device):
+        _lib.check(_lib.lib().stmp_gemm_blocks_image(_lib.ptr(packed), N, nblk, _lib.ptr(img), _lib.stream_ptr()))
+    return img
+
+
+def gemm_blocks_prepack(blocks):
     """Pack the per-block weights [(width_i, N) fp32 ...] of a blocked GEMM: every block is zero-padded to 64 rows, the stack
-    (nblk*64, N) is split into fp16 hi/lo by stmp_gemm_prepack."""
+    (nblk*64, N) is split into fp16 hi/lo (stmp_gemm_prepack) and rewritten as the per-k-block shared-memory image the kernel
+    fetches by TMA (stmp_gemm_blocks_image).  Returns (packed, image)."""
     N = blocks[0].size(1)
     W = torch.zeros(64 * len(blocks), N, device=blocks[0].device, dtype=torch.float32)
     for i, w in enumerate(blocks):
         if w.size(0) > 64 or w.size(1) != N:
             raise RuntimeError("blocked GEMM: weight blocks must be (<=64, N)")
         W[64 * i:64 * i + w.size(0)] = w
-    return gemm_prepack(W)
+    packed = gemm_prepack(W)
+    return packed, _weight_image(packed, N, len(blocks))
 
 
 def gemm_blocks(blocks, packed: torch.Tensor, N: int, ncols: int, bias: Optional[torch.Tensor] = None, epilogue: int = EPI_BIAS,
@@ -260,10 +269,11 @@ def gemm_blocks(blocks, packed: torch.Tensor, N: int, ncols: int, bias: Optional
         ptrs[i], lds[i], widths[i], shifts[i] = t.data_ptr(), t.stride(0), width, shift
     C = torch.empty((M, ncols), dtype=torch.float32, device=dev) if out is None else out
     v = [None if t is None else _f32c(t.detach(), "param") for t in (bias, gamma, beta)]
+    packed, image = packed if isinstance(packed, tuple) else (packed, None)
     with torch.cuda.device(dev):
         _lib.check(_lib.lib().stmp_gemm_blocks_f32(M, N, ncols, n, ctypes.cast(ptrs, ctypes.c_void_p), ctypes.cast(lds, ctypes.c_void_p),
                                                    ctypes.cast(widths, ctypes.c_void_p), ctypes.cast(shifts, ctypes.c_void_p), seq,
-                                                   _lib.ptr(packed), _lib.ptr(v[0]), epilogue, _lib.ptr(v[1]), _lib.ptr(v[2]), eps,
+                                                   _lib.ptr(packed), _lib.ptr(image), _lib.ptr(v[0]), epilogue, _lib.ptr(v[1]), _lib.ptr(v[2]), eps,
                                                    _lib.ptr(C), C.stride(0), _lib.stream_ptr()))
     return C
 
@@ -274,7 +284,8 @@ def spatial_attention_prepack(Vs: torch.Tensor) -> torch.Tensor:
     P = (n + 63) // 64 * 64
     W = torch.zeros(P, P, device=Vs.device, dtype=torch.float32)
     W[:n, :n] = Vs.detach().t()
-    return gemm_prepack(W)
+    packed = gemm_prepack(W)
+    return packed, _weight_image(packed, P, P // 64)
 
 
 def spatial_attention(lhs: torch.Tensor, rhs: torch.Tensor, bsT: torch.Tensor, vsT_packed: torch.Tensor) -> torch.Tensor:
@@ -283,9 +294,10 @@ def spatial_attention(lhs: torch.Tensor, rhs: torch.Tensor, bsT: torch.Tensor, v
     B, n, T = lhs.shape
     P = (n + 63) // 64 * 64
     st = torch.empty((B, n, P), dtype=torch.float32, device=lhs.device)
+    packed, image = vsT_packed if isinstance(vsT_packed, tuple) else (vsT_packed, None)
     with torch.cuda.device(lhs.device):
-        _lib.check(_lib.lib().stmp_spatial_attention_fwd(B, n, T, _lib.ptr(lhs), _lib.ptr(rhs), _lib.ptr(bsT), _lib.ptr(vsT_packed),
-                                                         _lib.ptr(st), P, _lib.stream_ptr()))
+        _lib.check(_lib.lib().stmp_spatial_attention_fwd(B, n, T, _lib.ptr(lhs), _lib.ptr(rhs), _lib.ptr(bsT), _lib.ptr(packed),
+                                                         _lib.ptr(image), _lib.ptr(st), P, _lib.stream_ptr()))
     return st
 
 

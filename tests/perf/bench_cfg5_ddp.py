@@ -94,7 +94,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item()) / args.steps
     if rank == 0:
-        pc = {k: v for k, v in _lib.path_counters().items() if v and k in ("k_gemm_split", "k_lstm_gate_bwd", "k_spmm", "k_spmm_pre")}
+        pc = {k: v for k, v in _lib.path_counters().items() if v and k in ("k_gemm_split", "k_lstm_gate_bwd", "k_spmm")}
         print(json.dumps({"config": f"cfg5 GConvLSTM(64,64,K=3) training, {N} nodes / {args.edges} edges, {args.windows} windows x 12 steps per GPU, "
                                     f"index-batched DDP, resident series {args.t_total}x{N}x64",
                           "n_gpus": world, "ms_per_step": ms, "snapshots_per_s": world * args.windows / (ms * 1e-3), "loss": float(loss),

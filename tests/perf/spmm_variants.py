@@ -21,7 +21,7 @@ def main():
     for (B, F) in ((32, 128), (32, 64), (96, 64), (8, 384)):
         x = torch.randn(B, 10000, F, device=dev)
         ref = None
-        for v in (0, 3, 5, 6):
+        for v in (0, 1, 2):
             _lib.set_option("spmm_variant", v)
             y = torch.empty_like(x)
             for _ in range(3):

@@ -33,7 +33,7 @@ with torch.no_grad():
     eg, wg = synthetic.large_graph(2000, 20000, 0)
     eg, wg = torch.from_numpy(eg).to(dev), torch.from_numpy(wg).to(dev)
     lstm = GConvLSTM(64, 64, 3).to(dev)
-    lstm(torch.randn(2000, 64, device=dev), eg, wg)              # k_spmm_pre + k_gemm_split<LSTM epilogue>
+    lstm(torch.randn(2000, 64, device=dev), eg, wg)              # k_spmm + k_gemm_split<LSTM epilogue>
 x = torch.randn(2, 2000, 64, device=dev, requires_grad=True)
 h, c = lstm(x, eg, wg)
 (h.sum() + c.sum()).backward()                                   # _LstmCellFn backward: k_gemm_split, k_lstm_gate_bwd, transposed SpMM
