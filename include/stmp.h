@@ -294,6 +294,13 @@ int stmp_gemm_blocks_f32(int64_t M, int64_t N, int64_t ncols, int64_t nblk, cons
                          const float* bias, int epilogue, const float* gamma, const float* beta, float eps, float* C, int64_t ldc, void* stream);
 int stmp_spatial_attention_fwd(int64_t B, int64_t n_nodes, int64_t n_steps, const float* lhs, const float* rhs, const float* bsT,
                                const void* vsT_packed, const void* vsT_image, float* st_out, int64_t ld_out, void* stream);
+/* The small-matrix front of an ASTGCN block in one launch (astgcn.py:311-328 temporal attention, :427-430 X~ = X E, :245-256 the spatial
+ * attention factors): x [B][nodes][T][F] channels-last; TemporalAttention parameters U1 [nodes], U2 [F][nodes], U3 [F], be [T][T],
+ * Ve [T][T]; SpatialAttention parameters W1 [T], W2 [F][T], W3 [F]  ->  lhs_s [B][nodes][T] = (X~ W1) W2, rhs_s [B][T][nodes] = (W3 X~)^T
+ * (the inputs of stmp_spatial_attention_fwd) and optionally E [B][T][T].  X~ is never materialised.  T <= 12, F in {1,2,4,...,64}. */
+int stmp_astgcn_factors_fwd(int64_t B, int64_t n_nodes, int64_t n_steps, int64_t f_in, const float* x, const float* U1, const float* U2,
+                            const float* U3, const float* be, const float* Ve, const float* W1, const float* W2, const float* W3,
+                            float* lhs_s, float* rhs_s, float* E_out, void* stream);
 int64_t stmp_gemm_blocks_image_bytes(int64_t N, int64_t nblk);
 int stmp_gemm_blocks_image(const void* packed, int64_t N, int64_t nblk, void* image, void* stream);
 

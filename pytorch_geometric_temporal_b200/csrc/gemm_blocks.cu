@@ -63,7 +63,8 @@ struct GbParams {
 __device__ __forceinline__ float sigmoid_g(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 
 template <int EPI>
-__global__ void __launch_bounds__(GB_NT, 1) k_gemm_blocks(const GbParams p) {
+__global__ void __launch_bounds__(GB_NT, EPI == EPI_SOFTMAX ? 1 : 2) k_gemm_blocks(const GbParams p) {
+  constexpr bool SPATT = EPI == EPI_SOFTMAX;         // spatial attention: generated A operand + row-softmax epilogue
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int N = p.N;
@@ -86,27 +87,67 @@ __global__ void __launch_bounds__(GB_NT, 1) k_gemm_blocks(const GbParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const long long m0 = (long long)blockIdx.x * GB_BM;
+  // row tiles: plain GEMMs tile M; spatial attention tiles every batch element separately (ceil(Nn/128) tiles each), so all rows of
+  // a tile share their batch index (warp-uniform LHS addresses, no divergence at batch boundaries)
+  const int sp_tiles = SPATT ? (p.Nn + GB_BM - 1) / GB_BM : 1;
+  const int sp_bt = SPATT ? (int)(blockIdx.x / sp_tiles) : 0;                       // batch element of this tile
+  const int sp_j0 = SPATT ? (int)(blockIdx.x % sp_tiles) * GB_BM : 0;              // first node of this tile
+  const long long m0 = SPATT ? (long long)sp_bt * p.Nn + sp_j0 : (long long)blockIdx.x * GB_BM;
+  const int rows_here = SPATT ? min(GB_BM, p.Nn - sp_j0) : (int)min((long long)GB_BM, (long long)p.M - m0);
   const int nkb = p.nblk, Kpad = p.nblk * 64;
   const int nh = N > 256 ? 2 : 1, Nh = N / nh;        // MMA column halves
   const uint32_t idesc = umma_idesc_f16(128, Nh);
 
   // MODE_SPATT register tile: thread = 4 consecutive rows (b, j..j+3) x 8 k of every k-block.  RHS columns of my rows live in
-  // registers for the whole tile; LHS rows are warp-uniform addresses (a warp shares k): broadcast 16-byte loads out of L1.
+  // registers for the whole tile; LHS rows are warp-uniform addresses (a warp shares k and the tile shares b): broadcast 16-byte loads.
   float rj[4][12];
-  int sp_b[4], sp_j[4];
+  int sp_j[4];
   const int sp_r0 = (tid & 31) * 4, sp_k8 = (tid >> 5) * 8;
-  if (p.spatt) {
+  if (SPATT) {
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-      const long long m = m0 + sp_r0 + r;
-      const long long mm = m < p.M ? m : p.M - 1;
-      sp_b[r] = (int)(mm / p.Nn);
-      sp_j[r] = (int)(mm - (long long)sp_b[r] * p.Nn);
+      const int jr = sp_j0 + sp_r0 + r;
+      sp_j[r] = jr < p.Nn ? jr : p.Nn - 1;
 #pragma unroll
-      for (int t = 0; t < 12; ++t) rj[r][t] = t < p.Tn ? __ldg(p.rhs + ((long long)sp_b[r] * p.Tn + t) * p.Nn + sp_j[r]) : 0.f;
+      for (int t = 0; t < 12; ++t) rj[r][t] = t < p.Tn ? __ldg(p.rhs + ((long long)sp_bt * p.Tn + t) * p.Nn + sp_j[r]) : 0.f;
     }
   }
+
+  // my 8 (row, 16-byte column) slots of an A tile are the same for every k-block: position of each row inside its sequence once
+  // (one 64-bit modulo per slot per CTA instead of one per slot per k-block: it was 22 % of the issued instructions)
+  float4 av[SPATT ? 1 : 8];
+  int tseq[SPATT ? 1 : 8];
+  if (!SPATT) {
+#pragma unroll
+    for (int jj = 0; jj < (SPATT ? 1 : 8); ++jj) {
+      const int r = (tid + jj * GB_NT) >> 4;
+      tseq[jj] = r < rows_here ? (int)((m0 + r) % p.seq) : -(1 << 20);      // rows past the end never fall inside a sequence
+    }
+  }
+  auto load_a = [&](int kb, float4 (&v)[SPATT ? 1 : 8]) {
+    if (SPATT) return;
+    const KBlock blk = p.blk[kb];
+    const bool vec = (blk.width % 4 == 0) && (blk.ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(blk.ptr) & 15) == 0);
+    const float* base = blk.ptr + (m0 + blk.shift) * blk.ld;
+#pragma unroll
+    for (int jj = 0; jj < (SPATT ? 1 : 8); ++jj) {
+      const int idx = tid + jj * GB_NT;
+      const int r = idx >> 4, k = 4 * (idx & 15);
+      v[jj] = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int tt = tseq[jj] + blk.shift;
+      if (k < blk.width && tt >= 0 && tt < p.seq) {
+        const float* src = base + (long long)r * blk.ld + k;
+        if (vec) {
+          v[jj] = __ldg(reinterpret_cast<const float4*>(src));
+        } else {
+          v[jj].x = __ldg(src);
+          if (k + 1 < blk.width) v[jj].y = __ldg(src + 1);
+          if (k + 2 < blk.width) v[jj].z = __ldg(src + 2);
+          if (k + 3 < blk.width) v[jj].w = __ldg(src + 3);
+        }
+      }
+    }
+  };
 
   for (int kb = 0; kb < nkb; ++kb) {
     const int s = kb & 1;
@@ -123,91 +164,59 @@ __global__ void __launch_bounds__(GB_NT, 1) k_gemm_blocks(const GbParams p) {
       mbar_arrive_expect_tx(&bars[2 + s], 2u * (uint32_t)b_bytes);
       tma_bulk_g2s(b_hi, p.w_img + (size_t)kb * 2 * b_bytes, 2u * (uint32_t)b_bytes, &bars[2 + s]);
     }
-    if (!p.spatt) {
-      // A: 128 x 64 fp32 of block kb (row-shifted, zero outside the sequence / beyond `width`) -> hi/lo fp16, swizzled.
-      const KBlock blk = p.blk[kb];
-      const bool vec = (blk.width % 4 == 0) && (blk.ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(blk.ptr) & 15) == 0);
-      float4 v[8];
+    if (!SPATT) {
+      // A: 128 x 64 fp32 of block kb (row-shifted, zero outside the sequence / beyond `width`) -> hi/lo fp16, swizzled.  The loads of
+      // block kb+1 are issued (into registers) before this block's barrier and MMAs, so a k-block does not cost a full HBM round trip.
+      if (kb == 0) load_a(0, av);
 #pragma unroll
       for (int jj = 0; jj < 8; ++jj) {
         const int idx = tid + jj * GB_NT;
-        const int r = idx >> 4, c4 = idx & 15;
-        const long long row = m0 + r;
-        const int k = 4 * c4;
-        v[jj] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (row < p.M && k < blk.width) {
-          const int tt = (int)(row % p.seq) + blk.shift;
-          if (tt >= 0 && tt < p.seq) {
-            const float* src = blk.ptr + (row + blk.shift) * blk.ld + k;
-            if (vec) {
-              v[jj] = __ldg(reinterpret_cast<const float4*>(src));
-            } else {
-              v[jj].x = __ldg(src);
-              if (k + 1 < blk.width) v[jj].y = __ldg(src + 1);
-              if (k + 2 < blk.width) v[jj].z = __ldg(src + 2);
-              if (k + 3 < blk.width) v[jj].w = __ldg(src + 3);
-            }
-          }
-        }
+        store_split4(a_hi, a_lo, idx >> 4, 4 * (idx & 15), av[jj]);
       }
-#pragma unroll
-      for (int jj = 0; jj < 8; ++jj) {
-        const int idx = tid + jj * GB_NT;
-        store_split4(a_hi, a_lo, idx >> 4, 4 * (idx & 15), v[jj]);
-      }
+      if (kb + 1 < nkb) load_a(kb + 1, av);
     } else {
-      // A generated: A[(b,j)][k] = sigmoid(sum_t LHS[b,k,t] RHS[b,t,j] + bsT[j][k])
+      // A generated: A[(b,j)][k] = sigmoid(sum_t LHS[b,k,t] RHS[b,t,j] + bsT[j][k]).  The 32 bs values of the thread are requested
+      // first so that their (row-strided, uncoalesced) loads are in flight under the FMA loops.
       const int Tn = p.Tn;
       float o[4][8];
-      const bool uni = sp_b[0] == sp_b[3];             // all four rows in one batch element (always, except across a batch boundary)
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const int k = k0 + sp_k8 + e;
-        const bool kv = k < p.Nn;
-        if (uni) {
-          float l[12];
-#pragma unroll
-          for (int t = 0; t < 12; ++t) l[t] = 0.f;
-          if (kv) {
-            const float* lk = p.lhs + ((long long)sp_b[0] * p.Nn + k) * Tn;
-            if (Tn == 12) {                              // 48-byte rows: three 16-byte broadcast loads
-#pragma unroll
-              for (int q4 = 0; q4 < 3; ++q4) {
-                const float4 v4 = __ldg(reinterpret_cast<const float4*>(lk) + q4);
-                l[4 * q4] = v4.x; l[4 * q4 + 1] = v4.y; l[4 * q4 + 2] = v4.z; l[4 * q4 + 3] = v4.w;
-              }
-            } else {
-#pragma unroll
-              for (int t = 0; t < 12; ++t)
-                if (t < Tn) l[t] = __ldg(lk + t);
-            }
-          }
-#pragma unroll
-          for (int r = 0; r < 4; ++r) {
-            float acc = 0.f;
-#pragma unroll
-            for (int t = 0; t < 12; ++t) acc = fmaf(l[t], rj[r][t], acc);
-            o[r][e] = acc;
-          }
-        } else {
-#pragma unroll
-          for (int r = 0; r < 4; ++r) {
-            float acc = 0.f;
-            if (kv) {
-              const float* lk = p.lhs + ((long long)sp_b[r] * p.Nn + k) * Tn;
-#pragma unroll
-              for (int t = 0; t < 12; ++t)
-                if (t < Tn) acc = fmaf(__ldg(lk + t), rj[r][t], acc);
-            }
-            o[r][e] = acc;
-          }
-        }
-      }
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
         const float* bsr = p.bsT + (long long)sp_j[r] * p.Nn + k0 + sp_k8;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) o[r][e] = (k0 + sp_k8 + e < p.Nn) ? sigmoid_g(o[r][e] + __ldg(bsr + e)) : 0.f;
+        for (int e = 0; e < 8; ++e) o[r][e] = (k0 + sp_k8 + e < p.Nn) ? __ldg(bsr + e) : 0.f;
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int k = k0 + sp_k8 + e;
+        float l[12];
+#pragma unroll
+        for (int t = 0; t < 12; ++t) l[t] = 0.f;
+        if (k < p.Nn) {
+          const float* lk = p.lhs + ((long long)sp_bt * p.Nn + k) * Tn;
+          if (Tn == 12) {                              // 48-byte rows: three 16-byte broadcast loads
+#pragma unroll
+            for (int q4 = 0; q4 < 3; ++q4) {
+              const float4 v4 = __ldg(reinterpret_cast<const float4*>(lk) + q4);
+              l[4 * q4] = v4.x; l[4 * q4 + 1] = v4.y; l[4 * q4 + 2] = v4.z; l[4 * q4 + 3] = v4.w;
+            }
+          } else {
+#pragma unroll
+            for (int t = 0; t < 12; ++t)
+              if (t < Tn) l[t] = __ldg(lk + t);
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          float acc = o[r][e];
+#pragma unroll
+          for (int t = 0; t < 12; ++t) acc = fmaf(l[t], rj[r][t], acc);
+          o[r][e] = acc;
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[r][e] = (k0 + sp_k8 + e < p.Nn) ? sigmoid_g(o[r][e]) : 0.f;
         store_split4(a_hi, a_lo, sp_r0 + r, sp_k8, make_float4(o[r][0], o[r][1], o[r][2], o[r][3]));
         store_split4(a_hi, a_lo, sp_r0 + r, sp_k8 + 4, make_float4(o[r][4], o[r][5], o[r][6], o[r][7]));
       }
@@ -264,7 +273,7 @@ __global__ void __launch_bounds__(GB_NT, 1) k_gemm_blocks(const GbParams p) {
   // ---- epilogue: TMEM lane == row ----------------------------------------------------------------------------------------
   const int q = warp & 3, half = warp >> 2;
   const long long row = m0 + q * 32 + lane;
-  const bool live = row < p.M;
+  const bool live = (q * 32 + lane) < rows_here;
   const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
   if (EPI == EPI_BIAS || EPI == EPI_RELU) {
     // warps 0-3 / 4-7 split the 16-column chunks
@@ -300,33 +309,49 @@ __global__ void __launch_bounds__(GB_NT, 1) k_gemm_blocks(const GbParams p) {
   } else if (EPI == EPI_RELU_LN) {
     // y = LayerNorm(relu(acc + bias)) over the row's 64 columns (torch: biased variance, eps inside the sqrt); warps 0-3 own the rows
     if (half == 0) {
-      float x[64];
+      // pass 1: mean and (two-pass) variance straight from TMEM; pass 2: normalise and store -- 16 values live at a time, so the
+      // kernel fits two CTAs per SM
+      float mean = 0.f;
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch) {
         uint32_t v[16];
         tmem_ld16(trow + 16 * ch, v);
         tmem_ld_wait();
 #pragma unroll
-        for (int jj = 0; jj < 16; ++jj) x[16 * ch + jj] = fmaxf(__uint_as_float(v[jj]) + (p.bias ? __ldg(p.bias + 16 * ch + jj) : 0.f), 0.f);
+        for (int jj = 0; jj < 16; ++jj) mean += fmaxf(__uint_as_float(v[jj]) + (p.bias ? __ldg(p.bias + 16 * ch + jj) : 0.f), 0.f);
       }
-      float mean = 0.f;
-#pragma unroll
-      for (int c = 0; c < 64; ++c) mean += x[c];
       mean *= (1.0f / 64.0f);
       float var = 0.f;
 #pragma unroll
-      for (int c = 0; c < 64; ++c) { const float d = x[c] - mean; var = fmaf(d, d, var); }
-      const float rstd = rsqrtf(var * (1.0f / 64.0f) + p.eps);
-      if (live) {
-        float* dst = p.C + row * p.ldc;
+      for (int ch = 0; ch < 4; ++ch) {
+        uint32_t v[16];
+        tmem_ld16(trow + 16 * ch, v);
+        tmem_ld_wait();
 #pragma unroll
-        for (int c = 0; c < 64; c += 4) {
-          float4 o;
-          o.x = (x[c] - mean) * rstd * __ldg(p.gamma + c) + __ldg(p.beta + c);
-          o.y = (x[c + 1] - mean) * rstd * __ldg(p.gamma + c + 1) + __ldg(p.beta + c + 1);
-          o.z = (x[c + 2] - mean) * rstd * __ldg(p.gamma + c + 2) + __ldg(p.beta + c + 2);
-          o.w = (x[c + 3] - mean) * rstd * __ldg(p.gamma + c + 3) + __ldg(p.beta + c + 3);
-          *reinterpret_cast<float4*>(dst + c) = o;
+        for (int jj = 0; jj < 16; ++jj) {
+          const float d = fmaxf(__uint_as_float(v[jj]) + (p.bias ? __ldg(p.bias + 16 * ch + jj) : 0.f), 0.f) - mean;
+          var = fmaf(d, d, var);
+        }
+      }
+      const float rstd = rsqrtf(var * (1.0f / 64.0f) + p.eps);
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+        uint32_t v[16];
+        tmem_ld16(trow + 16 * ch, v);
+        tmem_ld_wait();
+        if (live) {
+          float* dst = p.C + row * p.ldc + 16 * ch;
+#pragma unroll
+          for (int c = 0; c < 16; c += 4) {
+            float o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int cc = 16 * ch + c + e;
+              const float xv = fmaxf(__uint_as_float(v[c + e]) + (p.bias ? __ldg(p.bias + cc) : 0.f), 0.f);
+              o[e] = (xv - mean) * rstd * __ldg(p.gamma + cc) + __ldg(p.beta + cc);
+            }
+            *reinterpret_cast<float4*>(dst + c) = make_float4(o[0], o[1], o[2], o[3]);
+          }
         }
       }
     }
@@ -400,7 +425,7 @@ int gb_launch(GbParams& p, cudaStream_t st) {
   const int smem = 2 * (2 * GB_A_BYTES + 2 * p.N * 128) + 48 + 256 * 4;
   if (smem > 232448) return set_error(STMP_EUNSUPPORTED, "blocked GEMM: N=%d needs %d B of shared memory", p.N, smem);
   STMP_CUDA_OK(cudaFuncSetAttribute(k_gemm_blocks<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  const unsigned grid = (unsigned)((p.M + GB_BM - 1) / GB_BM);
+  const unsigned grid = EPI == EPI_SOFTMAX ? (unsigned)((p.M / p.Nn) * ((p.Nn + GB_BM - 1) / GB_BM)) : (unsigned)((p.M + GB_BM - 1) / GB_BM);
   k_gemm_blocks<EPI><<<grid, GB_NT, smem, st>>>(p);
   STMP_LAUNCH_OK("k_gemm_blocks");
   return STMP_OK;

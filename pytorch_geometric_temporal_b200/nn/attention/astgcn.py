@@ -15,8 +15,9 @@ What runs where
   (B, N, T, F) between blocks and runs every large product on tcgen05 with its neighbours fused (csrc/gemm_blocks.cu):
   spatial attention `softmax(Vs @ sigmoid(LHS @ RHS + bs))` in ONE kernel (the N x N sigmoid is generated in the operand
   stage, the softmax is the epilogue; the result is kept transposed and consumed so by `stmp_spmm_att_t`); the Chebyshev
-  contraction + ReLU; time convolution + residual convolution + ReLU + LayerNorm; the final convolution.  No im2col, cat
-  or permute of activations in HBM.  Only the T x T temporal attention and the (B,N,T) attention factors stay on torch;
+  contraction + ReLU; time convolution + residual convolution + ReLU + LayerNorm; the final convolution; and the small-matrix
+  front (temporal attention, X~ = X E, the (B,N,T) attention factors) in one launch (`stmp_astgcn_factors_fwd`).  No
+  im2col, cat or permute of activations in HBM;
 * training (autograd) and the per-timestep edge_index list path use the op-for-op torch formulation around `stmp_spmm`
   (dense products on cuBLAS through torch).
 * lambda_max for normalization != "sym": the reference calls scipy ARPACK on the host in EVERY block
@@ -241,14 +242,17 @@ class ASTGCNBlock(nn.Module):
         B, N, T, Fi = Xc.shape
         ta, sa, cc = self._temporal_attention, self._spatial_attention, self._chebconv_attention
         pk = self._native_packs()
-        # temporal attention (astgcn.py:311-328): T x T per batch row -- tiny, stays on torch
-        lhs = torch.matmul(torch.einsum("bntf,n->btf", Xc, ta._U1), ta._U2)                # (B,T,N)
-        rhs = torch.einsum("bntf,f->bnt", Xc, ta._U3)                                       # (B,N,T)
-        E = F.softmax(torch.matmul(ta._Ve, torch.sigmoid(torch.matmul(lhs, rhs) + ta._be)), dim=1)
-        Xt = torch.einsum("bntf,btu->bnuf", Xc, E)                                          # X~ channels-last (:427-430)
-        # spatial attention factors (:245-256), then the fused N x N kernel; ST[b, j, i] = S[b, i, j]
-        lhs_s = torch.matmul(torch.einsum("bnuf,u->bnf", Xt, sa._W1), sa._W2)               # (B,N,T)
-        rhs_s = torch.einsum("bnuf,f->bun", Xt, sa._W3).contiguous()                        # (B,T,N)
+        # temporal attention (astgcn.py:311-328), X~ = X E (:427-430) and the spatial-attention factors (:245-256): one launch
+        try:
+            lhs_s, rhs_s = ops.astgcn_factors(Xc, ta._U1, ta._U2, ta._U3, ta._be, ta._Ve, sa._W1, sa._W2, sa._W3)
+        except _lib.StmpUnsupported:         # odd channel counts: the same algebra on torch
+            lhs = torch.matmul(torch.einsum("bntf,n->btf", Xc, ta._U1), ta._U2)                # (B,T,N)
+            rhs = torch.einsum("bntf,f->bnt", Xc, ta._U3)                                       # (B,N,T)
+            E = F.softmax(torch.matmul(ta._Ve, torch.sigmoid(torch.matmul(lhs, rhs) + ta._be)), dim=1)
+            Xt = torch.einsum("bntf,btu->bnuf", Xc, E)                                          # X~ channels-last
+            lhs_s = torch.matmul(torch.einsum("bnuf,u->bnf", Xt, sa._W1), sa._W2)               # (B,N,T)
+            rhs_s = torch.einsum("bnuf,f->bun", Xt, sa._W3).contiguous()                        # (B,T,N)
+        # the fused N x N kernel; ST[b, j, i] = S[b, i, j]
         ST = ops.spatial_attention(lhs_s, rhs_s, pk["bsT"], pk["vsT"])
         # ChebConvAttention over all T timesteps at once (:141-183): T_0 = diag(S) x, T_1 = (norm * S) T_0, T_k = 2 L T_{k-1} - T_{k-2}
         lam = self._lambda_max(edge_index, N)

@@ -278,6 +278,21 @@ def gemm_blocks(blocks, packed: torch.Tensor, N: int, ncols: int, bias: Optional
     return C
 
 
+def astgcn_factors(Xc, U1, U2, U3, be, Ve, W1, W2, W3, want_E: bool = False):
+    """(lhs_s (B,N,T), rhs_s (B,T,N) [, E (B,T,T)]) of an ASTGCN block from channels-last X (B,N,T,F): temporal attention, X~ = X E and
+    the spatial-attention factors in one launch (stmp_astgcn_factors_fwd)."""
+    Xc = _f32c(Xc, "X")
+    B, N, T, Fi = Xc.shape
+    lhs = torch.empty((B, N, T), dtype=torch.float32, device=Xc.device)
+    rhs = torch.empty((B, T, N), dtype=torch.float32, device=Xc.device)
+    E = torch.empty((B, T, T), dtype=torch.float32, device=Xc.device) if want_E else None
+    v = [_f32c(t.detach(), "param") for t in (U1, U2, U3, be.reshape(T, T), Ve, W1, W2, W3)]
+    with torch.cuda.device(Xc.device):
+        _lib.check(_lib.lib().stmp_astgcn_factors_fwd(B, N, T, Fi, _lib.ptr(Xc), *[_lib.ptr(t) for t in v], _lib.ptr(lhs), _lib.ptr(rhs),
+                                                      _lib.ptr(E), _lib.stream_ptr()))
+    return (lhs, rhs, E) if want_E else (lhs, rhs)
+
+
 def spatial_attention_prepack(Vs: torch.Tensor) -> torch.Tensor:
     """Vs (N,N) -> packed fp16 hi/lo of Vs^T zero-padded to (P,P), P = N rounded up to 64."""
     n = Vs.size(0)

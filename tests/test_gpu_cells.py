@@ -220,6 +220,7 @@ def test_astgcn_config4_shape_vs_reference_golden(golden_dir):
         with torch.no_grad():
             out = m(c["X"].to(DEV), ei)
         assert _ran(c0, "k_gemm_blocks") == 3 * 3 + 1       # per block: spatial attention, Chebyshev contraction, time conv; + final conv
+        assert _ran(c0, "k_astgcn_factors") == 3
         assert _ran(c0, "k_spmm") == 6           # per block: attention-weighted hop + plain hop
         _close(out, c["out"])
         # the op-for-op torch path (what training uses) agrees as well
@@ -241,6 +242,35 @@ def test_spatial_attention_kernel_vs_fp64():
         err, err32 = (got.double() - S).abs().max().item(), (S32.double() - S).abs().max().item()
         assert err < 4 * err32 + 1e-7, (n, err, err32)
         assert torch.all(ST[:, :, n:] == 0)
+
+
+def test_astgcn_factors_kernel_vs_torch_fp64():
+    """stmp_astgcn_factors_fwd: temporal attention + X~ + spatial factors for F = 64 (vector path) and F = 1 (first block)."""
+    from pytorch_geometric_temporal_b200 import ops
+    for (B, N, T, Fi) in ((3, 307, 12, 64), (2, 307, 12, 1), (2, 50, 7, 8)):
+        g = torch.Generator().manual_seed(N + Fi)
+        r = lambda *s: torch.randn(*s, generator=g)
+        X = r(B, N, T, Fi) * 0.7
+        U1, U2, U3, be, Ve = r(N) * 0.1, r(Fi, N) * 0.2, r(Fi) * 0.5, r(1, T, T) * 0.3, r(T, T) * 0.5
+        W1, W2, W3 = r(T) * 0.4, r(Fi, T) * 0.3, r(Fi) * 0.5
+        d = lambda t: t.double()
+        Xr = d(X).permute(0, 1, 3, 2)                                        # reference layout (B,N,F,T)
+        lhs = torch.matmul(torch.matmul(Xr.permute(0, 3, 2, 1), d(U1)), d(U2))
+        rhs = torch.matmul(d(U3), Xr)
+        E = torch.softmax(torch.matmul(d(Ve), torch.sigmoid(torch.matmul(lhs, rhs) + d(be))), dim=1)
+        Xt = torch.matmul(Xr.reshape(B, -1, T), E).reshape(B, N, Fi, T)
+        want_l = torch.matmul(torch.matmul(Xt, d(W1)), d(W2))
+        want_r = torch.matmul(d(W3), Xt).transpose(-1, -2)
+        gl, gr, gE = ops.astgcn_factors(*(t.to(DEV) for t in (X, U1, U2, U3, be, Ve, W1, W2, W3)), want_E=True)
+        # yardstick: the same chain in torch fp32 (the reference's arithmetic) against float64
+        Xf = X.permute(0, 1, 3, 2)
+        lhs32 = torch.matmul(torch.matmul(Xf.permute(0, 3, 2, 1), U1), U2)
+        E32 = torch.softmax(torch.matmul(Ve, torch.sigmoid(torch.matmul(lhs32, torch.matmul(U3, Xf)) + be)), dim=1)
+        Xt32 = torch.matmul(Xf.reshape(B, -1, T), E32).reshape(B, N, Fi, T)
+        l32, r32 = torch.matmul(torch.matmul(Xt32, W1), W2), torch.matmul(W3, Xt32).transpose(-1, -2)
+        for got, want, ref32 in ((gl, want_l, l32), (gr, want_r, r32), (gE, E, E32)):
+            err, err32 = (got.cpu().double() - want).abs().max().item(), (ref32.double() - want).abs().max().item()
+            assert err < 4 * err32 + 2e-6, (err, err32)
 
 
 def test_gemm_blocks_shift_ln_epilogues_vs_torch():
