@@ -102,19 +102,41 @@ __global__ void __launch_bounds__(FA_NT) k_astgcn_factors(const FactorArgs a) {
   }
   __syncthreads();
   // ---- LHS[t][n] = sum_f lhs1[t][f] U2[f][n] ----------------------------------------------------------------------------
-  for (int idx = tid; idx < T * N; idx += FA_NT) {
-    const int t = idx / N, n = idx - t * N;
-    float s = 0.f;
-    for (int f = 0; f < F; ++f) s = fmaf(lhs1[t * F + f], __ldg(a.U2 + (long long)f * N + n), s);
-    LHS[idx] = s;
+  // thread = node n: U2[f][n] is read once (coalesced over n, 8 loads in flight) and feeds all T rows; lhs1 is a shared-memory broadcast
+  for (int n = tid; n < N; n += FA_NT) {
+    float s[FA_TMAX];
+#pragma unroll
+    for (int t = 0; t < FA_TMAX; ++t) s[t] = 0.f;
+    for (int f0 = 0; f0 < F; f0 += 8) {
+      float u[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) u[j] = (f0 + j < F) ? __ldg(a.U2 + (long long)(f0 + j) * N + n) : 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (f0 + j < F) {
+#pragma unroll
+          for (int t = 0; t < FA_TMAX; ++t)
+            if (t < T) s[t] = fmaf(lhs1[t * F + f0 + j], u[j], s[t]);
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < FA_TMAX; ++t)
+      if (t < T) LHS[t * N + n] = s[t];
   }
   __syncthreads();
   // ---- prod = LHS @ Rt ; sigmoid(prod + be) ; E0 = Ve @ .. ; softmax over dim 1 (rows) ------------------------------------
   for (int idx = tid; idx < T * T; idx += FA_NT) {
     const int t = idx / T, u = idx - t * T;
-    float s = 0.f;
-    for (int n = 0; n < N; ++n) s = fmaf(LHS[t * N + n], Rt[n * T + u], s);
-    Em[idx] = sigmoid_a(s + __ldg(a.be + idx));
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int n = 0;
+    for (; n + 4 <= N; n += 4) {
+      s0 = fmaf(LHS[t * N + n], Rt[n * T + u], s0);
+      s1 = fmaf(LHS[t * N + n + 1], Rt[(n + 1) * T + u], s1);
+      s2 = fmaf(LHS[t * N + n + 2], Rt[(n + 2) * T + u], s2);
+      s3 = fmaf(LHS[t * N + n + 3], Rt[(n + 3) * T + u], s3);
+    }
+    for (; n < N; ++n) s0 = fmaf(LHS[t * N + n], Rt[n * T + u], s0);
+    Em[idx] = sigmoid_a((s0 + s1) + (s2 + s3) + __ldg(a.be + idx));
   }
   __syncthreads();
   for (int idx = tid; idx < T * T; idx += FA_NT) {
