@@ -137,7 +137,7 @@ int stmp_dcrnn_seq_fwd(const stmp_plan* plan, int64_t B, int64_t T, int64_t cin,
                        const float* x, const int64_t* win_start, int64_t x_bstride, int64_t x_tstride,
                        const float* w_z, const float* w_r, const float* w_h, const float* b_z,
                        const float* b_r, const float* b_h, const float* h0, float* out, float* stash,
-                       const void* wimage, void* stream);
+                       const void* wimage, void* workspace, void* stream);
 /* 1 if stmp_dcrnn_seq_fwd can take this configuration on the current device, else 0. */
 int stmp_dcrnn_seq_supported(const stmp_plan* plan, int64_t cin, int64_t cout, int64_t K);
 
@@ -153,12 +153,17 @@ int stmp_dcrnn_seq_supported(const stmp_plan* plan, int64_t cin, int64_t cout, i
 int stmp_gru_seq_fwd(const stmp_plan* plan, int n_ops, int64_t B, int64_t T, int64_t cin, const float* x,
                      const int64_t* win_start, int64_t x_bstride, int64_t x_tstride, const float* wcat,
                      const float* bcat, const float* h0, int64_t h0_bstride, float* out, float* stash,
-                     const void* wimage, void* stream);
+                     const void* wimage, void* workspace, void* stream);
 /* Optional weight image for the tcgen05 kernel: the B operand (fp16 hi/lo halves, SWIZZLE_128B, + biases) exactly as the kernel
  * holds it in shared memory, so every CTA fetches it with one TMA bulk copy instead of converting the fp32 weights itself.
  * Build it once per weight update into a device buffer of stmp_gru_weight_image_bytes() bytes and pass it as `wimage`
  * (NULL => the kernel converts in place).  The plan carries the analogous graph image. */
 int64_t stmp_gru_weight_image_bytes(void);
+/* Optional workspace of the tcgen05 kernel (both entries): stmp_seq_workspace_bytes(plan, T, cin) bytes of device memory, reusable across
+ * calls on one stream.  The window prologue parks P_o X_t / P_i X_t of all steps there (per-CTA rows, rewritten every window => L2-resident,
+ * full-sector stores).  NULL => they are parked in the window's own not-yet-written output rows instead (same results; partial-sector
+ * writes cost extra DRAM traffic: 1.7x the algorithmic bytes measured). */
+int64_t stmp_seq_workspace_bytes(const stmp_plan* plan, int64_t T, int64_t cin);
 int stmp_dcrnn_pack_weights(int64_t cin, int64_t cout, int64_t K, const float* w_z, const float* w_r, const float* w_h,
                             const float* b_z, const float* b_r, const float* b_h, void* image, void* stream);
 int stmp_gru_pack_weights(const float* wcat, const float* bcat, void* image, void* stream);

@@ -8,7 +8,7 @@ import os
 from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_uint32, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libstmp.so")
+LIB_PATH = os.environ.get("STMP_LIB", os.path.join(_HERE, "lib", "libstmp.so"))   # STMP_LIB: A/B a second build of the library
 
 STMP_OK, STMP_EINVAL, STMP_ESHAPE, STMP_EGRAPH, STMP_ECUDA, STMP_EUNSUPPORTED, STMP_ENOMEM = range(7)
 FLAVOR_DCONV, FLAVOR_CHEB, FLAVOR_GCN, FLAVOR_CHEB_ATT = range(4)
@@ -46,9 +46,10 @@ _SIGNATURES = {
     "stmp_gemm_blocks_image": (c_int, [_P, c_int64, c_int64, _P, _P]),
     "stmp_spmm_att_grad": (c_int, [_P, c_int, c_int64, c_int64, _P, c_int64, c_int64, _P, c_int64, c_int64, _P, _P]),
     "stmp_dcrnn_seq_fwd": (c_int, [_P, c_int64, c_int64, c_int64, c_int64, c_int64, _P, _P, c_int64, c_int64,
-                                   _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+                                   _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "stmp_seq_workspace_bytes": (c_int64, [_P, c_int64, c_int64]),
     "stmp_dcrnn_seq_supported": (c_int, [_P, c_int64, c_int64, c_int64]),
-    "stmp_gru_seq_fwd": (c_int, [_P, c_int, c_int64, c_int64, c_int64, _P, _P, c_int64, c_int64, _P, _P, _P, c_int64, _P, _P, _P, _P]),
+    "stmp_gru_seq_fwd": (c_int, [_P, c_int, c_int64, c_int64, c_int64, _P, _P, c_int64, c_int64, _P, _P, _P, c_int64, _P, _P, _P, _P, _P]),
     "stmp_gru_weight_image_bytes": (c_int64, []),
     "stmp_dcrnn_pack_weights": (c_int, [c_int64, c_int64, c_int64, _P, _P, _P, _P, _P, _P, _P, _P]),
     "stmp_gru_pack_weights": (c_int, [_P, _P, _P, _P]),

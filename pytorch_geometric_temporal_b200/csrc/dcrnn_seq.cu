@@ -31,7 +31,7 @@ bool dcrnn_tc_supported(const stmp_plan* plan, long long cin, long long cout, lo
 int dcrnn_tc_launch(const stmp_plan* plan, long long B, long long T, long long cin, const float* x, const long long* win_start,
                     long long x_bstride, long long x_tstride, const float* w_z, const float* w_r, const float* w_h, const float* b_z,
                     const float* b_r, const float* b_h, const float* h0, float* out, float* stash, const void* wimage,
-                    cudaStream_t st);
+                    void* workspace, cudaStream_t st);
 int tc_pack_weight_image(const float* wcat, const float* bcat, const float* w0, const float* w1, const float* w2, const float* b0,
                          const float* b1, const float* b2, int cin, void* image, cudaStream_t st);
 int tc_weight_image_bytes();
@@ -39,7 +39,8 @@ int tc_weight_image_bytes();
 bool gru_tc_supported(const stmp_plan* plan, long long cin, int n_ops);
 int gru_tc_launch(const stmp_plan* plan, int n_ops, long long B, long long T, long long cin, const float* x, const long long* win_start,
                   long long x_bstride, long long x_tstride, const float* wcat, const float* bcat, const float* h0, long long h0_bstride,
-                  float* out, float* stash, const void* wimage, cudaStream_t st);
+                  float* out, float* stash, const void* wimage, void* workspace, cudaStream_t st);
+long long tc_workspace_bytes(const stmp_plan* plan, long long T, long long cin);
 
 int g_use_tc = -1;   // -1: read STMP_DCRNN_TC on first use
 
@@ -425,7 +426,7 @@ extern "C" int stmp_dcrnn_seq_fwd(const stmp_plan* plan, int64_t B, int64_t T, i
                                   const float* x, const int64_t* win_start, int64_t x_bstride, int64_t x_tstride,
                                   const float* w_z, const float* w_r, const float* w_h, const float* b_z,
                                   const float* b_r, const float* b_h, const float* h0, float* out, float* stash,
-                                  const void* wimage, void* stream) {
+                                  const void* wimage, void* workspace, void* stream) {
   STMP_REQUIRE(plan != nullptr, STMP_EINVAL, "stmp_dcrnn_seq_fwd: plan is NULL");
   STMP_REQUIRE(plan->flavor == STMP_FLAVOR_DCONV, STMP_EINVAL, "stmp_dcrnn_seq_fwd: plan is not a DConv plan");
   STMP_REQUIRE(B >= 0 && T >= 0, STMP_EINVAL, "stmp_dcrnn_seq_fwd: negative B/T");
@@ -442,7 +443,7 @@ extern "C" int stmp_dcrnn_seq_fwd(const stmp_plan* plan, int64_t B, int64_t T, i
     }
     if (g_use_tc && dcrnn_tc_supported(plan, cin, cout, K))
       return dcrnn_tc_launch(plan, B, T, cin, x, reinterpret_cast<const long long*>(win_start), x_bstride, x_tstride, w_z, w_r, w_h,
-                             b_z, b_r, b_h, h0, out, stash, wimage, (cudaStream_t)stream);
+                             b_z, b_r, b_h, h0, out, stash, wimage, workspace, (cudaStream_t)stream);
   }
   STMP_REQUIRE(T * (long long)plan->n * cin < (1ll << 24), STMP_ESHAPE, "window too long for the shared-memory X buffer");
   Layout L;
@@ -487,7 +488,7 @@ extern "C" int stmp_gru_seq_supported(const stmp_plan* plan, int n_ops, int64_t 
 extern "C" int stmp_gru_seq_fwd(const stmp_plan* plan, int n_ops, int64_t B, int64_t T, int64_t cin, const float* x,
                                 const int64_t* win_start, int64_t x_bstride, int64_t x_tstride, const float* wcat,
                                 const float* bcat, const float* h0, int64_t h0_bstride, float* out, float* stash,
-                                const void* wimage, void* stream) {
+                                const void* wimage, void* workspace, void* stream) {
   STMP_REQUIRE(plan != nullptr, STMP_EINVAL, "stmp_gru_seq_fwd: plan is NULL");
   STMP_REQUIRE(n_ops >= 0 && n_ops <= 2 && n_ops <= plan->n_ops, STMP_EINVAL, "stmp_gru_seq_fwd: n_ops=%d not available in this plan", n_ops);
   STMP_REQUIRE(B >= 0 && T >= 0, STMP_EINVAL, "stmp_gru_seq_fwd: negative B/T");
@@ -496,7 +497,7 @@ extern "C" int stmp_gru_seq_fwd(const stmp_plan* plan, int n_ops, int64_t B, int
     return set_error(STMP_EUNSUPPORTED, "fused graph-GRU kernel supports N<=207, cin<=4, cout=32 (got N=%d cin=%lld)", plan->n, (long long)cin);
   if (B == 0 || T == 0) return STMP_OK;
   return gru_tc_launch(plan, n_ops, B, T, cin, x, reinterpret_cast<const long long*>(win_start), x_bstride, x_tstride, wcat, bcat, h0,
-                       h0_bstride, out, stash, wimage, (cudaStream_t)stream);
+                       h0_bstride, out, stash, wimage, workspace, (cudaStream_t)stream);
 }
 
 /* Test hook: select the kernel family behind stmp_dcrnn_seq_fwd at run time ("dcrnn_tc": 1 tcgen05 / 0 FFMA), so the two
@@ -509,6 +510,9 @@ extern "C" int stmp_set_option(const char* name, int value) {
 }
 
 extern "C" int64_t stmp_gru_weight_image_bytes(void) { return tc_weight_image_bytes(); }
+extern "C" int64_t stmp_seq_workspace_bytes(const stmp_plan* plan, int64_t T, int64_t cin) {
+  return (plan && T > 0 && cin > 0) ? tc_workspace_bytes(plan, T, cin) : 0;
+}
 
 extern "C" int stmp_dcrnn_pack_weights(int64_t cin, int64_t cout, int64_t K, const float* w_z, const float* w_r, const float* w_h,
                                        const float* b_z, const float* b_r, const float* b_h, void* image, void* stream) {

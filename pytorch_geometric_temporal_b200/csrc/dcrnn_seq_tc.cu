@@ -60,6 +60,8 @@ struct TcParams {
   const void* wimage;     // prebuilt B-operand image (fp16 hi/lo, swizzled, + biases) or null
   float* out;
   float* stash;
+  float* ws;              // workspace [grid][N][2 operators][ws_pitch] for P_o X / P_i X of a window's steps, or null (park them in `out`)
+  int ws_pitch;
   int off_A, off_B, off_U, off_img, off_bias, off_bar;
 };
 
@@ -138,6 +140,7 @@ __device__ __forceinline__ float4 gather_groups(const float* __restrict__ Uj, co
   for (int g = 1; g <= ng; ++g) {
     const uint32_t un = idx4[g0 + g];      // (one spare group at the end of the arrays)
     const float4 vn = val4[g0 + g];
+    // (predicating the loads of pad entries off saves their wavefronts but costs more in compares / selects: measured -2 %, A/B on one box)
     const float4 x0 = ld4(Uj + (u & 0xffu) * TC_UP);
     const float4 x1 = ld4(Uj + ((u >> 8) & 0xffu) * TC_UP);
     const float4 x2 = ld4(Uj + ((u >> 16) & 0xffu) * TC_UP);
@@ -334,6 +337,18 @@ __global__ void __launch_bounds__(512, 1) k_dcrnn_seq_tc(const TcParams p) {
     for (int c = 0; c < CIN; ++c) xn[c] = __ldg(xb + t * p.x_tstride + row * CIN + c);
     xv = make_float4(xn[0], xn[1], xn[2], xn[3]);
     po = pi = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.ws) {             // per-CTA workspace rows [row][op][t*CIN + c]: rewritten every window, so they stay in L2
+      const float* w0 = p.ws + (((long long)blockIdx.x * N + row) * 2) * p.ws_pitch + t * CIN;
+      float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int c = 0; c < CIN; ++c) {
+        if (p.n_ops >= 1) a0[c] = w0[c];
+        if (p.n_ops >= 2) a1[c] = w0[p.ws_pitch + c];
+      }
+      po = make_float4(a0[0], a0[1], a0[2], a0[3]);
+      pi = make_float4(a1[0], a1[1], a1[2], a1[3]);
+      return;
+    }
     const float* sc = p.out + ((b * T + t) * (long long)N + row) * 32;   // parked there by the window prologue (plain loads:
     if (p.n_ops >= 1) po = *reinterpret_cast<const float4*>(sc);         //  written by this CTA earlier in this launch)
     if (p.n_ops >= 2) pi = *reinterpret_cast<const float4*>(sc + 4);
@@ -391,7 +406,16 @@ __global__ void __launch_bounds__(512, 1) k_dcrnn_seq_tc(const TcParams p) {
               const int drow = d & 0xff, op = (d >> 8) & 1;
               float* orow = p.out + ((b * T + t0) * (long long)N + drow) * 32 + op * 4;
               const long long tstep = (long long)N * 32;
-              if (CIN == 2) {           // floats 4j..4j+3 = (t, c) = (2j,0) (2j,1) (2j+1,0) (2j+1,1): two 8-byte stores
+              if (p.ws) {               // floats 4j..4j+3 of the row are consecutive (t, c) pairs: one 16-byte store, full sectors
+                float* wrow = p.ws + (((long long)blockIdx.x * N + drow) * 2 + op) * p.ws_pitch + t0 * CIN + 4 * j;
+                if (4 * j + 4 <= F) {
+                  *reinterpret_cast<float4*>(wrow) = acc;
+                } else {
+#pragma unroll
+                  for (int k = 0; k < 4; ++k)
+                    if (4 * j + k < F) wrow[k] = av[k];
+                }
+              } else if (CIN == 2) {           // floats 4j..4j+3 = (t, c) = (2j,0) (2j,1) (2j+1,0) (2j+1,1): two 8-byte stores
                 *reinterpret_cast<float2*>(orow + (2 * j) * tstep) = make_float2(av[0], av[1]);
                 if (4 * j + 2 < F) *reinterpret_cast<float2*>(orow + (2 * j + 1) * tstep) = make_float2(av[2], av[3]);
               } else if (CIN == 4) {    // one timestep per lane: a 16-byte store
@@ -542,6 +566,14 @@ bool tc_layout(const stmp_plan* plan, int n_ops, TcParams* p, int* smem_bytes) {
 
 }  // namespace
 
+int tc_ws_pitch(long long T, long long cin) { return (int)((T * cin + 7) / 8 * 8); }   // floats per (row, operator): whole 32-byte sectors
+
+long long tc_workspace_bytes(const stmp_plan* plan, long long T, long long cin) {
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return (long long)sms * plan->n * 2 * tc_ws_pitch(T, cin) * 4;
+}
+
 static bool tc_fits(const stmp_plan* plan, int n_ops) {
   if (!plan || plan->n > kImgMaxN || plan->n < 1) return false;
   if (n_ops > 0 && !plan->gimg[n_ops]) return false;      // no image: graph too large / too dense for the 8-bit format
@@ -566,26 +598,26 @@ static int tc_launch_params(const stmp_plan* plan, TcParams& p, cudaStream_t st)
 int dcrnn_tc_launch(const stmp_plan* plan, long long B, long long T, long long cin, const float* x, const long long* win_start,
                     long long x_bstride, long long x_tstride, const float* w_z, const float* w_r, const float* w_h, const float* b_z,
                     const float* b_r, const float* b_h, const float* h0, float* out, float* stash, const void* wimage,
-                    cudaStream_t st) {
+                    void* workspace, cudaStream_t st) {
   TcParams p;
   p.N = plan->n; p.CIN = (int)cin; p.T = (int)T; p.B = B;
   p.x = x; p.win_start = win_start; p.x_bstride = x_bstride; p.x_tstride = x_tstride;
   p.w[0] = w_z; p.w[1] = w_r; p.w[2] = w_h; p.bias[0] = b_z; p.bias[1] = b_r; p.bias[2] = b_h;
   p.h0 = h0; p.h0_bstride = (long long)plan->n * 32; p.wcat = nullptr; p.bcat = nullptr; p.n_ops = 2;
-  p.out = out; p.stash = stash; p.wimage = wimage;
+  p.out = out; p.stash = stash; p.wimage = wimage; p.ws = reinterpret_cast<float*>(workspace);
   return tc_launch_params(plan, p, st);
 }
 
 // generic graph-GRU: prepacked weights, any plan flavor with >= n_ops operators
 int gru_tc_launch(const stmp_plan* plan, int n_ops, long long B, long long T, long long cin, const float* x, const long long* win_start,
                   long long x_bstride, long long x_tstride, const float* wcat, const float* bcat, const float* h0, long long h0_bstride,
-                  float* out, float* stash, const void* wimage, cudaStream_t st) {
+                  float* out, float* stash, const void* wimage, void* workspace, cudaStream_t st) {
   TcParams p;
   p.N = plan->n; p.CIN = (int)cin; p.T = (int)T; p.B = B;
   p.x = x; p.win_start = win_start; p.x_bstride = x_bstride; p.x_tstride = x_tstride;
   for (int i = 0; i < 3; ++i) { p.w[i] = nullptr; p.bias[i] = nullptr; }
   p.h0 = h0; p.h0_bstride = h0_bstride; p.wcat = wcat; p.bcat = bcat; p.n_ops = n_ops;
-  p.out = out; p.stash = stash; p.wimage = wimage;
+  p.out = out; p.stash = stash; p.wimage = wimage; p.ws = reinterpret_cast<float*>(workspace);
   return tc_launch_params(plan, p, st);
 }
 
@@ -599,6 +631,7 @@ static int tc_launch_params(const stmp_plan* plan, TcParams& p, cudaStream_t st)
   STMP_CUDA_OK(cudaGetDevice(&dev));
   STMP_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int grid = (int)(B < sms ? B : sms);
+  p.ws_pitch = tc_ws_pitch(p.T, p.CIN);
   switch (p.CIN) {
 #define STMP_TC_CASE(C)                                                                                              \
   case C:                                                                                                            \

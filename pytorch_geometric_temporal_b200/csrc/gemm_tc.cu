@@ -78,6 +78,20 @@ __global__ void __launch_bounds__(GM_NT, 1) k_gemm_split(const GemmParams p) {
   const int nkb = p.Kpad / GM_BK;
   const uint32_t idesc = umma_idesc_f16(128, N);
 
+  float4 av[8];
+  auto load_a = [&](int kb) {
+    const int k0 = kb * GM_BK;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int idx = tid + j * GM_NT;
+      const int r = idx >> 4, c4 = idx & 15;
+      const long long row = m0 + r;
+      const int k = k0 + 4 * c4;
+      av[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row < p.M && k < p.K) av[j] = __ldg(reinterpret_cast<const float4*>(p.A + row * p.lda + k));   // K % 4 == 0
+    }
+  };
+
   for (int kb = 0; kb < nkb; ++kb) {
     const int s = kb & 1;
     unsigned char* a_hi = smem + s * stage_bytes;
@@ -89,25 +103,16 @@ __global__ void __launch_bounds__(GM_NT, 1) k_gemm_split(const GemmParams p) {
       tc_fence_after();
     }
     const int k0 = kb * GM_BK;
-    // A: 128 x 64 fp32 -> hi/lo fp16, swizzled.  16 lanes cover one row's 256 B contiguously; all 8 loads of a
-    // thread are issued before the first conversion (the kernel is bound by HBM latency, not by math).
-    {
-      float4 v[8];
+    // A: 128 x 64 fp32 -> hi/lo fp16, swizzled.  16 lanes cover one row's 256 B contiguously.  The 8 loads of k-block kb+1 are
+    // issued into registers right after k-block kb's tile is stored, i.e. before its barrier and MMAs: a k-block no longer costs a
+    // full HBM round trip (the kernel is bound by HBM latency, not by math).
+    if (kb == 0) load_a(0);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int idx = tid + j * GM_NT;
-        const int r = idx >> 4, c4 = idx & 15;
-        const long long row = m0 + r;
-        const int k = k0 + 4 * c4;
-        v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (row < p.M && k < p.K) v[j] = __ldg(reinterpret_cast<const float4*>(p.A + row * p.lda + k));   // K % 4 == 0
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int idx = tid + j * GM_NT;
-        store_split4(a_hi, a_lo, idx >> 4, 4 * (idx & 15), v[j]);
-      }
+    for (int j = 0; j < 8; ++j) {
+      const int idx = tid + j * GM_NT;
+      store_split4(a_hi, a_lo, idx >> 4, 4 * (idx & 15), av[j]);
     }
+    if (kb + 1 < nkb) load_a(kb + 1);
     // B: N x 64 fp16 (already split, L2-resident) -> swizzled; 4 x (hi, lo) 128-bit loads in flight per thread
     for (int base = 0; base < N * 8; base += 4 * GM_NT) {
       uint4 h[4], l[4];

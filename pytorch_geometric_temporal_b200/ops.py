@@ -77,6 +77,21 @@ def spmm(plan: GraphPlan, op: int, x: torch.Tensor, alpha: float = 1.0, z: Optio
     return _SpMM.apply(x, z, att, plan, op, float(alpha), float(beta))
 
 
+_SEQ_WS = {}
+
+
+def _seq_workspace(plan: GraphPlan, T: int, cin: int, device) -> torch.Tensor:
+    """Per-(device, stream) workspace of the fused sequence kernels (stmp_seq_workspace_bytes), grown on demand and reused: launches on
+    one stream are ordered, so consecutive calls may share it."""
+    need = int(_lib.lib().stmp_seq_workspace_bytes(plan.handle, T, cin))
+    key = (torch.device(device).index, torch.cuda.current_stream(device).cuda_stream)
+    buf = _SEQ_WS.get(key)
+    if buf is None or buf.numel() < need:
+        buf = torch.empty(max(need, 1), dtype=torch.uint8, device=device)
+        _SEQ_WS[key] = buf
+    return buf
+
+
 def dcrnn_seq_supported(plan: GraphPlan, cin: int, cout: int, K: int) -> bool:
     return bool(_lib.lib().stmp_dcrnn_seq_supported(plan.handle, cin, cout, K))
 
@@ -116,7 +131,7 @@ def dcrnn_seq_fwd(plan: GraphPlan, x: torch.Tensor, wz, wr, wh, bz, br, bh, K: i
         rc = _lib.lib().stmp_dcrnn_seq_fwd(plan.handle, B, T, cin, cout, K, _lib.ptr(x), _lib.ptr(ws), bstride, tstride,
                                            _lib.ptr(args[0]), _lib.ptr(args[1]), _lib.ptr(args[2]), _lib.ptr(bs[0]),
                                            _lib.ptr(bs[1]), _lib.ptr(bs[2]), _lib.ptr(h0c), _lib.ptr(out), _lib.ptr(st),
-                                           _lib.ptr(wimage), _lib.stream_ptr())
+                                           _lib.ptr(wimage), _lib.ptr(_seq_workspace(plan, T, cin, x.device)), _lib.stream_ptr())
     _lib.check(rc)
     return (out, st) if stash else out
 
@@ -146,7 +161,8 @@ def gru_seq_fwd(plan: GraphPlan, n_ops: int, x: torch.Tensor, wcat: torch.Tensor
         hs = 0 if h0_shared else N * 32
     with torch.cuda.device(x.device):
         rc = _lib.lib().stmp_gru_seq_fwd(plan.handle, n_ops, B, T, cin, _lib.ptr(x), None, T * N * cin, N * cin, _lib.ptr(wcat),
-                                         _lib.ptr(bcat), _lib.ptr(h0c), hs, _lib.ptr(out), None, _lib.ptr(wimage), _lib.stream_ptr())
+                                         _lib.ptr(bcat), _lib.ptr(h0c), hs, _lib.ptr(out), None, _lib.ptr(wimage),
+                                         _lib.ptr(_seq_workspace(plan, T, cin, x.device)), _lib.stream_ptr())
     _lib.check(rc)
     return out
 
