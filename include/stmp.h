@@ -315,7 +315,8 @@ int stmp_gemm_blocks_image(const void* packed, int64_t N, int64_t nblk, void* im
 int stmp_window_gather(const float* series, int64_t t_total, int64_t row_elems, const int64_t* start,
                        int64_t B, int64_t horizon, float* x, float* y, void* stream);
 
-/* Run-time switches for tests: "dcrnn_tc" = 1 (tcgen05 kernel, default) / 0 (FFMA kernel) behind stmp_dcrnn_seq_fwd. */
+/* Run-time switches for tests: "dcrnn_tc" = 1 (tcgen05 kernel, default) / 0 (FFMA kernel) behind stmp_dcrnn_seq_fwd; "spmm_variant" = 0
+ * (register gather, default) / 1, 2 (TMA-staged rows, 8 / 16 per warp); "dcrnn_bwd_all_cin" = 1 (default) / 0 (persistent backward only for cin == 2). */
 int stmp_set_option(const char* name, int value);
 
 /* ---- misc ---------------------------------------------------------------------------------------- */

@@ -19,6 +19,7 @@
 #include "common.cuh"
 
 namespace stmp {
+int g_bwd_all_cin = 1;
 namespace {
 
 constexpr int kCo = 32;          // hidden size served by these kernels
@@ -375,9 +376,10 @@ inline bool graph_in_smem(const stmp_plan* plan, int cin) {
 inline bool bwd_supported(const stmp_plan* plan, long long cin, long long cout, long long K) {
   if (!plan || plan->flavor != STMP_FLAVOR_DCONV || plan->n_ops != 2) return false;
   if (K != 2 || cout != kCo || cin < 1 || cin > 4) return false;
-  // Only cin == 2 (float2 slots, 104 columns) is exercised by the GPU parity tests so far; the instantiations for cin 1, 3, 4
-  // (scalar slots / 112 columns) compile but stay switched off until they have tests -- callers take the per-step backward.
-  if (cin != 2) return false;
+  // cin == 2 (float2 slots, 104 columns) is the benchmark configuration; cin 1, 3, 4 (scalar slots / 112 columns) are served too
+  // (tests/test_gpu_dcrnn.py::test_training_persistent_backward_other_channel_counts); stmp_set_option("dcrnn_bwd_all_cin", 0)
+  // restricts the persistent kernel to cin == 2 again.
+  if (cin != 2 && !g_bwd_all_cin) return false;
   return ((plan->n + 7) / 8) * (ncol_of((int)cin) / 8) <= kBwdThreads && seq_smem_base(plan->n, (int)cin) <= 227 * 1024 &&
          2 * sizeof(float) * (size_t)plan->n * (cin + kCo) <= 100 * 1024;
 }

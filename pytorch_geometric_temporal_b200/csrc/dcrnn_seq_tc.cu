@@ -137,6 +137,9 @@ __device__ __forceinline__ float4 gather_groups(const float* __restrict__ Uj, co
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   uint32_t u = idx4[g0];
   float4 v = val4[g0];
+#ifdef STMP_TC_GUNROLL
+  _Pragma("unroll 2")
+#endif
   for (int g = 1; g <= ng; ++g) {
     const uint32_t un = idx4[g0 + g];      // (one spare group at the end of the arrays)
     const float4 vn = val4[g0 + g];

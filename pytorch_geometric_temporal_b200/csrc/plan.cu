@@ -583,6 +583,17 @@ int build_gcn(Builder& b, stmp_plan* p, int n, int e, const int* row, const int*
   return 0;
 }
 
+// cost model of the static longest-first deal (tunable at build time for A/B runs: tests/perf/flagship_variants.py)
+#ifndef STMP_LPT_HANDICAP
+#define STMP_LPT_HANDICAP 24
+#endif
+#ifndef STMP_LPT_A
+#define STMP_LPT_A 2
+#endif
+#ifndef STMP_LPT_B
+#define STMP_LPT_B 3
+#endif
+
 // ---- shared-memory graph image for the fused tcgen05 kernel (graph_image.cuh) ---------------------------------------
 // One CTA.  Tasks (row, op) are rank-sorted per segment (destination row tile, operator) by descending group count, cut into
 // warp-tasks of four, and dealt longest-first to the least loaded of the 16 warps (loads carry over between the segments,
@@ -636,7 +647,7 @@ __global__ void __launch_bounds__(512) k_build_graph_image(const int* rp0, const
   if (tid == 0) {
     int load[kImgWarps], cntw[kImgWarps], pos[kImgWarps];
     for (int w = 0; w < kImgWarps; ++w) load[w] = 0;
-    load[0] = 24;                                        // warp 0 also issues the round's MMAs (~42 x 8 issue slots)
+    load[0] = STMP_LPT_HANDICAP;                         // warp 0 also issues the round's MMAs (~42 x 8 issue slots)
     int nwt = 0;
     int base = 0;
     for (int seg = 0; seg < kImgSegs; base += s_segcount[seg], ++seg) {
@@ -647,7 +658,7 @@ __global__ void __launch_bounds__(512) k_build_graph_image(const int* rp0, const
         for (int w = 1; w < kImgWarps; ++w)
           if (load[w] < load[best]) best = w;
         s_owner[k] = (unsigned char)best;
-        load[best] += 2 * s_ng[s_sorted[base + 4 * k]] + 3;   // ~ issue slots: per group 6 loads + 8 FMA2, per task a split store
+        load[best] += STMP_LPT_A * s_ng[s_sorted[base + 4 * k]] + STMP_LPT_B;   // ~ issue slots: per group 6 loads + 8 FMA2, per task a split store
         ++cntw[best];
       }
       int run = nwt;

@@ -345,3 +345,29 @@ def test_path_counters_name_the_kernel_that_served_the_call():
         m3(X, ei_t, ew_t)
     c2 = _lib.path_counters()
     assert c2.get("k_dcrnn_seq", 0) == c1.get("k_dcrnn_seq", 0) + 1 and c2["k_dcrnn_seq_tc"] == c1["k_dcrnn_seq_tc"]
+
+
+@pytest.mark.parametrize("cin", [1, 3, 4])
+def test_training_persistent_backward_other_channel_counts(cin):
+    """The persistent backward kernel pair for cin in {1, 3, 4} (scalar channel slots) against the per-step backward
+    (stmp_gru_bwd_* + transposed SpMM), which is itself pinned to autograd and to the reference goldens."""
+    from pytorch_geometric_temporal_b200.nn.recurrent.dcrnn import _DcrnnSeqFn
+    ei, ew, _ = synthetic.metr_la_like(5, 16)
+    ei_t, ew_t = torch.from_numpy(ei).to(DEV), torch.from_numpy(ew).to(DEV)
+    torch.manual_seed(cin)
+    X = torch.randn(4, 6, 207, cin, device=DEV)
+    a, b = BatchedDCRNN(cin, 32, 2).to(DEV), BatchedDCRNN(cin, 32, 2).to(DEV)
+    b.load_state_dict(a.state_dict())
+    w = torch.randn(4, 6, 207, 32, device=DEV)
+    Xa, Xb = X.clone().requires_grad_(True), X.clone().requires_grad_(True)
+    c0 = _lib.path_counters()
+    (a(Xa, ei_t, ew_t) * w).sum().backward()
+    assert _lib.path_counters().get("k_dcrnn_bwd_seq", 0) == c0.get("k_dcrnn_bwd_seq", 0) + 1      # the persistent kernel served it
+    _DcrnnSeqFn.fused_backward = False
+    try:
+        (b(Xb, ei_t, ew_t) * w).sum().backward()
+    finally:
+        _DcrnnSeqFn.fused_backward = True
+    _close(Xa.grad, Xb.grad.cpu(), 1e-3, 1e-5)
+    for (k, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
+        _close(pa.grad, pb.grad.cpu(), 1e-3, 2e-4)
