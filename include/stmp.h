@@ -224,6 +224,24 @@ int stmp_dcrnn_bwd_seq(const stmp_plan* plan, int64_t B, int64_t T, int64_t cin,
                        const float* out, const float* h0, const float* stash, const float* whsT, const float* wzrT,
                        float* dph_all, float* dpzr_all, float* dx, float* dh0, void* stream);
 
+/* Weight / bias gradients of the three DCRNN gates over all (t, b, n) rows (what autograd accumulates for the `matmul(basis, W)` and
+ * `+ bias` of dcrnn.py:86-111 across steps, gates and hops): S1 / S2 (rows, ld) are stmp_dcrnn_bwd_basis' bases (ld = 3(cin+cout) rounded
+ * up to 8), dpzr (rows, 2cout) / dph (rows, cout) stmp_dcrnn_bwd_seq's d pre-activations.  Writes gz / gr / gh in the module's
+ * (2, K, cin+cout, cout) layout and the bias gradients (nullable).  Two launches (per-CTA partials, fixed-order reduction: deterministic);
+ * workspace of stmp_dcrnn_bwd_wgrad_workspace_bytes(cin) bytes.  K = 2, cout = 32, cin <= 4. */
+int64_t stmp_dcrnn_bwd_wgrad_workspace_bytes(int64_t cin);
+int stmp_dcrnn_bwd_wgrad(int64_t cin, int64_t cout, int64_t K, int64_t rows, int64_t ld, const float* S1, const float* S2,
+                         const float* dpzr, const float* dph, void* workspace, float* gz, float* gr, float* gh, float* gbz,
+                         float* gbr, float* gbh, void* stream);
+
+/* torch.optim.Adam's update (the optimizer of examples/indexBatching/DCRNN/pems_ddp.py:90) over ONE flat fp32 buffer of n parameters:
+ * g' = grad * grad_scale (+ weight_decay * param); exp_avg.lerp(g', 1-beta1); exp_avg_sq = beta2 exp_avg_sq + (1-beta2) g'^2;
+ * param -= lr / (1-beta1^t) * exp_avg / (sqrt(exp_avg_sq) / sqrt(1-beta2^t) + eps), t = *step + 1.  `step` (one float) and `ticket`
+ * (one zero-initialised uint32) live on the device: the last block to finish bumps the counter, so a captured CUDA graph replays
+ * correctly.  zero_grad != 0 clears the gradient buffer in the same pass.  One launch. */
+int stmp_adam_flat(int64_t n, float* param, float* grad, float* exp_avg, float* exp_avg_sq, float* step, void* ticket, float lr,
+                   float beta1, float beta2, float eps, float weight_decay, float grad_scale, int zero_grad, void* stream);
+
 /* Transposed stacked DConv weights for the backward kernels, one launch: whsT (cout, (2K-1)C) from wh, wzrT (2cout, (2K-1)C)
  * from wz | wr; C = cin + cout; stacked block 0 = W[0,0] + W[1,0], block 1+2(k-1)+o = W[o,k] (the order of the basis). */
 int stmp_dcrnn_pack_bwd_weights(int64_t cin, int64_t cout, int64_t K, const float* wz, const float* wr, const float* wh,

@@ -61,6 +61,9 @@ _SIGNATURES = {
     "stmp_dcrnn_bwd_basis": (c_int, [_P] + [c_int64] * 4 + [_P, c_int64, c_int64, _P, _P, _P, _P, _P, c_int64, _P]),
     "stmp_dcrnn_bwd_seq": (c_int, [_P] + [c_int64] * 4 + [_P] * 11),
     "stmp_dcrnn_pack_bwd_weights": (c_int, [c_int64, c_int64, c_int64, _P, _P, _P, _P, _P, _P]),
+    "stmp_dcrnn_bwd_wgrad_workspace_bytes": (c_int64, [c_int64]),
+    "stmp_dcrnn_bwd_wgrad": (c_int, [c_int64, c_int64, c_int64, c_int64, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "stmp_adam_flat": (c_int, [c_int64, _P, _P, _P, _P, _P, _P, c_float, c_float, c_float, c_float, c_float, c_float, c_int, _P]),
     "stmp_masked_mae_workspace_floats": (c_int64, []),
     "stmp_masked_mae_fwd": (c_int, [c_int64, _P, _P, _P, _P, _P, _P]),
     "stmp_masked_mae_bwd": (c_int, [c_int64, _P, _P, _P, _P, _P, _P]),

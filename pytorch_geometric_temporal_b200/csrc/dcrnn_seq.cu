@@ -419,6 +419,7 @@ using namespace stmp;
 
 extern "C" int stmp_dcrnn_seq_supported(const stmp_plan* plan, int64_t cin, int64_t cout, int64_t K) {
   if (!shape_ok(plan, cin, cout, K)) return 0;
+  if (g_use_tc != 0 && dcrnn_tc_supported(plan, cin, cout, K)) return 1;   // the tcgen05 kernel's envelope is wider in cin than the FFMA kernel's
   Layout L;
   return make_layout(plan, (int)cin, (int)cout, (int)K, 12, &L) ? 1 : 0;
 }

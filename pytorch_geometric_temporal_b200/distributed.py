@@ -100,6 +100,44 @@ class FlatGradSync(object):
         self.flat.zero_()
 
 
+class FlatAdam(object):
+    """torch.optim.Adam (the optimizer of examples/indexBatching/DCRNN/pems_ddp.py:90) over the flat buffers of a FlatGradSync.
+
+    The parameters are moved into ONE flat fp32 buffer (each `p.data` becomes a view of it, like the gradients), the moments are
+    two more, and a step is ONE launch (`stmp_adam_flat`) instead of the ~35 of the capturable foreach implementation; the step
+    counter lives on the device, so the launch can be captured in a CUDA graph.  `step()` also clears the gradient buffer
+    (zero_grad=False keeps it) -- `sync.all_reduce(); opt.step()` is the whole tail of a data-parallel training step.
+    CUDA only: there is no CPU fallback.
+    """
+
+    def __init__(self, sync: FlatGradSync, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0):
+        if not sync.flat.is_cuda or sync.flat.dtype != torch.float32:
+            raise RuntimeError("FlatAdam needs CUDA fp32 parameters (the update is a CUDA kernel; there is no CPU fallback)")
+        self.sync = sync
+        self.lr, self.betas, self.eps, self.weight_decay = float(lr), (float(betas[0]), float(betas[1])), float(eps), float(weight_decay)
+        self.flat = torch.empty_like(sync.flat)
+        with torch.no_grad():
+            for p, off in zip(sync.params, sync._offsets):
+                view = self.flat[off:off + p.numel()].view_as(p)
+                view.copy_(p.data)
+                p.data = view
+        self.exp_avg = torch.zeros_like(self.flat)
+        self.exp_avg_sq = torch.zeros_like(self.flat)
+        self.step_count = torch.zeros(1, device=self.flat.device, dtype=torch.float32)
+        self._ticket = torch.zeros(1, device=self.flat.device, dtype=torch.int32)
+
+    def step(self, zero_grad: bool = True, grad_scale: float = 1.0):
+        from . import ops
+        self.sync._check_aliasing()
+        ops.adam_flat(self.flat, self.sync.flat, self.exp_avg, self.exp_avg_sq, self.step_count, self._ticket, self.lr, self.betas[0],
+                      self.betas[1], self.eps, self.weight_decay, grad_scale, zero_grad)
+        # the kernel wrote through the flat buffer: bump the version counters the packed-weight caches are keyed on
+        torch._C._increment_version(self.sync.params)
+
+    def zero_grad(self):
+        self.sync.zero()
+
+
 def broadcast_parameters(module: torch.nn.Module, src: int = 0):
     """Make every replica start from rank `src`'s parameters/buffers with one flat broadcast."""
     if world_size() == 1:

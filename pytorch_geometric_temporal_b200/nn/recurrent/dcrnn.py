@@ -124,9 +124,10 @@ class _DcrnnSeqFn(torch.autograd.Function):
         gout = gout.contiguous()
         if _DcrnnSeqFn.fused_backward and ops.dcrnn_bwd_supported(plan, Ci, Co, K):
             # small graph: the whole reverse recurrence is ONE persistent launch (dL/dH stays in shared memory), the bases
-            # of all steps are one more, and the weight gradients are chunked GEMMs over all (t, b, n) rows
-            S1 = torch.empty(T * B, N, nb * C, **f32)
-            S2 = torch.empty(T * B, N, nb * C, **f32)
+            # of all steps are one more, and the weight gradients are one contraction over all (t, b, n) rows
+            ld = ops.dcrnn_bwd_basis_ld(Ci, Co, K)                                   # pad columns are never written nor used
+            S1 = torch.empty(T * B, N, ld, **f32)
+            S2 = torch.empty(T * B, N, ld, **f32)
             dph_all = torch.empty(T, B, N, Co, **f32)
             dpzr_all = torch.empty(T, B, N, 2 * Co, **f32)
             dX = torch.empty(X.shape, **f32) if ctx.needs_input_grad[0] else None   # dense: the kernels write (B,T,N,Cin) row-major
@@ -141,7 +142,10 @@ class _DcrnnSeqFn(torch.autograd.Function):
                 ops.dcrnn_bwd_basis(plan, X, out, H0, stash, S1, S2)
             ops.dcrnn_bwd_seq(plan, Ci, gout, out, H0, stash, WhsT, WzrT, dph_all, dpzr_all, dX, dH0)
             main.wait_stream(side)
-            return _DcrnnSeqFn._finish(ctx, S1, S2, dph_all, dpzr_all, dX, dH0, K, C, Co)
+            # weight / bias gradients over all (t, b, n) rows: per-CTA partial products + one fixed-order reduction (2 launches)
+            gz, gr, gh, gbz, gbr, gbh = ops.dcrnn_bwd_wgrad(Ci, K, S1, S2, dpzr_all, dph_all, ctx.has_bias)
+            gH0 = dH0 if (ctx.has_h0 and ctx.needs_input_grad[1]) else None
+            return dX, gH0, gz, gr, gh, gbz, gbr, gbh, None, None, None
         Z, R, Ht = stash[:, :, 0], stash[:, :, 1], stash[:, :, 2]                          # (B,T,N,Co) strided views
         # ---- hoisted: H_{t-1} for every t (time-major so that [t] is a dense (B,N,Co) block) and both bases ------------
         Hp = torch.empty(T, B, N, Co, **f32)

@@ -438,6 +438,49 @@ def dcrnn_bwd_seq(plan: GraphPlan, cin: int, gout, out, h0, stash, whsT, wzrT, d
                                                  _lib.ptr(dpzr_all), _lib.ptr(dx), _lib.ptr(dh0), _lib.stream_ptr()))
 
 
+def dcrnn_bwd_basis_ld(cin: int, cout: int, K: int) -> int:
+    """Row pitch of the stacked bases: (2K-1)(cin+cout) rounded up to 8 floats (16-byte rows for the weight-gradient kernel's tiles)."""
+    return ((2 * K - 1) * (cin + cout) + 7) // 8 * 8
+
+
+_WGRAD_WS = {}
+
+
+def dcrnn_bwd_wgrad(cin: int, K: int, S1, S2, dpzr_all, dph_all, has_bias: bool):
+    """(gz, gr, gh, gbz, gbr, gbh): weight / bias gradients of the three gates over all (t, b, n) rows in two launches
+    (`stmp_dcrnn_bwd_wgrad`); S1 / S2 (T*B, N, ld) from dcrnn_bwd_basis with ld = dcrnn_bwd_basis_ld(...)."""
+    Co = dph_all.size(-1)
+    C = cin + Co
+    dev = S1.device
+    rows = S1.size(0) * S1.size(1)
+    key = (dev, torch.cuda.current_stream(dev).cuda_stream, cin)
+    ws = _WGRAD_WS.get(key)
+    if ws is None:
+        ws = torch.empty(int(_lib.lib().stmp_dcrnn_bwd_wgrad_workspace_bytes(cin)), device=dev, dtype=torch.uint8)
+        _WGRAD_WS[key] = ws
+    g = torch.empty(3, 2, K, C, Co, device=dev, dtype=torch.float32)
+    gb = torch.empty(3, Co, device=dev, dtype=torch.float32) if has_bias else None
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().stmp_dcrnn_bwd_wgrad(cin, Co, K, rows, S1.size(-1), _lib.ptr(S1), _lib.ptr(S2), _lib.ptr(dpzr_all), _lib.ptr(dph_all),
+                                                   _lib.ptr(ws), _lib.ptr(g[0]), _lib.ptr(g[1]), _lib.ptr(g[2]),
+                                                   _lib.ptr(None if gb is None else gb[0]), _lib.ptr(None if gb is None else gb[1]),
+                                                   _lib.ptr(None if gb is None else gb[2]), _lib.stream_ptr()))
+    if gb is None:
+        return g[0], g[1], g[2], None, None, None
+    return g[0], g[1], g[2], gb[0], gb[1], gb[2]
+
+
+def adam_flat(param, grad, exp_avg, exp_avg_sq, step, ticket, lr, beta1, beta2, eps, weight_decay=0.0, grad_scale=1.0, zero_grad=True):
+    """One-launch Adam over flat fp32 buffers (`stmp_adam_flat`); `step` (1 float) and `ticket` (1 int32, zero) are device tensors."""
+    for t, nm in ((param, "param"), (grad, "grad"), (exp_avg, "exp_avg"), (exp_avg_sq, "exp_avg_sq")):
+        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.numel() == param.numel()):
+            raise RuntimeError(f"adam_flat: {nm} must be a contiguous CUDA fp32 buffer of {param.numel()} elements")
+    with torch.cuda.device(param.device):
+        _lib.check(_lib.lib().stmp_adam_flat(param.numel(), _lib.ptr(param), _lib.ptr(grad), _lib.ptr(exp_avg), _lib.ptr(exp_avg_sq), _lib.ptr(step),
+                                             _lib.ptr(ticket), lr, beta1, beta2, eps, weight_decay, grad_scale, 1 if zero_grad else 0,
+                                             _lib.stream_ptr()))
+
+
 def dcrnn_pack_bwd_weights(wz, wr, wh, cin: int, K: int):
     """(whsT (Co, (2K-1)C), wzrT (2Co, (2K-1)C)): transposed stacked weights of the backward GEMMs, one launch."""
     Co = wz.size(-1)
