@@ -234,11 +234,11 @@ def train_probe(dev, world, rank, ei_d, ew_d, series, steps=5, windows=64):
     params = list(model.parameters()) + list(head.parameters())
     if world > 1:
         D.broadcast_parameters(model); D.broadcast_parameters(head)
-    sync = D.FlatGradSync(params)
+    sync = D.FlatGradSync(params, average=False)       # the 1/world average is folded into the optimizer launch
     tr, _, _ = index_splits(series.size(0), HORIZON)
     loader = IndexBatchLoader(series.to(dev), tr, HORIZON, windows, shuffle=True, world_size=world, rank=rank, seed=0, drop_last=True)
     feeder = EpochFeeder(loader)
-    opt = torch.optim.Adam(params, lr=1e-3, capturable=True)   # (torch's fused=True variant follows a different trajectory: tools/train_check.py)
+    opt = D.FlatAdam(sync, lr=1e-3)                    # torch.optim.Adam's update over the flat buffers: one launch (tests/test_gpu_train.py)
     sx = torch.empty((windows, HORIZON, N_NODES, F_IN), device=dev)
     sy = torch.empty((windows, HORIZON, N_NODES, F_IN), device=dev)
     loss_buf = torch.zeros((), device=dev)
@@ -249,15 +249,15 @@ def train_probe(dev, world, rank, ei_d, ew_d, series, steps=5, windows=64):
         loss = D.masked_mae_loss(pred, sy[:, 0, :, 0])
         loss.backward()
         sync.all_reduce()
-        opt.step()
-        sync.zero()
+        opt.step(grad_scale=1.0 / world)               # also clears the gradient buffer
         loss_buf.copy_(loss.detach())
 
     def feed():
         x, y = feeder.next()
         sx.copy_(x); sy.copy_(y)
 
-    # The step is a fixed sequence of ~100 launches (4 of ours, the rest loss/Adam plumbing): capture it ONCE in a CUDA graph (plans are cached, all
+    # The step is a fixed sequence of ~45 launches (the recurrence kernels, the weight-gradient contraction, the head / loss and one Adam
+    # launch): capture it ONCE in a CUDA graph (plans are cached, all
     # buffers static) and replay it -- graphs instead of a tracing compiler.  Falls back to eager if capture fails.
     mode = "cuda-graph"
     side = torch.cuda.Stream(device=dev)
@@ -293,7 +293,7 @@ def train_probe(dev, world, rank, ei_d, ew_d, series, steps=5, windows=64):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item()) / steps
     return {"value": world * windows / (ms * 1e-3), "unit": "snapshots/s", "ms_per_step": ms, "windows_per_step_per_gpu": windows,
-            "path": "fused fwd (stmp_dcrnn_seq_fwd + stash) + persistent bwd (stmp_dcrnn_bwd_basis || stmp_dcrnn_bwd_seq) + chunked weight-grad GEMMs + flat all-reduce + Adam", "launch": mode, "allreduce_bytes_per_step": sync.nbytes if world > 1 else 0,
+            "path": "fused fwd (stmp_dcrnn_seq_fwd + stash) + persistent bwd (stmp_dcrnn_bwd_basis || stmp_dcrnn_bwd_seq) + stmp_dcrnn_bwd_wgrad + flat all-reduce + stmp_adam_flat", "launch": mode, "allreduce_bytes_per_step": sync.nbytes if world > 1 else 0,
             "loss": float(loss.detach())}
 
 

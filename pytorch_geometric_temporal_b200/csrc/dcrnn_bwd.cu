@@ -20,6 +20,7 @@
 
 namespace stmp {
 int g_bwd_all_cin = 1;
+int g_bwd_split = 1;      // 1: a CTA pair per window when 2 B CTAs fit the machine; 0: always one CTA per window
 namespace {
 
 constexpr int kCo = 32;          // hidden size served by these kernels
@@ -143,40 +144,61 @@ struct BwdParams {
   float* dh0;                               // (B,N,Co)
 };
 
-// buf[8rg..8rg+8)[8cg..8cg+8) = sum_k dpT[k][8rg..] (x) W[k][8cg..]: one thread per 8x8 output tile.  Per k a thread
-// issues 4 LDS.128 (2 for the 8 rows -- dp is kept TRANSPOSED, k-major, so they are contiguous -- and 2 for the 8 weight
-// columns) for 64 FFMA: the shared-memory pipe and the FMA pipe are balanced (a 1 x 52 tile was 4x LSU-bound).  Adjacent
-// lanes take adjacent column groups, so the tile stores of a warp spread over the banks.
-template <int NCOL, int KD>
+// ---- thread-block-cluster helpers: with SPLIT == 2 a window is served by a CTA pair, each owning half of the node rows -----------------
+__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_peer(const void* p, uint32_t peer) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(peer));
+  return r;
+}
+__device__ __forceinline__ void st4_cluster(uint32_t addr, float4 v) {
+  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// buf[r0 + RT rg ..+RT)[8cg..8cg+8) = sum_k dpT[k][r0 + RT rg ..] (x) W[k][8cg..]: one thread per RT x 8 output tile, RG row groups starting at
+// row r0.  Per k a thread issues RT/4 + 2 LDS.128 (the rows -- dp is kept TRANSPOSED, k-major, so they are contiguous -- and the 8 weight
+// columns) for 8 RT FFMA: with RT = 8 the shared-memory pipe and the FMA pipe are balanced (a 1 x 52 tile was 4x LSU-bound).  Adjacent
+// lanes take adjacent column groups, so the tile stores of a warp spread over the banks.  PEER: the tile is also pushed into the partner
+// CTA's buf (distributed shared memory), whose adjoint gathers read rows of both halves.
+template <int NCOL, int KD, int RT, bool PEER>
 __device__ __forceinline__ void gemm_tiles(const float* __restrict__ dpT, int dpp, const float* __restrict__ W, float* __restrict__ buf,
-                                           int RG) {
+                                           int r0, int RG, uint32_t peer_buf) {
   constexpr int CGN = NCOL / 8;
   const int tid = threadIdx.x;
   if (tid >= RG * CGN) return;
   const int rg = tid / CGN, cg = tid - rg * CGN;
-  float acc[8][8];
+  float acc[RT][8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < RT; ++i)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-  const float* ap = dpT + 8 * rg;
+  const float* ap = dpT + r0 + RT * rg;
   const float* wp = W + 8 * cg;
 #pragma unroll 2
   for (int k = 0; k < KD; ++k) {
-    const float4 a0 = *reinterpret_cast<const float4*>(ap + k * dpp), a1 = *reinterpret_cast<const float4*>(ap + k * dpp + 4);
+    float a[RT];
+#pragma unroll
+    for (int q = 0; q < RT / 4; ++q) {
+      const float4 t = *reinterpret_cast<const float4*>(ap + k * dpp + 4 * q);
+      a[4 * q] = t.x; a[4 * q + 1] = t.y; a[4 * q + 2] = t.z; a[4 * q + 3] = t.w;
+    }
     const float4 w0 = *reinterpret_cast<const float4*>(wp + k * NCOL), w1 = *reinterpret_cast<const float4*>(wp + k * NCOL + 4);
-    const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
     const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < RT; ++i)
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
   }
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    float4* o = reinterpret_cast<float4*>(buf + (8 * rg + i) * NCOL + 8 * cg);
-    o[0] = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-    o[1] = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
+  for (int i = 0; i < RT; ++i) {
+    const int off = (r0 + RT * rg + i) * NCOL + 8 * cg;
+    const float4 v0 = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]), v1 = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
+    float4* o = reinterpret_cast<float4*>(buf + off);
+    o[0] = v0; o[1] = v1;
+    if constexpr (PEER) { st4_cluster(peer_buf + off * 4, v0); st4_cluster(peer_buf + off * 4 + 16, v1); }
   }
 }
 
@@ -200,12 +222,23 @@ __device__ __forceinline__ void adjoint_at(const Gr<SG> (&g)[2], const float* __
   }
 }
 
-template <int CIN, bool SG>
+// SPLIT = 2: a thread-block cluster of two CTAs per window (launched when 2 B CTAs still fit the machine, i.e. at the reference's batch of 64
+// on 148 SMs): each CTA owns half of the node rows (a multiple of 8), runs the GEMMs / adjoints / gate derivatives of its rows only, and
+// pushes its rows of dS into the partner's buf so that the adjoint gathers stay local.  All four per-step barriers become cluster barriers
+// (the partner must have finished reading buf before it is overwritten, and finished writing it before it is gathered).
+template <int CIN, bool SG, int SPLIT>
 __global__ void __launch_bounds__(kBwdThreads, 1) k_dcrnn_bwd_seq(BwdParams p) {
-  constexpr int C = CIN + kCo, NCOL = ncol_of(CIN), V = (C % 2 == 0) ? 2 : 1, CP = C / V;
+  constexpr int C = CIN + kCo, NCOL = ncol_of(CIN), V = (C % 2 == 0) ? 2 : 1, CP = C / V, RT = SPLIT == 2 ? 4 : 8;
   extern __shared__ __align__(16) float sm[];
-  const int N = p.N, T = p.T, b = blockIdx.x, tid = threadIdx.x;
-  const int RG = (N + 7) / 8, dpp = RG * 8 + 4, NP = N * CP, NH = N * kCo;
+  const int N = p.N, T = p.T, b = blockIdx.x / SPLIT, tid = threadIdx.x;
+  const int RG = (N + 7) / 8, dpp = RG * 8 + 4, NH = N * kCo;
+  // rows [r_lo, r_hi) are this CTA's; the GEMM covers whole groups of RT rows (pad rows of dpT are zero)
+  const int half_rows = ((RG + 1) / 2) * 8;
+  const int hrank = SPLIT == 2 ? (int)cluster_rank() : 0;
+  const int r_lo = SPLIT == 2 ? hrank * half_rows : 0;
+  const int r_hi = SPLIT == 2 ? (r_lo + half_rows < N ? r_lo + half_rows : N) : N;
+  const int g_r0 = r_lo, g_RG = SPLIT == 2 ? ((hrank == 0 ? half_rows : RG * 8 - half_rows) / RT) : RG;
+  const int s_lo = r_lo * CP, NP = r_hi * CP;                     // slot range of the pointwise loops
   float* Wh = sm;                            // [Co][NCOL]
   float* Wzr = Wh + kCo * NCOL;              // [2Co][NCOL]
   float* buf = Wzr + 2 * kCo * NCOL;         // [8RG][NCOL]
@@ -238,10 +271,13 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_dcrnn_bwd_seq(BwdParams p) {
     sm[i] = v;
   }
   for (int i = tid; i < 2 * kCo * dpp; i += kBwdThreads) dpT[i] = 0.f;
-  __syncthreads();
+  uint32_t peer_buf = 0;
+  if constexpr (SPLIT == 2) peer_buf = map_to_peer(buf, (uint32_t)(hrank ^ 1));
+  auto sync_all = [&]() { if constexpr (SPLIT == 2) cluster_sync_all(); else __syncthreads(); };
+  sync_all();
   // ---- open step T-1
   const long long bT = (long long)b * T;
-  for (int i = tid; i < NH; i += kBwdThreads) {
+  for (int i = r_lo * kCo + tid; i < r_hi * kCo; i += kBwdThreads) {
     const int n = i / kCo, cc = i - n * kCo;
     const long long bt = bT + (T - 1);
     const float gg = __ldg(p.gout + bt * NH + i);
@@ -251,19 +287,19 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_dcrnn_bwd_seq(BwdParams p) {
     dpT[cc * dpp + n] = d;
     p.dph_all[(((long long)(T - 1) * p.B + b) * N) * kCo + i] = d;
   }
-  __syncthreads();
+  sync_all();
 #pragma unroll 1
   for (int t = T - 1; t >= 0; --t) {
     const long long bt = bT + t;
     const float* st = p.stash + bt * 3 * NH;
     const float* hprev = t > 0 ? p.out + (bt - 1) * NH : (p.h0 ? p.h0 + (long long)b * NH : nullptr);
     // dS2 = dpre_h @ Wh^T
-    gemm_tiles<NCOL, kCo>(dpT, dpp, Wh, buf, RG);
-    __syncthreads();
+    gemm_tiles<NCOL, kCo, RT, SPLIT == 2>(dpT, dpp, Wh, buf, g_r0, g_RG, peer_buf);
+    sync_all();
     // dU2 = adjoint; d pre-activations of z and r; partial carry  g*Z + dHR*R
     float* dpzr = p.dpzr_all + (((long long)t * p.B + b) * N) * 2 * kCo;
 #pragma unroll 1
-    for (int base = tid; base < NP; base += kBatch * kBwdThreads) {
+    for (int base = s_lo + tid; base < NP; base += kBatch * kBwdThreads) {
       float hp[kBatch][V], zz[kBatch][V], rr[kBatch][V], hh[kBatch][V];
 #pragma unroll
       for (int j = 0; j < kBatch; ++j) {                       // all global operands of the batch in flight together
@@ -304,15 +340,15 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_dcrnn_bwd_seq(BwdParams p) {
         }
       }
     }
-    __syncthreads();
+    sync_all();
     // dS1 = dpre_zr @ Wzr^T
-    gemm_tiles<NCOL, 2 * kCo>(dpT, dpp, Wzr, buf, RG);
-    __syncthreads();
+    gemm_tiles<NCOL, 2 * kCo, RT, SPLIT == 2>(dpT, dpp, Wzr, buf, g_r0, g_RG, peer_buf);
+    sync_all();
     // dU1 = adjoint; dX_t; dL/dH_{t-1}; open step t-1
     const float* stn = st - 3 * NH;          // stash of step t-1 (only dereferenced when t > 0)
     float* dphn = p.dph_all + (((long long)(t - 1) * p.B + b) * N) * kCo;
 #pragma unroll 1
-    for (int base = tid; base < NP; base += kBatch * kBwdThreads) {
+    for (int base = s_lo + tid; base < NP; base += kBatch * kBwdThreads) {
       float go[kBatch][V], zz[kBatch][V], hh[kBatch][V];
 #pragma unroll
       for (int j = 0; j < kBatch; ++j) {
@@ -357,7 +393,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_dcrnn_bwd_seq(BwdParams p) {
         }
       }
     }
-    __syncthreads();
+    sync_all();
   }
 }
 
@@ -391,9 +427,20 @@ int launch_basis(const BasisParams& p, size_t smem, cudaStream_t st) {
   return STMP_OK;
 }
 template <int CIN, bool SG>
-int launch_seq(const BwdParams& p, size_t smem, cudaStream_t st) {
-  STMP_CUDA_OK(cudaFuncSetAttribute(k_dcrnn_bwd_seq<CIN, SG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_dcrnn_bwd_seq<CIN, SG><<<(unsigned)p.B, kBwdThreads, smem, st>>>(p);
+int launch_seq(const BwdParams& p, size_t smem, int split, cudaStream_t st) {
+  if (split == 2) {
+    STMP_CUDA_OK(cudaFuncSetAttribute(k_dcrnn_bwd_seq<CIN, SG, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)p.B * 2); cfg.blockDim = dim3(kBwdThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    STMP_CUDA_OK(cudaLaunchKernelEx(&cfg, k_dcrnn_bwd_seq<CIN, SG, 2>, p));
+    return STMP_OK;
+  }
+  STMP_CUDA_OK(cudaFuncSetAttribute(k_dcrnn_bwd_seq<CIN, SG, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_dcrnn_bwd_seq<CIN, SG, 1><<<(unsigned)p.B, kBwdThreads, smem, st>>>(p);
   return STMP_OK;
 }
 
@@ -454,18 +501,23 @@ extern "C" int stmp_dcrnn_bwd_seq(const stmp_plan* plan, int64_t B, int64_t T, i
   const bool sg = graph_in_smem(plan, (int)cin);
   const size_t smem = seq_smem_base(plan->n, (int)cin) + (sg ? seq_smem_graph(plan) : 0);
   cudaStream_t st = (cudaStream_t)stream;
+  int dev = 0, sms = 0;
+  STMP_CUDA_OK(cudaGetDevice(&dev));
+  STMP_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int split = (g_bwd_split && 2 * B <= sms && plan->n >= 16) ? 2 : 1;      // small batches: two CTAs per window (cluster), rows halved
   int rc = STMP_OK;
   switch ((int)cin * 2 + (sg ? 1 : 0)) {
-    case 2: rc = launch_seq<1, false>(p, smem, st); break;
-    case 3: rc = launch_seq<1, true>(p, smem, st); break;
-    case 4: rc = launch_seq<2, false>(p, smem, st); break;
-    case 5: rc = launch_seq<2, true>(p, smem, st); break;
-    case 6: rc = launch_seq<3, false>(p, smem, st); break;
-    case 7: rc = launch_seq<3, true>(p, smem, st); break;
-    case 8: rc = launch_seq<4, false>(p, smem, st); break;
-    default: rc = launch_seq<4, true>(p, smem, st); break;
+    case 2: rc = launch_seq<1, false>(p, smem, split, st); break;
+    case 3: rc = launch_seq<1, true>(p, smem, split, st); break;
+    case 4: rc = launch_seq<2, false>(p, smem, split, st); break;
+    case 5: rc = launch_seq<2, true>(p, smem, split, st); break;
+    case 6: rc = launch_seq<3, false>(p, smem, split, st); break;
+    case 7: rc = launch_seq<3, true>(p, smem, split, st); break;
+    case 8: rc = launch_seq<4, false>(p, smem, split, st); break;
+    default: rc = launch_seq<4, true>(p, smem, split, st); break;
   }
   if (rc != STMP_OK) return rc;
   STMP_LAUNCH_OK("k_dcrnn_bwd_seq");
+  if (split == 2) { static const int slot2 = path_slot("k_dcrnn_bwd_seq[cluster2]"); count_path(slot2); }
   return STMP_OK;
 }

@@ -28,6 +28,7 @@ namespace stmp {
 // tcgen05 variant (dcrnn_seq_tc.cu)
 extern int g_spmm_variant;
 extern int g_bwd_all_cin;
+extern int g_bwd_split;
 bool dcrnn_tc_supported(const stmp_plan* plan, long long cin, long long cout, long long K);
 int dcrnn_tc_launch(const stmp_plan* plan, long long B, long long T, long long cin, const float* x, const long long* win_start,
                     long long x_bstride, long long x_tstride, const float* w_z, const float* w_r, const float* w_h, const float* b_z,
@@ -509,6 +510,7 @@ extern "C" int stmp_set_option(const char* name, int value) {
   if (strcmp(name, "dcrnn_tc") == 0) { g_use_tc = value ? 1 : 0; return STMP_OK; }
   if (strcmp(name, "spmm_variant") == 0) { g_spmm_variant = value; return STMP_OK; }
   if (strcmp(name, "dcrnn_bwd_all_cin") == 0) { g_bwd_all_cin = value ? 1 : 0; return STMP_OK; }
+  if (strcmp(name, "dcrnn_bwd_split") == 0) { g_bwd_split = value ? 1 : 0; return STMP_OK; }
   return set_error(STMP_EINVAL, "stmp_set_option: unknown option '%s'", name);
 }
 

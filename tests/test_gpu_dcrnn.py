@@ -3,6 +3,8 @@ kernel and tiled path vs the CPU oracle and the committed reference goldens.
 Tolerance (strict fp32 mode): rtol=1e-4, atol=1e-5 per layer output."""
 import os
 
+import numpy as np
+
 import pytest
 import torch
 
@@ -371,3 +373,33 @@ def test_training_persistent_backward_other_channel_counts(cin):
     _close(Xa.grad, Xb.grad.cpu(), 1e-3, 1e-5)
     for (k, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
         _close(pa.grad, pb.grad.cpu(), 1e-3, 2e-4)
+
+
+@pytest.mark.parametrize("n_nodes,cin", [(207, 2), (50, 2), (121, 3)])
+def test_persistent_backward_cluster_pair_equals_single_cta(n_nodes, cin):
+    """Small batches run the reverse recurrence on a 2-CTA cluster per window (rows halved, dS exchanged through distributed shared
+    memory); every row's arithmetic is the same sequence as in the one-CTA kernel, so the gradients must agree to the last bit."""
+    rng = np.random.default_rng(n_nodes)
+    E = 6 * n_nodes
+    ei = torch.from_numpy(np.stack([rng.integers(0, n_nodes, E), rng.integers(0, n_nodes, E)])).to(DEV)
+    ew = torch.from_numpy(rng.random(E).astype(np.float32)).to(DEV)
+    torch.manual_seed(cin + n_nodes)
+    X = torch.randn(5, 6, n_nodes, cin, device=DEV)
+    w = torch.randn(5, 6, n_nodes, 32, device=DEV)
+    model = BatchedDCRNN(cin, 32, 2).to(DEV)
+    grads = []
+    for split in (1, 0):
+        _lib.set_option("dcrnn_bwd_split", split)
+        try:
+            model.zero_grad()
+            Xa = X.clone().requires_grad_(True)
+            c0 = _lib.path_counters()
+            (model(Xa, ei, ew) * w).sum().backward()
+            c1 = _lib.path_counters()
+        finally:
+            _lib.set_option("dcrnn_bwd_split", 1)
+        assert c1.get("k_dcrnn_bwd_seq", 0) == c0.get("k_dcrnn_bwd_seq", 0) + 1
+        assert c1.get("k_dcrnn_bwd_seq[cluster2]", 0) - c0.get("k_dcrnn_bwd_seq[cluster2]", 0) == split
+        grads.append([Xa.grad.clone()] + [p.grad.clone() for p in model.parameters()])
+    for ga, gb in zip(*grads):
+        assert torch.equal(ga, gb), f"max abs diff {(ga - gb).abs().max():.3e}"
