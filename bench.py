@@ -169,34 +169,42 @@ def run_reference(args):
 # our arm
 # ------------------------------------------------------------------------------------------------------
 def spmm_probe(dev, pk):
-    """SpMM GB/s vs HBM peak on the cfg5 shape (N=10^4, E=10^5 + N loops, F=128=[X|H], batch 32 > L2)."""
+    """SpMM GB/s vs HBM peak on the cfg5 shape (N=10^4, E=10^5 + N loops, F=128=[X|H], batch 32 > L2): the random graph of BASELINE
+    configs[4] (headline of this leg) and, next to it, a sensor-network-like banded graph of the same size."""
     from pytorch_geometric_temporal_b200 import _lib, ops
     from pytorch_geometric_temporal_b200.dataset import synthetic
     from pytorch_geometric_temporal_b200.plan import GraphPlan
-    ei, ew = synthetic.large_graph(10000, 100000, 0)
-    plan = GraphPlan(_lib.FLAVOR_CHEB, torch.from_numpy(ei).to(dev), torch.from_numpy(ew).to(dev), 10000, normalization="sym")
     B, N, F = 32, 10000, 128
     x = torch.randn(B, N, F, device=dev)
     y = torch.empty_like(x)
-    nnz = plan.nnz(0)
-    bytes_alg = B * (8 * N * F) + 8 * nnz + 4 * (N + 1)
-    for _ in range(3):
-        ops.spmm_raw(plan, 0, x, out=y)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    iters = 10
-    e0.record()
-    for _ in range(iters):
-        ops.spmm_raw(plan, 0, x, out=y)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / iters
-    gbs = bytes_alg / (ms * 1e-3) / 1e9
+
+    def run(ei, ew):
+        plan = GraphPlan(_lib.FLAVOR_CHEB, torch.from_numpy(ei).to(dev), torch.from_numpy(ew).to(dev), N, normalization="sym")
+        nnz = plan.nnz(0)
+        bytes_alg = B * (8 * N * F) + 8 * nnz + 4 * (N + 1)
+        for _ in range(3):
+            ops.spmm_raw(plan, 0, x, out=y)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        iters = 10
+        e0.record()
+        for _ in range(iters):
+            ops.spmm_raw(plan, 0, x, out=y)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        return nnz, bytes_alg, ms, bytes_alg / (ms * 1e-3) / 1e9
+
+    nnz, bytes_alg, ms, gbs = run(*synthetic.large_graph(N, 100000, 0))
     gather = 4 * nnz * F * B                       # source rows delivered L2 -> SM (every entry reads a 4F-byte row); not HBM traffic
-    return {"workload": "SpMM N=10000 nnz=%d F=128 batch=32 (in 164 MB + out 164 MB > L2)" % nnz, "ms": ms,
-            "algorithmic_bytes": bytes_alg, "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
-            "l2_gather_bytes": gather, "l2_to_sm_gbs": (gather + bytes_alg) / (ms * 1e-3) / 1e9,
-            "note": "random graph: bound by the L2->SM delivery of the gathered rows (5.5x the algorithmic bytes), see DESIGN.md section 3"}
+    out = {"workload": "SpMM N=10000 nnz=%d F=128 batch=32 (in 164 MB + out 164 MB > L2)" % nnz, "ms": ms,
+           "algorithmic_bytes": bytes_alg, "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
+           "l2_gather_bytes": gather, "l2_to_sm_gbs": (gather + bytes_alg) / (ms * 1e-3) / 1e9,
+           "note": "random graph: bound by the L2->SM delivery of the gathered rows (5.5x the algorithmic bytes), see DESIGN.md section 3"}
+    nnz2, bytes2, ms2, gbs2 = run(*synthetic.banded_graph(N, 100000, 64, 0))
+    out["banded_graph"] = {"workload": "same sizes, every edge within 64 node ids (sensor-network-like ordering): gathered rows are re-used out of L1",
+                           "nnz": nnz2, "ms": ms2, "achieved": gbs2, "frac": gbs2 / pk["hbm_gbs"]}
+    return out
 
 
 class EpochFeeder(object):

@@ -30,6 +30,12 @@
 #include "graph_image.cuh"
 #include "tc_common.cuh"
 
+#ifndef STMP_TC_GUNROLL
+#define STMP_TC_GUNROLL 2
+#endif
+#define STMP_TC_PRAGMA(x) _Pragma(#x)
+#define STMP_TC_UNROLL(n) STMP_TC_PRAGMA(unroll n)
+
 namespace stmp {
 namespace {
 
@@ -132,22 +138,37 @@ __device__ __forceinline__ float tanh_fast(float x) { return 2.0f * __fdividef(1
 // Four edges per group: one broadcast 32-bit load carries their four 8-bit source rows, one 128-bit load their values; the
 // next group's entries are fetched while the current group's four feature rows are in flight.  Summation order = CSR order
 // (the reference's scatter order), products by FMA as in the round-1 kernel.
-__device__ __forceinline__ float4 gather_groups(const float* __restrict__ Uj, const uint32_t* __restrict__ idx4,
+#if STMP_IMG_OFF16
+typedef uint2 img_idx_t;
+#else
+typedef uint32_t img_idx_t;
+#endif
+static_assert(kImgRowPitchBytes == TC_UP * 4, "graph image offsets are pre-scaled by the gather buffer's row pitch");
+static_assert(kImgZeroRow * kImgRowPitchBytes < 65536, "row offsets must fit 16 bits");
+__device__ __forceinline__ float4 ld4_off(const float* base, uint32_t byte_off) {
+  return *reinterpret_cast<const float4*>(reinterpret_cast<const unsigned char*>(base) + byte_off);
+}
+__device__ __forceinline__ float4 gather_groups(const float* __restrict__ Uj, const img_idx_t* __restrict__ idx4,
                                                 const float4* __restrict__ val4, int g0, int ng) {
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  uint32_t u = idx4[g0];
+  img_idx_t u = idx4[g0];
   float4 v = val4[g0];
-#ifdef STMP_TC_GUNROLL
-  _Pragma("unroll 2")
-#endif
-  for (int g = 1; g <= ng; ++g) {
-    const uint32_t un = idx4[g0 + g];      // (one spare group at the end of the arrays)
+  STMP_TC_UNROLL(STMP_TC_GUNROLL)    // 2: +6 % over the rolled loop (A/B on one box: 886 k -> 942 k snapshots/s) -- a task has 2-3 groups on average,
+  for (int g = 1; g <= ng; ++g) {    // the loop branch and its convergence barrier were 10 % of the issued instructions
+    const img_idx_t un = idx4[g0 + g];     // (one spare group at the end of the arrays)
     const float4 vn = val4[g0 + g];
     // (predicating the loads of pad entries off saves their wavefronts but costs more in compares / selects: measured -2 %, A/B on one box)
+#if STMP_IMG_OFF16
+    const float4 x0 = ld4_off(Uj, u.x & 0xffffu);
+    const float4 x1 = ld4_off(Uj, u.x >> 16);
+    const float4 x2 = ld4_off(Uj, u.y & 0xffffu);
+    const float4 x3 = ld4_off(Uj, u.y >> 16);
+#else
     const float4 x0 = ld4(Uj + (u & 0xffu) * TC_UP);
     const float4 x1 = ld4(Uj + ((u >> 8) & 0xffu) * TC_UP);
     const float4 x2 = ld4(Uj + ((u >> 16) & 0xffu) * TC_UP);
     const float4 x3 = ld4(Uj + (u >> 24) * TC_UP);
+#endif
     fma4(acc, v.x, x0);
     fma4(acc, v.y, x1);
     fma4(acc, v.z, x2);
@@ -184,7 +205,7 @@ __global__ void __launch_bounds__(512, 1) k_dcrnn_seq_tc(const TcParams p) {
   const uint16_t* s_wstart = reinterpret_cast<const uint16_t*>(img + p.gl.off_wstart);
   const uint16_t* s_wcount = reinterpret_cast<const uint16_t*>(img + p.gl.off_wcount);
   const uint32_t* s_wt = reinterpret_cast<const uint32_t*>(img + p.gl.off_wt);
-  const uint32_t* s_idx = reinterpret_cast<const uint32_t*>(img + p.gl.off_idx);
+  const img_idx_t* s_idx = reinterpret_cast<const img_idx_t*>(img + p.gl.off_idx);
   const float4* s_val = reinterpret_cast<const float4*>(img + p.gl.off_val);
   float* Bs = reinterpret_cast<float*>(smem + p.off_bias);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.off_bar);   // [0..3] MMA done (gemm*2+tile), [4] prologue TMA

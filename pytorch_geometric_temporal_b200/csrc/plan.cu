@@ -695,20 +695,24 @@ __global__ void __launch_bounds__(512) k_build_graph_image(const int* rp0, const
     const int2* cv = op ? cv1 : cv0;
     const int beg = rp[i], len = rp[i + 1] - beg;
     for (int g = 0; g < s_ng[task]; ++g) {
-      uint32_t u = 0;
+      uint32_t u = 0, w[2] = {0u, 0u};
       float v[4];
       for (int e = 0; e < 4; ++e) {
         const int k = 4 * g + e;
         const int2 c = k < len ? cv[beg + k] : make_int2(kImgZeroRow, 0);
         u |= ((uint32_t)c.x & 0xffu) << (8 * e);
+        w[e >> 1] |= ((uint32_t)c.x * kImgRowPitchBytes) << (16 * (e & 1));
         v[e] = __int_as_float(c.y);
       }
-      idx4[s_g0[task] + g] = u;
+      if (STMP_IMG_OFF16) reinterpret_cast<uint2*>(idx4)[s_g0[task] + g] = make_uint2(w[0], w[1]);
+      else idx4[s_g0[task] + g] = u;
       val4[s_g0[task] + g] = make_float4(v[0], v[1], v[2], v[3]);
     }
   }
   if (tid == 0) {   // the spare group the gather loop prefetches past the last task
-    idx4[s_g0[NT]] = kImgZeroRow * 0x01010101u;
+    const uint32_t z = (uint32_t)kImgZeroRow * kImgRowPitchBytes;
+    if (STMP_IMG_OFF16) reinterpret_cast<uint2*>(idx4)[s_g0[NT]] = make_uint2(z | (z << 16), z | (z << 16));
+    else idx4[s_g0[NT]] = kImgZeroRow * 0x01010101u;
     val4[s_g0[NT]] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }

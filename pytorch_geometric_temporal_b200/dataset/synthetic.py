@@ -62,3 +62,23 @@ def large_graph(num_nodes=10000, num_edges=100000, seed=0):
     ei = np.stack([k // num_nodes, k % num_nodes]).astype(np.int64)
     ew = rng.uniform(0.1, 1.0, size=num_edges).astype(np.float32)
     return ei, ew
+
+
+def banded_graph(num_nodes=10000, num_edges=100000, span=64, seed=0):
+    """Sensor-network-like graph: nodes numbered along the roads, every edge joins two nodes at most `span` apart (the kNN-by-road-distance
+    adjacency of METR-LA / PEMS-BAY after a locality-preserving ordering); directed, no loops, w~U(0.1,1)."""
+    rng = np.random.RandomState(seed)
+    keys = set()
+    while len(keys) < num_edges:
+        r = rng.randint(0, num_nodes, size=num_edges)
+        d = rng.randint(1, span + 1, size=num_edges) * rng.choice([-1, 1], size=num_edges)
+        c = r + d
+        ok = (c >= 0) & (c < num_nodes)
+        for a, b in zip(r[ok], c[ok]):
+            keys.add(int(a) * num_nodes + int(b))
+            if len(keys) == num_edges:
+                break
+    k = np.array(sorted(keys), dtype=np.int64)
+    ei = np.stack([k // num_nodes, k % num_nodes]).astype(np.int64)
+    ew = rng.uniform(0.1, 1.0, size=num_edges).astype(np.float32)
+    return ei, ew

@@ -11,11 +11,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 LIBDIR = os.path.join(ROOT, "pytorch_geometric_temporal_b200", "lib")
 VARIANTS = {
-    "h0": ["-DSTMP_LPT_HANDICAP=0"],
-    "h60": ["-DSTMP_LPT_HANDICAP=60"],
-    "c11": ["-DSTMP_LPT_A=1", "-DSTMP_LPT_B=1"],
-    "c32": ["-DSTMP_LPT_A=3", "-DSTMP_LPT_B=2"],
-    "gu2": ["-DSTMP_TC_GUNROLL=2"],
+    "off8": ["-DSTMP_IMG_OFF16=0"],
+    "gu1": ["-DSTMP_TC_GUNROLL=1"],
+    "gu3": ["-DSTMP_TC_GUNROLL=3"],
+    "gu4": ["-DSTMP_TC_GUNROLL=4"],
 }
 
 if sys.argv[1] == "build":

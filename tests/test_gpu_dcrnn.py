@@ -381,8 +381,11 @@ def test_persistent_backward_cluster_pair_equals_single_cta(n_nodes, cin):
     memory); every row's arithmetic is the same sequence as in the one-CTA kernel, so the gradients must agree to the last bit."""
     rng = np.random.default_rng(n_nodes)
     E = 6 * n_nodes
-    ei = torch.from_numpy(np.stack([rng.integers(0, n_nodes, E), rng.integers(0, n_nodes, E)])).to(DEV)
-    ew = torch.from_numpy(rng.random(E).astype(np.float32)).to(DEV)
+    ring = np.arange(n_nodes)                      # every node keeps an in- and an out-edge (a zero degree is 1/0 in the DConv norms)
+    src = np.concatenate([rng.integers(0, n_nodes, E), ring])
+    dst = np.concatenate([rng.integers(0, n_nodes, E), (ring + 1) % n_nodes])
+    ei = torch.from_numpy(np.stack([src, dst])).to(DEV)
+    ew = torch.from_numpy((rng.random(E + n_nodes) + 0.1).astype(np.float32)).to(DEV)
     torch.manual_seed(cin + n_nodes)
     X = torch.randn(5, 6, n_nodes, cin, device=DEV)
     w = torch.randn(5, 6, n_nodes, 32, device=DEV)
@@ -402,4 +405,5 @@ def test_persistent_backward_cluster_pair_equals_single_cta(n_nodes, cin):
         assert c1.get("k_dcrnn_bwd_seq[cluster2]", 0) - c0.get("k_dcrnn_bwd_seq[cluster2]", 0) == split
         grads.append([Xa.grad.clone()] + [p.grad.clone() for p in model.parameters()])
     for ga, gb in zip(*grads):
+        assert bool(torch.isfinite(ga).all())
         assert torch.equal(ga, gb), f"max abs diff {(ga - gb).abs().max():.3e}"
