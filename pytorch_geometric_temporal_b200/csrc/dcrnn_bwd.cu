@@ -146,9 +146,14 @@ struct BwdParams {
 
 // ---- thread-block-cluster helpers: with SPLIT == 2 a window is served by a CTA pair, each owning half of the node rows -----------------
 __device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ void cluster_sync_all() {
+__device__ __forceinline__ void cluster_sync_all() {          // data barrier: my (remote) shared-memory stores are visible to the pair behind it
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// execution-only barrier, split: "I am done READING buf" is signalled right after the gather phase (relaxed: no memory ordering, so the
+// phase's global stores are not drained -- the release form spent 14 % of the kernel in ERRBAR) and waited for only where the next GEMM is
+// about to overwrite the partner's buf, i.e. behind its FFMA loop.
+__device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 __device__ __forceinline__ uint32_t map_to_peer(const void* p, uint32_t peer) {
   uint32_t r;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(peer));
@@ -168,8 +173,8 @@ __device__ __forceinline__ void gemm_tiles(const float* __restrict__ dpT, int dp
                                            int r0, int RG, uint32_t peer_buf) {
   constexpr int CGN = NCOL / 8;
   const int tid = threadIdx.x;
-  if (tid >= RG * CGN) return;
-  const int rg = tid / CGN, cg = tid - rg * CGN;
+  const bool active = tid < RG * CGN;
+  const int rg = active ? tid / CGN : 0, cg = active ? tid - rg * CGN : 0;
   float acc[RT][8];
 #pragma unroll
   for (int i = 0; i < RT; ++i)
@@ -177,6 +182,7 @@ __device__ __forceinline__ void gemm_tiles(const float* __restrict__ dpT, int dp
     for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
   const float* ap = dpT + r0 + RT * rg;
   const float* wp = W + 8 * cg;
+  if (active) {
 #pragma unroll 2
   for (int k = 0; k < KD; ++k) {
     float a[RT];
@@ -192,6 +198,9 @@ __device__ __forceinline__ void gemm_tiles(const float* __restrict__ dpT, int dp
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
   }
+  }
+  if constexpr (PEER) cluster_wait();          // the pair has finished gathering from buf (signalled at the end of the previous phase)
+  if (!active) return;
 #pragma unroll
   for (int i = 0; i < RT; ++i) {
     const int off = (r0 + RT * rg + i) * NCOL + 8 * cg;
@@ -224,8 +233,9 @@ __device__ __forceinline__ void adjoint_at(const Gr<SG> (&g)[2], const float* __
 
 // SPLIT = 2: a thread-block cluster of two CTAs per window (launched when 2 B CTAs still fit the machine, i.e. at the reference's batch of 64
 // on 148 SMs): each CTA owns half of the node rows (a multiple of 8), runs the GEMMs / adjoints / gate derivatives of its rows only, and
-// pushes its rows of dS into the partner's buf so that the adjoint gathers stay local.  All four per-step barriers become cluster barriers
-// (the partner must have finished reading buf before it is overwritten, and finished writing it before it is gathered).
+// pushes its rows of dS into the partner's buf so that the adjoint gathers stay local.  Behind a GEMM the pair meets at a release / acquire
+// cluster barrier (dS visible); behind a gather phase each CTA only signals "done reading buf" (relaxed arrival) and the matching wait sits
+// in the next GEMM between its FFMA loop and its stores.
 template <int CIN, bool SG, int SPLIT>
 __global__ void __launch_bounds__(kBwdThreads, 1) k_dcrnn_bwd_seq(BwdParams p) {
   constexpr int C = CIN + kCo, NCOL = ncol_of(CIN), V = (C % 2 == 0) ? 2 : 1, CP = C / V, RT = SPLIT == 2 ? 4 : 8;
@@ -273,8 +283,11 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_dcrnn_bwd_seq(BwdParams p) {
   for (int i = tid; i < 2 * kCo * dpp; i += kBwdThreads) dpT[i] = 0.f;
   uint32_t peer_buf = 0;
   if constexpr (SPLIT == 2) peer_buf = map_to_peer(buf, (uint32_t)(hrank ^ 1));
-  auto sync_all = [&]() { if constexpr (SPLIT == 2) cluster_sync_all(); else __syncthreads(); };
-  sync_all();
+  // data_sync: behind a GEMM (dS of both halves complete and visible); free_sync: behind a gather phase (block barrier for dpT / G, plus the
+  // relaxed "done reading buf" arrival that the next GEMM waits for just before it stores)
+  auto data_sync = [&]() { if constexpr (SPLIT == 2) cluster_sync_all(); else __syncthreads(); };
+  auto free_sync = [&]() { if constexpr (SPLIT == 2) cluster_arrive_relaxed(); __syncthreads(); };
+  data_sync();
   // ---- open step T-1
   const long long bT = (long long)b * T;
   for (int i = r_lo * kCo + tid; i < r_hi * kCo; i += kBwdThreads) {
@@ -287,7 +300,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_dcrnn_bwd_seq(BwdParams p) {
     dpT[cc * dpp + n] = d;
     p.dph_all[(((long long)(T - 1) * p.B + b) * N) * kCo + i] = d;
   }
-  sync_all();
+  free_sync();
 #pragma unroll 1
   for (int t = T - 1; t >= 0; --t) {
     const long long bt = bT + t;
@@ -295,7 +308,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_dcrnn_bwd_seq(BwdParams p) {
     const float* hprev = t > 0 ? p.out + (bt - 1) * NH : (p.h0 ? p.h0 + (long long)b * NH : nullptr);
     // dS2 = dpre_h @ Wh^T
     gemm_tiles<NCOL, kCo, RT, SPLIT == 2>(dpT, dpp, Wh, buf, g_r0, g_RG, peer_buf);
-    sync_all();
+    data_sync();
     // dU2 = adjoint; d pre-activations of z and r; partial carry  g*Z + dHR*R
     float* dpzr = p.dpzr_all + (((long long)t * p.B + b) * N) * 2 * kCo;
 #pragma unroll 1
@@ -340,10 +353,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_dcrnn_bwd_seq(BwdParams p) {
         }
       }
     }
-    sync_all();
+    free_sync();
     // dS1 = dpre_zr @ Wzr^T
     gemm_tiles<NCOL, 2 * kCo, RT, SPLIT == 2>(dpT, dpp, Wzr, buf, g_r0, g_RG, peer_buf);
-    sync_all();
+    data_sync();
     // dU1 = adjoint; dX_t; dL/dH_{t-1}; open step t-1
     const float* stn = st - 3 * NH;          // stash of step t-1 (only dereferenced when t > 0)
     float* dphn = p.dph_all + (((long long)(t - 1) * p.B + b) * N) * kCo;
@@ -393,8 +406,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_dcrnn_bwd_seq(BwdParams p) {
         }
       }
     }
-    sync_all();
+    free_sync();
   }
+  if constexpr (SPLIT == 2) cluster_wait();      // pairs with the last arrival; nobody leaves while the partner may still be in its phase
 }
 
 inline size_t seq_smem_base(int N, int cin) {

@@ -9,9 +9,9 @@
 //   wstart   [16][4]  u16  first warp-task of warp w in segment s = 2 * (MMA row tile of the destination: rows <128 | >=128) + operator
 //   wcount   [16][4]  u16  number of warp-tasks of warp w in segment s
 //   wt       [n_warp_tasks][4] u32 task descriptors: row | op << 8 | n_groups << 9 | first_group << 16  (0xFFFFFFFF = none)
-//   idx4     [n_groups + 1]  four source rows of an edge group (pad entries point at the all-zero row 207): as 16-bit BYTE OFFSETS of the
-//                            rows in the gather buffer (row * kImgRowPitchBytes; one 64-bit load, the address of a row is one extract +
-//                            one add) -- or, with STMP_IMG_OFF16=0, as 8-bit row numbers in one u32 (shift + mask + two multiply-adds)
+//   idx4     [n_groups + 1]  four source rows of an edge group (pad entries point at the all-zero row 207): 8-bit row numbers in one u32
+//                            (shift + mask + two multiply-adds per address) -- or, built with -DSTMP_IMG_OFF16=1, 16-bit BYTE OFFSETS of the
+//                            rows in the gather buffer (one 64-bit load, one extract + one add per address; measured 0.6 % slower)
 //   val4     [n_groups + 1]  float4: their four values (pad = 0)
 //
 // Edge order inside a task is the plan's CSR order (= the reference's scatter order).  Warp-tasks are dealt to warps by
@@ -29,7 +29,7 @@ constexpr int kImgSegs = 4;
 constexpr int kImgZeroRow = 207;
 constexpr uint32_t kImgNoTask = 0xFFFFFFFFu;
 #ifndef STMP_IMG_OFF16
-#define STMP_IMG_OFF16 1
+#define STMP_IMG_OFF16 0     // A/B on one box (tests/perf/flagship_variants.py): 8-bit rows 942.8 k snapshots/s, 16-bit pre-scaled offsets 937.5 k
 #endif
 constexpr int kImgIdxBytes = STMP_IMG_OFF16 ? 8 : 4;     // bytes per edge group in idx4
 constexpr int kImgRowPitchBytes = 144;                  // pitch of the kernel's gather buffer (dcrnn_seq_tc.cu: TC_UP floats)

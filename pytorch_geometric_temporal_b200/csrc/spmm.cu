@@ -13,6 +13,9 @@
 #include "common.cuh"
 
 namespace stmp {
+int g_spmm_rows_per_group = 8;   // consecutive destination rows walked by one lane group (stmp_set_option("spmm_rows_per_group")): cfg5 probe
+                                 // 1: 1451 GB/s, 4: 1810, 8: 1855, 16: 1700 on the random graph; 1533 / 1920 / 1986 / 1879 on a banded one
+int g_spmm_block = 256;          // threads per CTA (stmp_set_option("spmm_block"): 256 or 1024)
 int g_spmm_variant = -1;   // 0 (default): k_spmm register gather; 1 / 2: k_spmm_tma with 8 / 16 staged rows per warp
 namespace {
 
@@ -55,16 +58,20 @@ struct SpmmArgs {
 };
 
 // G lanes per row (power of two, <=32).  blockDim.x = 256.
-template <int VEC>
-__global__ void __launch_bounds__(256) k_spmm(SpmmArgs a, int G, int log2G) {
+// A CTA owns `rpg` * (256 / G) CONSECUTIVE destination rows of one batch element and walks them 256 / G rows at a time: with a node
+// numbering that has locality (sensor networks numbered along the roads) the source rows of neighbouring destinations overlap and are
+// re-used out of L1 instead of crossing the L2 -> SM crossbar once per edge.
+template <int VEC, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_spmm(SpmmArgs a, int G, int log2G, int rpg, int blocks_per_b) {
   const int lane_in_group = threadIdx.x & (G - 1);
-  const long long group = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> log2G;
-  const long long total = a.batch * (long long)a.n;
-  if (group >= total) return;
-  const int i = (int)(group % a.n);
-  const long long b = group / a.n;
+  const int gpc = BLOCK >> log2G;
+  const long long b = blockIdx.x / blocks_per_b;
+  const int blk = blockIdx.x - (int)(b * blocks_per_b);
   const float* xb = a.x + b * a.bsx;
   const float* attb = a.att ? a.att + b * (long long)a.n * a.att_ld : nullptr;
+  for (int r = 0; r < rpg; ++r) {
+  const int i = (blk * rpg + r) * gpc + (threadIdx.x >> log2G);
+  if (i >= a.n) return;
   const int beg = a.rowptr[i], end = a.rowptr[i + 1];
 
   for (int f0 = lane_in_group * VEC; f0 < a.f; f0 += G * VEC) {
@@ -116,6 +123,7 @@ __global__ void __launch_bounds__(256) k_spmm(SpmmArgs a, int G, int log2G) {
       for (int v = 0; v < VEC; ++v) o[v] = (a.alpha == 1.0f) ? acc[v] : __fmul_rn(a.alpha, acc[v]);
     }
     st_vec<VEC>(a.y + b * a.bsy + (long long)i * a.ldy + f0, o);
+  }
   }
 }
 
@@ -271,8 +279,14 @@ static int spmm_impl(const stmp_plan* plan, int op, int transposed, int64_t batc
   int G = 1, lg = 0;
   while (G < lanes && G < 32) { G <<= 1; ++lg; }
   long long groups = batch * (long long)c.n;
-  long long threads = groups * G;
-  long long blocks = (threads + 255) / 256;
+  const int blk = g_spmm_block == 1024 ? 1024 : 256;
+  const int gpc = blk / G;
+  int rpg = g_spmm_rows_per_group;
+  if (rpg < 1) rpg = 1;
+  // small problems keep one row per group: the row blocks must still fill the machine (>= 8 CTAs of 256 threads per SM's worth of blocks)
+  while (rpg > 1 && batch * ((c.n + (long long)gpc * rpg - 1) / ((long long)gpc * rpg)) < 1184) rpg >>= 1;
+  const int blocks_per_b = (int)((c.n + (long long)gpc * rpg - 1) / ((long long)gpc * rpg));
+  long long blocks = batch * (long long)blocks_per_b;
   STMP_REQUIRE(blocks < (1ll << 31), STMP_ESHAPE, "stmp_spmm: problem too large for one launch");
   cudaStream_t st = (cudaStream_t)stream;
   if (g_spmm_variant < 0) {
@@ -308,9 +322,15 @@ static int spmm_impl(const stmp_plan* plan, int op, int transposed, int64_t batc
       return STMP_OK;
     }
   }
-  if (vec == 4) k_spmm<4><<<(unsigned)blocks, 256, 0, st>>>(a, G, lg);
-  else if (vec == 2) k_spmm<2><<<(unsigned)blocks, 256, 0, st>>>(a, G, lg);
-  else k_spmm<1><<<(unsigned)blocks, 256, 0, st>>>(a, G, lg);
+  if (blk == 1024) {
+    if (vec == 4) k_spmm<4, 1024><<<(unsigned)blocks, 1024, 0, st>>>(a, G, lg, rpg, blocks_per_b);
+    else if (vec == 2) k_spmm<2, 1024><<<(unsigned)blocks, 1024, 0, st>>>(a, G, lg, rpg, blocks_per_b);
+    else k_spmm<1, 1024><<<(unsigned)blocks, 1024, 0, st>>>(a, G, lg, rpg, blocks_per_b);
+  } else {
+    if (vec == 4) k_spmm<4, 256><<<(unsigned)blocks, 256, 0, st>>>(a, G, lg, rpg, blocks_per_b);
+    else if (vec == 2) k_spmm<2, 256><<<(unsigned)blocks, 256, 0, st>>>(a, G, lg, rpg, blocks_per_b);
+    else k_spmm<1, 256><<<(unsigned)blocks, 256, 0, st>>>(a, G, lg, rpg, blocks_per_b);
+  }
   STMP_LAUNCH_OK("k_spmm");
   return STMP_OK;
 }

@@ -5,7 +5,7 @@
 //                               k_dcrnn_bwd_seq.  What autograd records for the `torch.matmul(basis, W)` / `+ bias` of
 //                               torch_geometric_temporal/nn/recurrent/dcrnn.py:86-111 once per step, per gate, per diffusion hop.
 //                               The contraction axis is the long one (T*B*N rows = 159 k at the reference's batch size), the output is
-//                               102 x 96: every CTA takes a strided set of 32-row tiles (TMA bulk copies, two stages), keeps an 8 x 8
+//                               102 x 96: every CTA takes a strided set of 16-row tiles (TMA bulk copies, four stages), keeps an 8 x 8
 //                               register tile per thread (4 LDS.128 per 64 FFMA) and writes ONE partial; a second launch sums the
 //                               partials in a fixed order (deterministic) and scatters them straight into the (2, K, C, Co) weight
 //                               gradients (block 0 of the stack feeds W[0,0] and W[1,0]).
@@ -18,7 +18,8 @@
 namespace stmp {
 namespace {
 
-constexpr int kWgTK = 32;            // rows per staged tile
+constexpr int kWgTK = 16;            // rows per staged tile
+constexpr int kWgStages = 4;         // tiles in flight per CTA: 3 x 19 KB x 2 CTAs per SM keeps ~115 KB per SM on the wire (2 stages of 32 rows were load-latency bound)
 constexpr int kWgThreads = 192;      // >= 12 * ceil(3C/8) for cin <= 4
 constexpr int kCo = 32;
 
@@ -36,8 +37,11 @@ __global__ void __launch_bounds__(kWgThreads, 2) k_dcrnn_wgrad(WgradParams p) {
   const int ld = p.ld, tid = threadIdx.x, MG = p.MG;
   const int stage_floats = kWgTK * (2 * ld + 3 * kCo);
   float* stages = reinterpret_cast<float*>(smraw);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smraw + (size_t)2 * stage_floats * 4);
-  if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); fence_mbar_init(); }
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smraw + (size_t)kWgStages * stage_floats * 4);
+  if (tid == 0) {
+    for (int i = 0; i < kWgStages; ++i) mbar_init(&bars[i], 1);
+    fence_mbar_init();
+  }
   __syncthreads();
 
   auto issue = [&](int tile, int s) {
@@ -69,12 +73,16 @@ __global__ void __launch_bounds__(kWgThreads, 2) k_dcrnn_wgrad(WgradParams p) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
   }
-  if (tid == 0 && (int)blockIdx.x < p.n_tiles) issue(blockIdx.x, 0);
+  if (tid == 0) {
+    for (int q = 0; q < kWgStages - 1; ++q)
+      if ((int)blockIdx.x + q * (int)gridDim.x < p.n_tiles) issue(blockIdx.x + q * gridDim.x, q);
+  }
   int it = 0;
   for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
-    const int s = it & 1;
-    if (tid == 0 && tile + (int)gridDim.x < p.n_tiles) issue(tile + gridDim.x, s ^ 1);   // stage s^1 was released by the barrier below
-    mbar_wait(&bars[s], (it >> 1) & 1);
+    const int s = it % kWgStages;
+    // the stage refilled here was consumed in iteration it - 1 and released by the barrier at its end
+    if (tid == 0 && tile + (kWgStages - 1) * (int)gridDim.x < p.n_tiles) issue(tile + (kWgStages - 1) * gridDim.x, (it + kWgStages - 1) % kWgStages);
+    mbar_wait(&bars[s], (it / kWgStages) & 1);
     if (active) {
       const long long r0 = (long long)tile * kWgTK;
       const int nr = (int)((p.rows - r0) < kWgTK ? (p.rows - r0) : kWgTK);
@@ -115,39 +123,49 @@ __global__ void __launch_bounds__(kWgThreads, 2) k_dcrnn_wgrad(WgradParams p) {
   }
 }
 
-// Sum the partials in launch order and scatter: gate weights W (2, 2, C, Co) <- stacked rows (block 0 -> W[0,0] and W[1,0]; block 1 + o -> W[o,1]).
+// Sum the partials in a fixed order and scatter: gate weights W (2, 2, C, Co) <- stacked rows (block 0 -> W[0,0] and W[1,0]; block 1 + o -> W[o,1]).
+// A block covers 32 consecutive outputs; its 8 warps each sum a contiguous eighth of the partials, then thread (0, x) adds the 8 sub-sums
+// in warp order -- the same association whatever the launch, hence bit-reproducible.
 __global__ void __launch_bounds__(256) k_dcrnn_wgrad_reduce(int parts, int MG, int C, const float* __restrict__ partial, float* __restrict__ gz,
                                                             float* __restrict__ gr, float* __restrict__ gh, float* __restrict__ gbz,
                                                             float* __restrict__ gbr, float* __restrict__ gbh) {
+  __shared__ float sub[8][32];
   const int per_w = 4 * C * kCo, total = 3 * per_w + 3 * kCo;
-  const int i = blockIdx.x * 256 + threadIdx.x;
-  if (i >= total) return;
+  const int x = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + x;
   const size_t stride = (size_t)MG * 8 * 3 * kCo + 3 * kCo;
-  size_t src;
-  float* dst;
+  size_t src = 0;
+  float* dst = nullptr;
   if (i < 3 * per_w) {
     const int gate = i / per_w, r = i - gate * per_w;            // 0 = z, 1 = r, 2 = h
     const int o = r / (2 * C * kCo), r2 = r - o * 2 * C * kCo, k = r2 / (C * kCo), r3 = r2 - k * C * kCo, c = r3 / kCo, j = r3 - c * kCo;
     const int m = (k == 0 ? 0 : 1 + o) * C + c;
     src = gate == 2 ? (size_t)MG * 8 * 2 * kCo + (size_t)m * kCo + j : (size_t)m * 2 * kCo + gate * kCo + j;
     dst = (gate == 0 ? gz : gate == 1 ? gr : gh) + r;
-  } else {
+  } else if (i < total) {
     const int b = i - 3 * per_w;                                 // bias sums are stored z | r | h
     src = (size_t)MG * 8 * 3 * kCo + b;
     float* base = b < kCo ? gbz : (b < 2 * kCo ? gbr : gbh);
-    if (!base) return;
-    dst = base + (b & (kCo - 1));
+    dst = base ? base + (b & (kCo - 1)) : nullptr;
   }
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  int q = 0;
-  for (; q + 4 <= parts; q += 4) {
-    s0 += partial[(size_t)q * stride + src];
-    s1 += partial[(size_t)(q + 1) * stride + src];
-    s2 += partial[(size_t)(q + 2) * stride + src];
-    s3 += partial[(size_t)(q + 3) * stride + src];
+  const int per = (parts + 7) / 8, q0 = w * per, q1 = (q0 + per < parts) ? q0 + per : parts;
+  float s0 = 0.f, s1 = 0.f;
+  if (dst) {
+    int q = q0;
+    for (; q + 2 <= q1; q += 2) {
+      s0 += partial[(size_t)q * stride + src];
+      s1 += partial[(size_t)(q + 1) * stride + src];
+    }
+    if (q < q1) s0 += partial[(size_t)q * stride + src];
   }
-  for (; q < parts; ++q) s0 += partial[(size_t)q * stride + src];
-  *dst = (s0 + s1) + (s2 + s3);
+  sub[w][x] = s0 + s1;
+  __syncthreads();
+  if (w == 0 && dst) {
+    float t = sub[0][x];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) t += sub[k][x];
+    *dst = t;
+  }
 }
 
 // ---- Adam over one flat buffer -------------------------------------------------------------------------------------------------
@@ -210,12 +228,12 @@ extern "C" int stmp_dcrnn_bwd_wgrad(int64_t cin, int64_t cout, int64_t K, int64_
   p.partial = reinterpret_cast<float*>(workspace);
   int grid = wgrad_grid();
   if (p.n_tiles < grid) grid = p.n_tiles > 0 ? p.n_tiles : 1;
-  const int smem = 2 * kWgTK * (2 * (int)ld + 3 * kCo) * 4 + 64;
+  const int smem = kWgStages * kWgTK * (2 * (int)ld + 3 * kCo) * 4 + 64;
   STMP_CUDA_OK(cudaFuncSetAttribute(k_dcrnn_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   k_dcrnn_wgrad<<<grid, kWgThreads, smem, st>>>(p);
   STMP_LAUNCH_OK("k_dcrnn_wgrad");
   const int total = 3 * 4 * C * kCo + 3 * kCo;
-  k_dcrnn_wgrad_reduce<<<(total + 255) / 256, 256, 0, st>>>(grid, MG, C, p.partial, gz, gr, gh, gbz, gbr, gbh);
+  k_dcrnn_wgrad_reduce<<<(total + 31) / 32, 256, 0, st>>>(grid, MG, C, p.partial, gz, gr, gh, gbz, gbr, gbh);
   STMP_LAUNCH_OK("k_dcrnn_wgrad_reduce");
   return STMP_OK;
 }

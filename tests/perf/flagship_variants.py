@@ -11,9 +11,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 LIBDIR = os.path.join(ROOT, "pytorch_geometric_temporal_b200", "lib")
 VARIANTS = {
-    "off8": ["-DSTMP_IMG_OFF16=0"],
+    "off16": ["-DSTMP_IMG_OFF16=1"],
     "gu1": ["-DSTMP_TC_GUNROLL=1"],
-    "gu3": ["-DSTMP_TC_GUNROLL=3"],
     "gu4": ["-DSTMP_TC_GUNROLL=4"],
 }
 
