@@ -200,9 +200,9 @@ def spmm_probe(dev, pk):
     out = {"workload": "SpMM N=10000 nnz=%d F=128 batch=32 (in 164 MB + out 164 MB > L2)" % nnz, "ms": ms,
            "algorithmic_bytes": bytes_alg, "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
            "l2_gather_bytes": gather, "l2_to_sm_gbs": (gather + bytes_alg) / (ms * 1e-3) / 1e9,
-           "note": "random graph: bound by the L2->SM delivery of the gathered rows (5.5x the algorithmic bytes), see DESIGN.md section 3"}
+           "note": "random graph: the gathered rows (5.5x the algorithmic bytes) leave L2 at its throughput cap (~6300 B/clk); l2_to_sm_gbs is that rate, see DESIGN.md section 3"}
     nnz2, bytes2, ms2, gbs2 = run(*synthetic.banded_graph(N, 100000, 64, 0))
-    out["banded_graph"] = {"workload": "same sizes, every edge within 64 node ids (sensor-network-like ordering): gathered rows are re-used out of L1",
+    out["banded_graph"] = {"workload": "same sizes, every edge within 64 node ids (sensor-network-like ordering)",
                            "nnz": nnz2, "ms": ms2, "achieved": gbs2, "frac": gbs2 / pk["hbm_gbs"]}
     return out
 
