@@ -72,8 +72,30 @@ def test_flat_adam_cuda_graph_replay_counts_steps_on_device():
         torch.testing.assert_close(pa, pb, rtol=2e-5, atol=1e-6)
 
 
-@pytest.mark.parametrize("cin,rows", [(2, 12 * 5 * 207), (1, 1000), (4, 207 * 3 + 5)])
-def test_dcrnn_wgrad_vs_float64(cin, rows):
+@pytest.mark.parametrize("tc", [0, 1])
+@pytest.mark.parametrize("cin,rows", [(2, 12 * 5 * 207), (1, 1000), (4, 207 * 3 + 5), (2, 7)])
+def test_dcrnn_wgrad_vs_float64(cin, rows, tc):
+    """tc = 1: the tcgen05 contraction (TF32 hi/lo split, MN-major operands); tc = 0: the fp32 FFMA kernel."""
+    _lib.set_option("dcrnn_wgrad_tc", tc)
+    try:
+        _wgrad_case(cin, rows, "k_dcrnn_wgrad_tc" if tc else "k_dcrnn_wgrad")
+    finally:
+        _lib.set_option("dcrnn_wgrad_tc", WGRAD_TC_DEFAULT)
+
+
+def test_dcrnn_wgrad_small_gradients_keep_their_precision():
+    """d pre-activations of a mean loss are ~1e-6: the operand split must not lose them (an fp16 split would flush them to subnormals)."""
+    _lib.set_option("dcrnn_wgrad_tc", 1)
+    try:
+        _wgrad_case(2, 4 * 207, "k_dcrnn_wgrad_tc", dp_scale=1e-6)
+    finally:
+        _lib.set_option("dcrnn_wgrad_tc", WGRAD_TC_DEFAULT)
+
+
+WGRAD_TC_DEFAULT = 1
+
+
+def _wgrad_case(cin, rows, kernel, dp_scale=1.0):
     torch.manual_seed(cin)
     Co, K = 32, 2
     C = cin + Co
@@ -82,9 +104,11 @@ def test_dcrnn_wgrad_vs_float64(cin, rows):
     S2 = torch.full((rows, 1, ld), float("nan"), device=DEV)
     S1[..., :3 * C] = torch.randn(rows, 1, 3 * C, device=DEV)
     S2[..., :3 * C] = torch.randn(rows, 1, 3 * C, device=DEV)
-    dpzr = torch.randn(rows, 2 * Co, device=DEV)
-    dph = torch.randn(rows, Co, device=DEV)
+    dpzr = torch.randn(rows, 2 * Co, device=DEV) * dp_scale
+    dph = torch.randn(rows, Co, device=DEV) * dp_scale
+    c0 = _lib.path_counters().get(kernel, 0)
     gz, gr, gh, gbz, gbr, gbh = ops.dcrnn_bwd_wgrad(cin, K, S1, S2, dpzr, dph, True)
+    assert _lib.path_counters().get(kernel, 0) == c0 + 1
     s1, s2 = S1[:, 0, :3 * C].double(), S2[:, 0, :3 * C].double()
     dWzr, dWh = s1.t() @ dpzr.double(), s2.t() @ dph.double()
 
@@ -92,7 +116,7 @@ def test_dcrnn_wgrad_vs_float64(cin, rows):
         blk = d.view(3, C, Co)
         return torch.stack([torch.stack([blk[0], blk[1]]), torch.stack([blk[0], blk[2]])])
 
-    scale = (rows ** 0.5)
+    scale = (rows ** 0.5) * dp_scale
     for got, ref in ((gz, unstack(dWzr[:, :Co])), (gr, unstack(dWzr[:, Co:])), (gh, unstack(dWh))):
         assert got.shape == (2, K, C, Co)
         assert float((got.double() - ref).abs().max()) < 2e-6 * scale * 4
