@@ -228,7 +228,8 @@ int stmp_dcrnn_bwd_seq(const stmp_plan* plan, int64_t B, int64_t T, int64_t cin,
  * `+ bias` of dcrnn.py:86-111 across steps, gates and hops): S1 / S2 (rows, ld) are stmp_dcrnn_bwd_basis' bases (ld = 3(cin+cout) rounded
  * up to 8), dpzr (rows, 2cout) / dph (rows, cout) stmp_dcrnn_bwd_seq's d pre-activations.  Writes gz / gr / gh in the module's
  * (2, K, cin+cout, cout) layout and the bias gradients (nullable).  Two launches (per-CTA partials, fixed-order reduction: deterministic);
- * workspace of stmp_dcrnn_bwd_wgrad_workspace_bytes(cin) bytes.  K = 2, cout = 32, cin <= 4. */
+ * the contraction runs on tcgen05 (kind::tf32, MN-major operands, TF32 hi/lo split; stmp_set_option("dcrnn_wgrad_tc", 0) selects the
+ * fp32 FFMA kernel).  Workspace of stmp_dcrnn_bwd_wgrad_workspace_bytes(cin) bytes.  K = 2, cout = 32, cin <= 4. */
 int64_t stmp_dcrnn_bwd_wgrad_workspace_bytes(int64_t cin);
 int stmp_dcrnn_bwd_wgrad(int64_t cin, int64_t cout, int64_t K, int64_t rows, int64_t ld, const float* S1, const float* S2,
                          const float* dpzr, const float* dph, void* workspace, float* gz, float* gr, float* gh, float* gbz,
@@ -335,7 +336,8 @@ int stmp_window_gather(const float* series, int64_t t_total, int64_t row_elems, 
 
 /* Run-time switches for tests: "dcrnn_tc" = 1 (tcgen05 kernel, default) / 0 (FFMA kernel) behind stmp_dcrnn_seq_fwd; "spmm_variant" = 0
  * (register gather, default) / 1, 2 (TMA-staged rows, 8 / 16 per warp); "dcrnn_bwd_all_cin" = 1 (default) / 0 (persistent backward only for cin == 2); "dcrnn_bwd_split" = 1 (default: a 2-CTA cluster per window
- * when 2 B <= SM count) / 0 (one CTA per window). */
+ * when 2 B <= SM count) / 0 (one CTA per window); "dcrnn_wgrad_tc" = 1 (default, tcgen05) / 0 (FFMA); "spmm_rows_per_group" (default 8) and
+ * "spmm_block" (256 / 1024): the SpMM's row blocking. */
 int stmp_set_option(const char* name, int value);
 
 /* ---- misc ---------------------------------------------------------------------------------------- */
