@@ -224,6 +224,17 @@ int stmp_dcrnn_bwd_seq(const stmp_plan* plan, int64_t B, int64_t T, int64_t cin,
                        const float* out, const float* h0, const float* stash, const float* whsT, const float* wzrT,
                        float* dph_all, float* dpzr_all, float* dx, float* dh0, void* stream);
 
+/* Backward of stmp_tgcn_attn_fwd for H = NULL (the training configuration of the reference's A3TGCN2 example; what autograd records for
+ * attentiontemporalgcn.py:130-157 / temporalgcn.py:187-233 over all periods): given gout (B, N, 32) it recomputes A^X and the gates and
+ * reduces dA (fin, 96; the r-gate columns are zero: R multiplies H = 0), dc (96) and dprobs (periods; nullable when probs is NULL) over all
+ * (batch row, node, period).  The gradients of the module parameters follow from the (differentiable, host-side) folding A = (L1 W)^T,
+ * c = L1 b + l and probs = softmax(attention).  No gradient w.r.t. X.  Two launches (per-CTA partials, fixed-order reduction);
+ * workspace of stmp_tgcn_attn_bwd_workspace_bytes(plan, B) bytes. */
+int64_t stmp_tgcn_attn_bwd_workspace_bytes(const stmp_plan* plan, int64_t B);
+int stmp_tgcn_attn_bwd(const stmp_plan* plan, int64_t B, int64_t fin, int64_t periods, const float* x, const float* A,
+                       const float* c, const float* probs, const float* gout, void* workspace, float* dA, float* dc,
+                       float* dprobs, void* stream);
+
 /* Weight / bias gradients of the three DCRNN gates over all (t, b, n) rows (what autograd accumulates for the `matmul(basis, W)` and
  * `+ bias` of dcrnn.py:86-111 across steps, gates and hops): S1 / S2 (rows, ld) are stmp_dcrnn_bwd_basis' bases (ld = 3(cin+cout) rounded
  * up to 8), dpzr (rows, 2cout) / dph (rows, cout) stmp_dcrnn_bwd_seq's d pre-activations.  Writes gz / gr / gh in the module's

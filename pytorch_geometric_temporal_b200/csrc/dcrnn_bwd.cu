@@ -16,7 +16,7 @@
 //
 // Everything here is fp32 FFMA: the per-window GEMMs are 207x32x102 / 207x64x102, the problem is latency-bound on
 // the serial recurrence with 64 windows per step (the reference's batch size), not throughput-bound.
-#include "common.cuh"
+#include "dcrnn_common.cuh"
 
 namespace stmp {
 int g_bwd_all_cin = 1;
@@ -183,7 +183,10 @@ __device__ __forceinline__ void gemm_tiles(const float* __restrict__ dpT, int dp
   const float* ap = dpT + r0 + RT * rg;
   const float* wp = W + 8 * cg;
   if (active) {
-#pragma unroll 2
+  // 4-row tiles (the cluster-pair variant) have half the FMAs per operand load: their k loop is unrolled 4 deep to keep the LDS latency covered
+  // (the profile of the first version showed 77 % of the FMA line's stalls on the short scoreboard); packed FFMA2 halves the issue slots
+  // (bit-identical: two independent IEEE fmas per instruction)
+#pragma unroll (RT == 4 ? 4 : 2)
   for (int k = 0; k < KD; ++k) {
     float a[RT];
 #pragma unroll
@@ -196,7 +199,10 @@ __device__ __forceinline__ void gemm_tiles(const float* __restrict__ dpT, int dp
 #pragma unroll
     for (int i = 0; i < RT; ++i)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+      for (int j = 0; j < 8; j += 2) {
+        const float2 r = ffma2(make_float2(a[i], a[i]), make_float2(w[j], w[j + 1]), make_float2(acc[i][j], acc[i][j + 1]));
+        acc[i][j] = r.x; acc[i][j + 1] = r.y;
+      }
   }
   }
   if constexpr (PEER) cluster_wait();          // the pair has finished gathering from buf (signalled at the end of the previous phase)

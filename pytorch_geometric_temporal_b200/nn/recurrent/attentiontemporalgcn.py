@@ -23,6 +23,16 @@ class _A3Base(torch.nn.Module):
             if X.dim() == 3:                                        # A3TGCN: (N,F,P), H (N,out)
                 return ops.tgcn_attn_fwd(plan, X.unsqueeze(0), A, Bm, c, probs, H, h_shared=True)[0]
             return ops.tgcn_attn_fwd(plan, X, A, Bm, c, probs, H)   # A3TGCN2: (B,N,F,P), H (B,N,out)
+        if base._attn_train_ok(X, H, P):
+            # training without an incoming state: the same launch + a hand-written backward (gates recomputed, gradients of the folded
+            # weights and of the attention probabilities reduced on the device)
+            N, F = X.shape[-3], X.shape[-2]
+            plan = base._plan(edge_index, edge_weight, N)
+            A, Bm, c = base._fold3()
+            probs = torch.nn.functional.softmax(self._attention, dim=0)
+            if X.dim() == 3:
+                return ops.tgcn_attn_train(plan, X.unsqueeze(0), A, Bm, c, probs)[0]
+            return ops.tgcn_attn_train(plan, X, A, Bm, c, probs)
         # (..., N, F, P) -> (P, ..., N, F): periods become the leading batch axis of the SpMM
         Xp = X.movedim(-1, 0).contiguous()
         lead = Xp.shape[:-2]

@@ -192,6 +192,41 @@ def tgcn_attn_fwd(plan: GraphPlan, x: torch.Tensor, A: torch.Tensor, Bm: torch.T
     return out
 
 
+class _TgcnAttnFn(torch.autograd.Function):
+    """Training form of the fused A3TGCN(2) / TGCN(2) forward for H = None: forward = `stmp_tgcn_attn_fwd`, backward =
+    `stmp_tgcn_attn_bwd` (gates recomputed, gradients of the folded weights A, c and of the attention probabilities reduced on the
+    device).  No gradient w.r.t. X."""
+
+    @staticmethod
+    def forward(ctx, plan, x, A, Bm, c, probs):
+        out = tgcn_attn_fwd(plan, x, A.detach(), Bm.detach(), c.detach(), None if probs is None else probs.detach(), None)
+        ctx.plan, ctx.has_probs = plan, probs is not None
+        ctx.save_for_backward(x, A.detach(), c.detach(), probs.detach() if probs is not None else x.new_empty(0))
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, A, c, probs = ctx.saved_tensors
+        plan = ctx.plan
+        B, N, fin, P = x.shape
+        gout = _f32c(gout, "gout")
+        dev = x.device
+        ws = torch.empty(int(_lib.lib().stmp_tgcn_attn_bwd_workspace_bytes(plan.handle, B)), dtype=torch.uint8, device=dev)
+        dA = torch.empty(fin, 96, dtype=torch.float32, device=dev)
+        dc = torch.empty(96, dtype=torch.float32, device=dev)
+        dprobs = torch.empty(P, dtype=torch.float32, device=dev) if ctx.has_probs else None
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().stmp_tgcn_attn_bwd(plan.handle, B, fin, P, _lib.ptr(_f32c(x, "X")), _lib.ptr(_f32c(A, "A")), _lib.ptr(_f32c(c, "c")),
+                                                     _lib.ptr(_f32c(probs, "probs")) if ctx.has_probs else None, _lib.ptr(gout), _lib.ptr(ws),
+                                                     _lib.ptr(dA), _lib.ptr(dc), _lib.ptr(dprobs), _lib.stream_ptr()))
+        return None, None, dA, None, dc, dprobs
+
+
+def tgcn_attn_train(plan: GraphPlan, x, A, Bm, c, probs=None) -> torch.Tensor:
+    """Differentiable (w.r.t. A, c, probs) fused A3TGCN(2) / TGCN(2) forward for H = None."""
+    return _TgcnAttnFn.apply(plan, x, A, Bm, c, probs)
+
+
 def spmm_cols(plan: GraphPlan, op: int, buf: torch.Tensor, src_col: int, dst_col: int, width: int, alpha: float = 1.0,
               z_col: Optional[int] = None, beta: float = 0.0, transposed: bool = False):
     """In-place column-block product inside one basis buffer `buf` (..., N, LD):

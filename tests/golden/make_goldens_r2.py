@@ -3,6 +3,7 @@ through oracle/refload.py on top of oracle/stubs).  Run in the build container o
 
 * dcrnn_cfg2_grads   -- BatchedDCRNN(2,32,K=2) at the METR-LA shape: output AND autograd gradients (input + parameters)
 * a3tgcn2_cfg3       -- A3TGCN2(2,32,12,B) at the PEMS-BAY shape (325 nodes), all rows, with and without an incoming H
+* a3tgcn2_cfg3_grads -- the same shape without an incoming state: outputs and autograd gradients of every parameter
 * astgcn_cfg4        -- ASTGCN(3 blocks, K=3, 64/64 filters) at the PeMS04 shape (307 nodes, B=32 rows subsampled to keep the
                         file small: the model is row-independent, so B rows of the reference output are exact for those rows)
 * gconv_lstm_cfg5seq -- GConvLSTM(64,64,K=3) 12-step recurrence on a 2 000-node slice-shaped graph (CPU-tractable) + grads
@@ -64,6 +65,28 @@ def a3tgcn2_cfg3():
          state1=sd(m1), out1=out1, out1H=out1H, state_cell=sd(c2), cell=cell, cellH=cellH)
 
 
+def a3tgcn2_cfg3_grads():
+    """A3TGCN2 / TGCN2 at the PEMS-BAY shape WITHOUT an incoming state (the training call of the reference's A3TGCN2 example): outputs and
+    autograd gradients of every parameter of the unmodified reference."""
+    at = refload.load("nn.recurrent.attentiontemporalgcn")
+    tg = refload.load("nn.recurrent.temporalgcn")
+    ei, ew, _ = synthetic.pems_bay_like(0, 16)
+    ei_t, ew_t = torch.from_numpy(ei), torch.from_numpy(ew)
+    torch.manual_seed(3)
+    m = at.A3TGCN2(2, 32, 12, 8)
+    g = torch.Generator().manual_seed(9)
+    X = torch.randn(8, 325, 2, 12, generator=g)
+    out = m(X, ei_t, ew_t)
+    w = torch.linspace(-1, 1, out.numel()).view_as(out)
+    (out * w).sum().backward()
+    c2 = tg.TGCN2(2, 32, 8)
+    cell = c2(X[..., 3], ei_t, ew_t)
+    (cell * w).sum().backward()
+    save("a3tgcn2_cfg3_grads", edge_index=ei_t, edge_weight=ew_t, X=X, state=sd(m), out=out.detach(),
+         grads={k: p.grad.detach().clone() for k, p in m.named_parameters() if p.grad is not None},
+         state_cell=sd(c2), cell=cell.detach(), grads_cell={k: p.grad.detach().clone() for k, p in c2.named_parameters() if p.grad is not None})
+
+
 def astgcn_cfg4():
     """BASELINE configs[3]: ASTGCN(3 blocks, K=3, 64 Chebyshev / 64 time filters, stride 1, 12 -> 12) on the PeMS04 shape (307 nodes,
     340 undirected links), batch 32, normalization "sym"; plus normalization None (lambda_max by scipy) on 8 rows."""
@@ -109,7 +132,7 @@ def gconv_lstm_cfg5seq():
          gX=X.grad.clone(), grads={k: p.grad.detach().clone() for k, p in m.named_parameters()})
 
 
-GENERATORS = {"dcrnn_cfg2_grads": dcrnn_cfg2_grads, "a3tgcn2_cfg3": a3tgcn2_cfg3, "astgcn_cfg4": astgcn_cfg4,
+GENERATORS = {"dcrnn_cfg2_grads": dcrnn_cfg2_grads, "a3tgcn2_cfg3": a3tgcn2_cfg3, "a3tgcn2_cfg3_grads": a3tgcn2_cfg3_grads, "astgcn_cfg4": astgcn_cfg4,
               "gconv_lstm_cfg5seq": gconv_lstm_cfg5seq}
 
 

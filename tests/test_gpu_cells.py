@@ -464,3 +464,52 @@ def test_masked_mae_fused_matches_reference_form():
     assert torch.allclose(la, lb, rtol=1e-5)
     la.backward()
     assert pa.grad[..., 1].abs().max() == 0 and pa.grad[..., 0].abs().max() > 0
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_a3tgcn2_config3_training_gradients_vs_reference_golden(golden_dir, fused):
+    """Training call of the reference's A3TGCN2 example (no incoming state) at the PEMS-BAY shape: output and the gradient of EVERY
+    parameter against the unmodified reference's autograd (tests/golden/make_goldens_r2.py::a3tgcn2_cfg3_grads) -- through the fused
+    forward + hand-written backward (stmp_tgcn_attn_fwd / _bwd) and through the op-for-op autograd path; same for a TGCN2 cell."""
+    from pytorch_geometric_temporal_b200.nn.recurrent import TGCN2
+    g = _load(golden_dir, "a3tgcn2_cfg3_grads")
+    ei, ew, X = (g[k].to(DEV) for k in ("edge_index", "edge_weight", "X"))
+    m = A3TGCN2(2, 32, 12, 8).to(DEV)
+    m.load_state_dict(g["state"])
+    m._base_tgcn.fused_training = fused
+    c0 = _lib.path_counters()
+    out = m(X, ei, ew)
+    w = torch.linspace(-1, 1, out.numel(), device=DEV).view_as(out)
+    (out * w).sum().backward()
+    assert (_ran(c0, "k_tgcn_attn_bwd") == 1) == fused
+    _close(out, g["out"])
+    for k, p in m.named_parameters():
+        ref = g["grads"][k]
+        assert p.grad is not None, k
+        _close(p.grad, ref, 1e-3, 1e-3 * ref.abs().max().item() + 1e-6)
+    c2 = TGCN2(2, 32, 8).to(DEV)
+    c2.load_state_dict(g["state_cell"])
+    c2.fused_training = fused
+    c0 = _lib.path_counters()
+    cell = c2(X[..., 3], ei, ew)
+    (cell * w).sum().backward()
+    assert (_ran(c0, "k_tgcn_attn_bwd") == 1) == fused
+    _close(cell, g["cell"])
+    for k, p in c2.named_parameters():
+        ref = g["grads_cell"][k]
+        _close(p.grad, ref, 1e-3, 1e-3 * ref.abs().max().item() + 1e-6)
+
+
+def test_a3tgcn2_training_step_with_state_or_input_grad_takes_the_autograd_path():
+    """An incoming state or a gradient w.r.t. X is outside the hand-written backward: those calls stay on the differentiable op-for-op path."""
+    ei, ew, _ = synthetic.pems_bay_like(0, 16)
+    ei, ew = torch.from_numpy(ei).to(DEV), torch.from_numpy(ew).to(DEV)
+    torch.manual_seed(0)
+    m = A3TGCN2(2, 32, 12, 4).to(DEV)
+    X = torch.randn(4, 325, 2, 12, device=DEV)
+    H = torch.randn(4, 325, 32, device=DEV) * 0.5
+    c0 = _lib.path_counters()
+    m(X, ei, ew, H).sum().backward()
+    Xg = X.clone().requires_grad_(True)
+    m(Xg, ei, ew).sum().backward()
+    assert Xg.grad is not None and _ran(c0, "k_tgcn_attn_bwd") == 0
