@@ -149,6 +149,25 @@ __device__ __forceinline__ void tma_store_wait() {
   asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// ---- thread-block-cluster helpers (CTA pairs: the small-batch variants of the DCRNN sequence kernels) ------------------------------
+__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {          // data barrier: my (remote) shared-memory stores are visible to the pair behind it
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// execution-only barrier, split: "I am done READING buf" is signalled right after the gather phase (relaxed: no memory ordering, so the
+// phase's global stores are not drained -- the release form spent 14 % of the kernel in ERRBAR) and waited for only where the next GEMM is
+// about to overwrite the partner's buf, i.e. behind its FFMA loop.
+__device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t map_to_peer(const void* p, uint32_t peer) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(peer));
+  return r;
+}
+__device__ __forceinline__ void st4_cluster(uint32_t addr, float4 v) {
+  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 // 1/(1+e^-x): __frcp_rn is the correctly rounded reciprocal == IEEE 1.0f/y, without the division slow path.
 __device__ __forceinline__ float sigmoidf_acc(float x) { return __frcp_rn(1.0f + expf(-x)); }
 

@@ -144,25 +144,6 @@ struct BwdParams {
   float* dh0;                               // (B,N,Co)
 };
 
-// ---- thread-block-cluster helpers: with SPLIT == 2 a window is served by a CTA pair, each owning half of the node rows -----------------
-__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ void cluster_sync_all() {          // data barrier: my (remote) shared-memory stores are visible to the pair behind it
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// execution-only barrier, split: "I am done READING buf" is signalled right after the gather phase (relaxed: no memory ordering, so the
-// phase's global stores are not drained -- the release form spent 14 % of the kernel in ERRBAR) and waited for only where the next GEMM is
-// about to overwrite the partner's buf, i.e. behind its FFMA loop.
-__device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
-__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
-__device__ __forceinline__ uint32_t map_to_peer(const void* p, uint32_t peer) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(peer));
-  return r;
-}
-__device__ __forceinline__ void st4_cluster(uint32_t addr, float4 v) {
-  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
-
 // buf[r0 + RT rg ..+RT)[8cg..8cg+8) = sum_k dpT[k][r0 + RT rg ..] (x) W[k][8cg..]: one thread per RT x 8 output tile, RG row groups starting at
 // row r0.  Per k a thread issues RT/4 + 2 LDS.128 (the rows -- dp is kept TRANSPOSED, k-major, so they are contiguous -- and the 8 weight
 // columns) for 8 RT FFMA: with RT = 8 the shared-memory pipe and the FMA pipe are balanced (a 1 x 52 tile was 4x LSU-bound).  Adjacent

@@ -30,6 +30,7 @@ extern int g_spmm_variant;
 extern int g_spmm_rows_per_group;
 extern int g_spmm_block;
 extern int g_wgrad_tc;
+extern int g_fwd_split;
 extern int g_bwd_all_cin;
 extern int g_bwd_split;
 bool dcrnn_tc_supported(const stmp_plan* plan, long long cin, long long cout, long long K);
@@ -513,6 +514,7 @@ extern "C" int stmp_set_option(const char* name, int value) {
   if (strcmp(name, "dcrnn_tc") == 0) { g_use_tc = value ? 1 : 0; return STMP_OK; }
   if (strcmp(name, "spmm_variant") == 0) { g_spmm_variant = value; return STMP_OK; }
   if (strcmp(name, "spmm_rows_per_group") == 0) { g_spmm_rows_per_group = value < 1 ? 1 : value; return STMP_OK; }
+  if (strcmp(name, "dcrnn_fwd_split") == 0) { g_fwd_split = value ? 1 : 0; return STMP_OK; }
   if (strcmp(name, "dcrnn_wgrad_tc") == 0) { g_wgrad_tc = value ? 1 : 0; return STMP_OK; }
   if (strcmp(name, "spmm_block") == 0) { g_spmm_block = value == 1024 ? 1024 : 256; return STMP_OK; }
   if (strcmp(name, "dcrnn_bwd_all_cin") == 0) { g_bwd_all_cin = value ? 1 : 0; return STMP_OK; }

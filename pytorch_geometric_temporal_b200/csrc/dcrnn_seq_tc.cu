@@ -37,6 +37,7 @@
 #define STMP_TC_UNROLL(n) STMP_TC_PRAGMA(unroll n)
 
 namespace stmp {
+int g_fwd_split = 1;      // 1: a CTA pair per window for small batches (stmp_set_option("dcrnn_fwd_split")): 64 windows 160.8 -> 132.2 us
 namespace {
 
 constexpr int kMaxSmemTc = 232448;
@@ -190,9 +191,14 @@ __device__ __forceinline__ float4 gather_groups(const float* __restrict__ Uj, co
 // barriers cheap (round 1 profile: 25 % of all warp time was barrier wait behind the warp that always drew the longest rows).
 // X is never gathered per step: P_o X_t, P_i X_t of ALL steps of a window are produced by one gather pass over rows of
 // T*Cin floats in the window prologue and parked in the window's own (not yet written) output rows out[b, t, :, 0:8].
-template <int CIN>
+// SPLIT = 2 (small batches: 2 B CTAs still fit the machine, N > 128): a window is served by a 2-CTA thread-block cluster.  CTA c owns MMA
+// row tile c -- its gather tasks, its MMAs, its epilogue (all 16 warps: thread = (row, channel quarter)) -- and pushes the rows of H*R / H_t it
+// produces into the partner's gather buffer U through distributed shared memory, so both gathers stay local.  Per round: "done reading U"
+// is a relaxed cluster arrival right after the gather, waited for just before the epilogue overwrites U; the barrier that closes an epilogue is
+// a release / acquire cluster barrier (the pushed rows are visible).
+template <int CIN, int SPLIT>
 __global__ void __launch_bounds__(512, 1) k_dcrnn_seq_tc(const TcParams p) {
-  constexpr int CW = 16;   // channels per thread (two threads share a row)
+  constexpr int CW = SPLIT == 2 ? 8 : 16;   // channels per thread (two / four threads share a row)
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int N = p.N, T = p.T;
@@ -211,7 +217,9 @@ __global__ void __launch_bounds__(512, 1) k_dcrnn_seq_tc(const TcParams p) {
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.off_bar);   // [0..3] MMA done (gemm*2+tile), [4] prologue TMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
 
-  if (blockIdx.x >= p.B) return;
+  const int crank = SPLIT == 2 ? (int)cluster_rank() : 0;
+  const long long cta = blockIdx.x / SPLIT, n_cta = gridDim.x / SPLIT;
+  if (cta >= p.B) return;
 
   // ---- one-time per CTA ------------------------------------------------------------------------------------
   if (warp == 0) {
@@ -263,7 +271,8 @@ __global__ void __launch_bounds__(512, 1) k_dcrnn_seq_tc(const TcParams p) {
   const uint32_t tmem = *tmem_slot;
 
   // thread = (row, channel half): warp = half*8 + tile*4 + q ; TMEM lane == row, a warp may only touch lanes 32*(warp%4)..
-  const int half = warp >> 3, tile = (warp >> 2) & 1, q = warp & 3;
+  // (cluster pair: thread = (row of my tile, channel quarter): warp = quarter*4 + q)
+  const int half = SPLIT == 2 ? (warp >> 2) : (warp >> 3), tile = SPLIT == 2 ? crank : ((warp >> 2) & 1), q = warp & 3;
   const int row = tile * 128 + q * 32 + lane;
   const int ch0 = CW * half;
   const bool live = row < N;
@@ -275,6 +284,20 @@ __global__ void __launch_bounds__(512, 1) k_dcrnn_seq_tc(const TcParams p) {
   const bool two_tiles = N > 128;
   const int j = lane & 7, quarter = lane >> 3;
   const float* Uj = U + 4 * j;
+  uint32_t peer_U = 0;
+  if constexpr (SPLIT == 2) peer_U = map_to_peer(U, (uint32_t)(crank ^ 1));
+  // store a float4 of my row into U -- and into the partner's U in the cluster-pair variant
+  auto put_u = [&](int off, float4 v) {
+    st4(U + off, v);
+    if constexpr (SPLIT == 2) st4_cluster(peer_U + (uint32_t)off * 4u, v);
+  };
+  // barrier that closes an epilogue / the window prologue: operand + U stores of everybody visible to the MMAs and the next gather
+  auto close_phase = [&]() {
+    fence_proxy_async();
+    tc_fence_before();
+    if constexpr (SPLIT == 2) cluster_sync_all(); else __syncthreads();
+    tc_fence_after();
+  };
 
   // The 3 x 7 MMAs of one (tile, gemm) are issued in three groups, each as soon as its k-steps are in shared memory, each with
   // its own commit to the (tile, gemm) barrier (count 3):
@@ -322,6 +345,22 @@ __global__ void __launch_bounds__(512, 1) k_dcrnn_seq_tc(const TcParams p) {
   // that tile's MMAs (same issuing thread => in order).  The task lists are balanced (graph_image.cuh), so the two barriers are cheap;
   // the closing one also tells the epilogue that nobody reads U any more.
   auto gather_round = [&](int gm) {
+    if constexpr (SPLIT == 2) {
+      if (tid == 0) issue_group(crank, gm, 0);
+      if (p.n_ops > 0) gather_segment(2 * crank);
+      if (p.n_ops > 1) gather_segment(2 * crank + 1);
+      cluster_arrive_relaxed();   // this CTA has finished reading U (waited for by the partner before its epilogue overwrites my U)
+      fence_proxy_async();
+      tc_fence_before();
+      __syncthreads();
+      tc_fence_after();
+      if (tid == 0) {
+        issue_group(crank, gm, 1);
+        issue_group(crank, gm, 2);
+        umma_commit(&bars[2 * gm + crank]);
+      }
+      return;
+    }
     if (tid == 0) {
       issue_group(0, gm, 0);
       if (two_tiles) issue_group(1, gm, 0);
@@ -389,7 +428,7 @@ __global__ void __launch_bounds__(512, 1) k_dcrnn_seq_tc(const TcParams p) {
     store_split4(a_hi + TC_PANEL_A, a_lo + TC_PANEL_A, row, 40, mask_c(pi));
   };
 
-  for (long long b = blockIdx.x; b < p.B; b += gridDim.x) {
+  for (long long b = cta; b < p.B; b += n_cta) {
     const float* xb = x_base(b);
     // ---- window prologue A: P_o X_t, P_i X_t for every step of the window, TCH steps per gather pass ------------------------
     if (p.n_ops) {
@@ -420,7 +459,7 @@ __global__ void __launch_bounds__(512, 1) k_dcrnn_seq_tc(const TcParams p) {
           }
         }
         __syncthreads();
-        for (int seg = 0; seg < 4; ++seg) {
+        for (int seg = SPLIT == 2 ? 2 * crank : 0; seg < (SPLIT == 2 ? 2 * crank + 2 : 4); ++seg) {
           const int ws = s_wstart[warp * 4 + seg], wc = s_wcount[warp * 4 + seg];
           for (int i = 0; i < wc; ++i) {
             const uint32_t d = s_wt[(ws + i) * 4 + quarter];
@@ -462,12 +501,16 @@ __global__ void __launch_bounds__(512, 1) k_dcrnn_seq_tc(const TcParams p) {
     }
     // ---- window prologue B: H_0 into U (fp32) and the A panels (fp16 hi/lo); the X k-step of step 0 ---------------------------
     float hreg[CW];
+    if constexpr (SPLIT == 2) {   // the partner has finished the X gather of its prologue: its U may be overwritten
+      cluster_arrive_relaxed();
+      cluster_wait();
+    }
     if (live) {
 #pragma unroll
       for (int c = 0; c < CW / 4; ++c) {
         const float4 h = p.h0 ? __ldg(reinterpret_cast<const float4*>(p.h0 + b * p.h0_bstride + row * 32 + ch0) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
         hreg[4 * c] = h.x; hreg[4 * c + 1] = h.y; hreg[4 * c + 2] = h.z; hreg[4 * c + 3] = h.w;
-        st4(U + row * TC_UP + ch0 + 4 * c, h);
+        put_u(row * TC_UP + ch0 + 4 * c, h);
       }
       store_split_row<CW>(a_hi, a_lo, row, half, hreg);
       if (owner) {
@@ -476,10 +519,7 @@ __global__ void __launch_bounds__(512, 1) k_dcrnn_seq_tc(const TcParams p) {
         store_x(xv, po, pi);
       }
     }
-    fence_proxy_async();       // the first MMA group of step 0 is issued right behind this barrier
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
+    close_phase();             // the first MMA group of step 0 is issued right behind this barrier
 
     for (int t = 0; t < T; ++t) {
       // ---- round 1: diffuse H ------------------------------------------------------------------------------------------
@@ -499,9 +539,10 @@ __global__ void __launch_bounds__(512, 1) k_dcrnn_seq_tc(const TcParams p) {
           hr[c] = hreg[c] * r;
           vr[c] = __float_as_uint(r);
         }
+        if constexpr (SPLIT == 2) cluster_wait();       // the partner is done gathering from its U
         if (live) {
 #pragma unroll
-          for (int c = 0; c < CW / 4; ++c) st4(U + row * TC_UP + ch0 + 4 * c, make_float4(hr[4 * c], hr[4 * c + 1], hr[4 * c + 2], hr[4 * c + 3]));
+          for (int c = 0; c < CW / 4; ++c) put_u(row * TC_UP + ch0 + 4 * c, make_float4(hr[4 * c], hr[4 * c + 1], hr[4 * c + 2], hr[4 * c + 3]));
           store_split_row<CW>(a_hi, a_lo, row, half, hr);
           if (p.stash) {
             float* sp = p.stash + ((obase * 3) + row) * 32 + ch0;
@@ -513,10 +554,7 @@ __global__ void __launch_bounds__(512, 1) k_dcrnn_seq_tc(const TcParams p) {
           }
         }
       }
-      fence_proxy_async();
-      tc_fence_before();
-      __syncthreads();
-      tc_fence_after();
+      close_phase();
       // ---- round 2: re-diffuse H*R ---------------------------------------------------------------------------------------
       gather_round(1);
       // ---- epilogue 2: candidate, H_t --------------------------------------------------------------------------------------
@@ -539,12 +577,13 @@ __global__ void __launch_bounds__(512, 1) k_dcrnn_seq_tc(const TcParams p) {
           ht[c] = tanh_fast(__uint_as_float(vh[c]) + Bs[64 + ch0 + c]);
           hreg[c] = zreg[c] * hreg[c] + (1.0f - zreg[c]) * ht[c];   // dcrnn.py:190-192
         }
+        if constexpr (SPLIT == 2) cluster_wait();
         if (live) {
           float* op = p.out + (obase + row) * 32 + ch0;
 #pragma unroll
           for (int c = 0; c < CW / 4; ++c) {
             const float4 hv = make_float4(hreg[4 * c], hreg[4 * c + 1], hreg[4 * c + 2], hreg[4 * c + 3]);
-            st4(U + row * TC_UP + ch0 + 4 * c, hv);
+            put_u(row * TC_UP + ch0 + 4 * c, hv);
             st4(op + 4 * c, hv);
           }
           store_split_row<CW>(a_hi, a_lo, row, half, hreg);
@@ -560,10 +599,7 @@ __global__ void __launch_bounds__(512, 1) k_dcrnn_seq_tc(const TcParams p) {
         }
       }
       parity ^= 1u;
-      fence_proxy_async();
-      tc_fence_before();
-      __syncthreads();
-      tc_fence_after();
+      close_phase();
     }
   }
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TC_TMEM_COLS));
@@ -654,19 +690,33 @@ static int tc_launch_params(const stmp_plan* plan, TcParams& p, cudaStream_t st)
   int dev = 0, sms = 0;
   STMP_CUDA_OK(cudaGetDevice(&dev));
   STMP_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const int grid = (int)(B < sms ? B : sms);
+  // small batches: a CTA pair (thread-block cluster) per window when both tiles exist and 2 B CTAs fit the machine
+  const bool split = g_fwd_split != 0 && plan->n > 128 && 2 * B <= sms;
+  const int grid = split ? (int)(2 * B) : (int)(B < sms ? B : sms);
   p.ws_pitch = tc_ws_pitch(p.T, p.CIN);
   switch (p.CIN) {
 #define STMP_TC_CASE(C)                                                                                              \
   case C:                                                                                                            \
-    STMP_CUDA_OK(cudaFuncSetAttribute(k_dcrnn_seq_tc<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));        \
-    k_dcrnn_seq_tc<C><<<grid, 512, smem, st>>>(p);                                                                   \
+    if (split) {                                                                                                     \
+      STMP_CUDA_OK(cudaFuncSetAttribute(k_dcrnn_seq_tc<C, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));   \
+      cudaLaunchConfig_t cfg = {};                                                                                   \
+      cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(512); cfg.dynamicSmemBytes = (size_t)smem; cfg.stream = st; \
+      cudaLaunchAttribute at[1];                                                                                     \
+      at[0].id = cudaLaunchAttributeClusterDimension;                                                                \
+      at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;                            \
+      cfg.attrs = at; cfg.numAttrs = 1;                                                                              \
+      STMP_CUDA_OK(cudaLaunchKernelEx(&cfg, k_dcrnn_seq_tc<C, 2>, p));                                               \
+    } else {                                                                                                         \
+      STMP_CUDA_OK(cudaFuncSetAttribute(k_dcrnn_seq_tc<C, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));   \
+      k_dcrnn_seq_tc<C, 1><<<grid, 512, smem, st>>>(p);                                                              \
+    }                                                                                                                \
     break;
     STMP_TC_CASE(1) STMP_TC_CASE(2) STMP_TC_CASE(3) STMP_TC_CASE(4)
 #undef STMP_TC_CASE
-    default: return set_error(STMP_EUNSUPPORTED, "tcgen05 graph-GRU kernel: cin=%d", p.CIN);
+    default: return set_error(STMP_EUNSUPPORTED, "tcgen05 graph-GRU kernel: cin %d not in 1..4", p.CIN);
   }
   STMP_LAUNCH_OK("k_dcrnn_seq_tc");
+  if (split) { static const int slot2 = path_slot("k_dcrnn_seq_tc[cluster2]"); count_path(slot2); }
   return STMP_OK;
 }
 

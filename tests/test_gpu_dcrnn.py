@@ -407,3 +407,48 @@ def test_persistent_backward_cluster_pair_equals_single_cta(n_nodes, cin):
     for ga, gb in zip(*grads):
         assert bool(torch.isfinite(ga).all())
         assert torch.equal(ga, gb), f"max abs diff {(ga - gb).abs().max():.3e}"
+
+
+@pytest.mark.parametrize("cin", [2, 1])
+def test_forward_cluster_pair_equals_single_cta(cin):
+    """Small batches may run the fused forward on a 2-CTA cluster per window (one MMA row tile each, H rows exchanged through distributed
+    shared memory).  Row arithmetic is unchanged: outputs, the training stash and gradients agree with the one-CTA kernel to the last bit."""
+    ei, ew, _ = synthetic.metr_la_like(4, 16)
+    ei_t, ew_t = torch.from_numpy(ei).to(DEV), torch.from_numpy(ew).to(DEV)
+    torch.manual_seed(10 + cin)
+    X = torch.randn(7, 12, 207, cin, device=DEV)
+    w = torch.randn(7, 12, 207, 32, device=DEV)
+    model = BatchedDCRNN(cin, 32, 2).to(DEV)
+    res = []
+    for split in (1, 0):
+        _lib.set_option("dcrnn_fwd_split", split)
+        try:
+            c0 = _lib.path_counters()
+            with torch.no_grad():
+                out = model(X, ei_t, ew_t)
+            model.zero_grad()
+            Xa = X.clone().requires_grad_(True)
+            (model(Xa, ei_t, ew_t) * w).sum().backward()
+            c1 = _lib.path_counters()
+        finally:
+            _lib.set_option("dcrnn_fwd_split", FWD_SPLIT_DEFAULT)
+        assert c1.get("k_dcrnn_seq_tc[cluster2]", 0) - c0.get("k_dcrnn_seq_tc[cluster2]", 0) == 2 * split
+        res.append([out, Xa.grad.clone()] + [p.grad.clone() for p in model.parameters()])
+    for a, b in zip(*res):
+        assert bool(torch.isfinite(a).all())
+        assert torch.equal(a, b), f"max abs diff {(a - b).abs().max():.3e}"
+    # one cell step with an incoming state (H0 is pushed into both gather buffers by the window prologue)
+    cell = DCRNN(cin, 32, 2).to(DEV)
+    x1, h1 = torch.randn(207, cin, device=DEV), torch.randn(207, 32, device=DEV) * 0.5
+    outs = []
+    for split in (1, 0):
+        _lib.set_option("dcrnn_fwd_split", split)
+        try:
+            with torch.no_grad():
+                outs.append(cell(x1, ei_t, ew_t, h1))
+        finally:
+            _lib.set_option("dcrnn_fwd_split", FWD_SPLIT_DEFAULT)
+    assert torch.equal(outs[0], outs[1])
+
+
+FWD_SPLIT_DEFAULT = 1
