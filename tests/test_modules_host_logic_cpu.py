@@ -238,6 +238,49 @@ def test_tgcn_attention_folding_host_logic_vs_reference_golden(golden_dir, dense
         _close(c2(X[..., 0], ei, ew), g["cell"]); _close(c2(X[..., 0], ei, ew, H), g["cellH"])
 
 
+def test_tgcn_attention_training_host_logic_vs_reference_golden_gradients(golden_dir, dense_dconv_gcn_ops, monkeypatch):
+    """Host side of the fused TRAINING path (stmp_tgcn_attn_fwd + stmp_tgcn_attn_bwd): the differentiable folding `TGCN._fold3`, the
+    softmax of the attention and the routing (no state, no input gradient -> `ops.tgcn_attn_train`), with the kernel pair replaced by a
+    dense differentiable restatement -- output and EVERY parameter gradient against the unmodified reference at the PEMS-BAY shape."""
+    calls = []
+
+    def fake_train(plan, x, A, Bm, c, probs=None):
+        calls.append(tuple(x.shape))
+        L = plan.mats[0]
+        out = 0
+        for t in range(x.shape[-1]):
+            ax = torch.matmul(L, x[..., t])
+            Z = torch.sigmoid(ax @ A[:, 0:32] + c[0:32])
+            Ht = torch.tanh(ax @ A[:, 64:96] + c[64:96])                       # H = 0: the r gate and Bm drop out
+            out = out + (1 - Z) * Ht * (1.0 if probs is None else probs[t])
+        return out
+    monkeypatch.setattr(ops, "tgcn_attn_train", fake_train)
+    g = _load(golden_dir, "a3tgcn2_cfg3_grads")
+    ei, ew, X = g["edge_index"], g["edge_weight"], g["X"]
+    m = A3TGCN2(2, 32, 12, 8)
+    m.load_state_dict(g["state"])
+    out = m(X, ei, ew)
+    w = torch.linspace(-1, 1, out.numel()).view_as(out)
+    (out * w).sum().backward()
+    _close(out, g["out"])
+    for k, p in m.named_parameters():
+        ref = g["grads"][k]
+        assert p.grad is not None, k
+        assert torch.allclose(p.grad, ref, rtol=1e-3, atol=1e-3 * float(ref.abs().max()) + 1e-6), k
+    c2 = TGCN2(2, 32, 8)
+    c2.load_state_dict(g["state_cell"])
+    cell = c2(X[..., 3], ei, ew)
+    (cell * w).sum().backward()
+    _close(cell, g["cell"])
+    for k, p in c2.named_parameters():
+        ref = g["grads_cell"][k]
+        assert torch.allclose(p.grad, ref, rtol=1e-3, atol=1e-3 * float(ref.abs().max()) + 1e-6), k
+    assert calls == [(8, 325, 2, 12), (8, 325, 2, 1)]
+    # a call with an incoming state stays on the op-for-op path
+    m(X[:2], ei, ew, torch.zeros(2, 325, 32)).sum().backward()
+    assert len(calls) == 2
+
+
 # ---- ASTGCN: attention-weighted first hop, timesteps folded into the feature axis, fp32 time convolutions ---------------
 import pytorch_geometric_temporal_b200.nn.attention.astgcn as astgcn_mod  # noqa: E402
 from oracle import attention as OA  # noqa: E402

@@ -5,7 +5,7 @@
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 for tool in memcheck racecheck; do
-  timeout 900 compute-sanitizer --tool $tool --print-limit 30 python tools/sanitize_smoke.py > gpurun_out/r02_sanitizer_$tool.txt 2>&1
+  timeout 330 compute-sanitizer --tool $tool --print-limit 30 python tools/sanitize_smoke.py > gpurun_out/r02_sanitizer_$tool.txt 2>&1
   echo "[$tool] rc=$?" >> gpurun_out/r02_sanitizer_$tool.txt
   tail -4 gpurun_out/r02_sanitizer_$tool.txt
 done

@@ -19,7 +19,19 @@ X = torch.from_numpy(series[:36]).reshape(3, 12, 207, 2).to(dev)
 m = BatchedDCRNN(2, 32, 2).to(dev)
 with torch.no_grad():
     m(X, ei_t, ew_t)                                             # k_dcrnn_seq_tc (tcgen05, TMA images, MMA groups)
-m(X[:2], ei_t, ew_t).square().mean().backward()                  # + stash, k_dcrnn_bwd_basis / k_dcrnn_bwd_seq
+m(X[:2], ei_t, ew_t).square().mean().backward()                  # + stash; CTA-pair (cluster) forward and backward, k_dcrnn_bwd_basis, k_dcrnn_wgrad_tc
+for opt in ("dcrnn_fwd_split", "dcrnn_bwd_split", "dcrnn_wgrad_tc"):
+    _lib.set_option(opt, 0)
+with torch.no_grad():
+    m(X, ei_t, ew_t)                                             # one CTA per window
+m(X[:2], ei_t, ew_t).square().mean().backward()                  # one-CTA backward, FFMA weight-gradient kernel
+for opt in ("dcrnn_fwd_split", "dcrnn_bwd_split", "dcrnn_wgrad_tc"):
+    _lib.set_option(opt, 1)
+from pytorch_geometric_temporal_b200 import distributed as D   # noqa: E402
+sync = D.FlatGradSync(m.parameters())
+opt_ = D.FlatAdam(sync, lr=1e-3)
+m(X[:2], ei_t, ew_t).square().mean().backward()
+opt_.step()                                                      # k_adam_flat
 with torch.no_grad():
     BatchedDCRNN(2, 16, 3).to(dev)(X[:2], ei_t, ew_t)            # k_dcrnn_seq (FFMA2, TMA window buffers)
     g = GConvGRU(2, 32, 2).to(dev)
@@ -28,6 +40,9 @@ with torch.no_grad():
     a3 = A3TGCN2(2, 32, 12, 4).to(dev)
     a3(torch.randn(4, 325, 2, 12, device=dev), torch.from_numpy(e3).to(dev), torch.from_numpy(w3).to(dev),
        torch.randn(4, 325, 32, device=dev))                      # k_tgcn_attn (TMA-staged X)
+with torch.enable_grad():
+    a3(torch.randn(4, 325, 2, 12, device=dev), torch.from_numpy(e3).to(dev), torch.from_numpy(w3).to(dev)).square().mean().backward()   # k_tgcn_attn_bwd
+with torch.no_grad():
     e4 = torch.from_numpy(synthetic.pems04_like(0)).to(dev)
     ASTGCN(2, 1, 3, 64, 64, 1, 12, 12, 307, normalization="sym").to(dev)(torch.randn(2, 307, 1, 12, device=dev), e4)   # k_gemm_blocks x7
     eg, wg = synthetic.large_graph(2000, 20000, 0)
