@@ -228,6 +228,16 @@ extern "C" int stmp_dcrnn_bwd_wgrad(int64_t cin, int64_t cout, int64_t K, int64_
   const int C = (int)(cin + cout), MG = (3 * C + 7) / 8;
   STMP_REQUIRE(ld == 8 * MG, STMP_EINVAL, "stmp_dcrnn_bwd_wgrad: the basis row pitch must be 3(cin+cout) rounded up to 8");
   cudaStream_t st = (cudaStream_t)stream;
+  if (rows == 0) {                                   // nothing to contract: the gradients are zero
+    const size_t wbytes = (size_t)4 * C * kCo * 4;
+    STMP_CUDA_OK(cudaMemsetAsync(gz, 0, wbytes, st));
+    STMP_CUDA_OK(cudaMemsetAsync(gr, 0, wbytes, st));
+    STMP_CUDA_OK(cudaMemsetAsync(gh, 0, wbytes, st));
+    if (gbz) STMP_CUDA_OK(cudaMemsetAsync(gbz, 0, kCo * 4, st));
+    if (gbr) STMP_CUDA_OK(cudaMemsetAsync(gbr, 0, kCo * 4, st));
+    if (gbh) STMP_CUDA_OK(cudaMemsetAsync(gbh, 0, kCo * 4, st));
+    return STMP_OK;
+  }
   WgradParams p;
   p.S1 = S1; p.S2 = S2; p.dpzr = dpzr; p.dph = dph; p.rows = rows; p.ld = (int)ld; p.MG = MG;
   p.n_tiles = (int)((rows + kWgTK - 1) / kWgTK);

@@ -156,7 +156,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_dcrnn_wgrad_tc(WgTcParams p) {
 
   if (warp == kConvThreads / 32) {
     // ---- producer / issuer warp: one lane keeps the TMA ring full and issues the 12 MMAs of every tile as soon as its operand buffer is
-    // complete -- the converting warps never wait for the ~150 serial instructions of descriptor set-up and MMA issue
+    // complete -- the converting warps never wait for the ~150 serial instructions of descriptor set-up and MMA issue.  (Letting all 32
+    // lanes of this warp run the loop and its waits, with one lane issuing, measured slower: 85 vs 77 us.)  Profile of this version
+    // (profiles/r02_dcrnn_wgrad_tc.txt): 69 us, the converting warps spend 56 % of their time waiting for the MMAs of tile it - 2 to retire
+    // (tensor pipe active 17 %): the six dependent K = 8 MMAs per accumulator and tile are latency-, not throughput-bound.
     if (lane == 0) {
       for (int q = 0; q < kStages - 1 && q < n_local; ++q) issue_tma(blockIdx.x + q * gridDim.x, q);
       for (int it = 0; it < n_local; ++it) {
