@@ -168,6 +168,13 @@ __device__ __forceinline__ void st4_cluster(uint32_t addr, float4 v) {
   asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+// 16-byte store into the partner CTA's shared memory that also completes 16 transaction bytes on an mbarrier THERE: the receiver waits on its
+// own mbarrier for the expected byte count instead of meeting the sender at a release / acquire cluster barrier.
+__device__ __forceinline__ void st4_async_cluster(uint32_t addr, float4 v, uint32_t remote_mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(addr), "f"(v.x),
+               "f"(v.y), "f"(v.z), "f"(v.w), "r"(remote_mbar)
+               : "memory");
+}
 // 1/(1+e^-x): __frcp_rn is the correctly rounded reciprocal == IEEE 1.0f/y, without the division slow path.
 __device__ __forceinline__ float sigmoidf_acc(float x) { return __frcp_rn(1.0f + expf(-x)); }
 

@@ -151,7 +151,7 @@ struct BwdParams {
 // CTA's buf (distributed shared memory), whose adjoint gathers read rows of both halves.
 template <int NCOL, int KD, int RT, bool PEER>
 __device__ __forceinline__ void gemm_tiles(const float* __restrict__ dpT, int dpp, const float* __restrict__ W, float* __restrict__ buf,
-                                           int r0, int RG, uint32_t peer_buf) {
+                                           int r0, int RG, uint32_t peer_buf, uint32_t peer_bar) {
   constexpr int CGN = NCOL / 8;
   const int tid = threadIdx.x;
   const bool active = tid < RG * CGN;
@@ -194,7 +194,7 @@ __device__ __forceinline__ void gemm_tiles(const float* __restrict__ dpT, int dp
     const float4 v0 = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]), v1 = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
     float4* o = reinterpret_cast<float4*>(buf + off);
     o[0] = v0; o[1] = v1;
-    if constexpr (PEER) { st4_cluster(peer_buf + off * 4, v0); st4_cluster(peer_buf + off * 4 + 16, v1); }
+    if constexpr (PEER) { st4_async_cluster(peer_buf + off * 4, v0, peer_bar); st4_async_cluster(peer_buf + off * 4 + 16, v1, peer_bar); }
   }
 }
 
@@ -268,13 +268,33 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_dcrnn_bwd_seq(BwdParams p) {
     sm[i] = v;
   }
   for (int i = tid; i < 2 * kCo * dpp; i += kBwdThreads) dpT[i] = 0.f;
-  uint32_t peer_buf = 0;
-  if constexpr (SPLIT == 2) peer_buf = map_to_peer(buf, (uint32_t)(hrank ^ 1));
+  // The partner's rows of dS arrive by st.async: every 16-byte store completes 16 transaction bytes on MY mbarrier `dbar`, which thread 0 arms
+  // with the byte count of the partner's half before each phase -- no release / acquire cluster barrier on the data path (that barrier and
+  // its memory fence were 47 % + 12 % of the warp time of the first cluster version).
+  __shared__ __align__(8) uint64_t dbar;
+  uint32_t peer_buf = 0, peer_bar = 0, dpar = 0;
+  const uint32_t expect_bytes = (uint32_t)((hrank == 0 ? RG * 8 - half_rows : half_rows) * NCOL * 4);   // what the partner sends per GEMM
+  if constexpr (SPLIT == 2) {
+    peer_buf = map_to_peer(buf, (uint32_t)(hrank ^ 1));
+    peer_bar = map_to_peer(&dbar, (uint32_t)(hrank ^ 1));
+    if (tid == 0) {
+      mbar_init(&dbar, 1);
+      fence_mbar_init();
+      mbar_arrive_expect_tx(&dbar, expect_bytes);
+    }
+  }
   // data_sync: behind a GEMM (dS of both halves complete and visible); free_sync: behind a gather phase (block barrier for dpT / G, plus the
   // relaxed "done reading buf" arrival that the next GEMM waits for just before it stores)
-  auto data_sync = [&]() { if constexpr (SPLIT == 2) cluster_sync_all(); else __syncthreads(); };
+  auto data_sync = [&]() {
+    __syncthreads();                                           // my own rows of dS (and dpT / G) are visible inside the CTA
+    if constexpr (SPLIT == 2) {
+      mbar_wait(&dbar, dpar);                                  // the partner's rows have landed
+      dpar ^= 1u;
+      if (tid == 0) mbar_arrive_expect_tx(&dbar, expect_bytes);   // armed for the next GEMM (the partner cannot send before my next arrival)
+    }
+  };
   auto free_sync = [&]() { if constexpr (SPLIT == 2) cluster_arrive_relaxed(); __syncthreads(); };
-  data_sync();
+  if constexpr (SPLIT == 2) cluster_sync_all(); else __syncthreads();     // barriers initialised, weights / graph staged
   // ---- open step T-1
   const long long bT = (long long)b * T;
   for (int i = r_lo * kCo + tid; i < r_hi * kCo; i += kBwdThreads) {
@@ -294,7 +314,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_dcrnn_bwd_seq(BwdParams p) {
     const float* st = p.stash + bt * 3 * NH;
     const float* hprev = t > 0 ? p.out + (bt - 1) * NH : (p.h0 ? p.h0 + (long long)b * NH : nullptr);
     // dS2 = dpre_h @ Wh^T
-    gemm_tiles<NCOL, kCo, RT, SPLIT == 2>(dpT, dpp, Wh, buf, g_r0, g_RG, peer_buf);
+    gemm_tiles<NCOL, kCo, RT, SPLIT == 2>(dpT, dpp, Wh, buf, g_r0, g_RG, peer_buf, peer_bar);
     data_sync();
     // dU2 = adjoint; d pre-activations of z and r; partial carry  g*Z + dHR*R
     float* dpzr = p.dpzr_all + (((long long)t * p.B + b) * N) * 2 * kCo;
@@ -342,7 +362,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_dcrnn_bwd_seq(BwdParams p) {
     }
     free_sync();
     // dS1 = dpre_zr @ Wzr^T
-    gemm_tiles<NCOL, 2 * kCo, RT, SPLIT == 2>(dpT, dpp, Wzr, buf, g_r0, g_RG, peer_buf);
+    gemm_tiles<NCOL, 2 * kCo, RT, SPLIT == 2>(dpT, dpp, Wzr, buf, g_r0, g_RG, peer_buf, peer_bar);
     data_sync();
     // dU1 = adjoint; dX_t; dL/dH_{t-1}; open step t-1
     const float* stn = st - 3 * NH;          // stash of step t-1 (only dereferenced when t > 0)
