@@ -33,6 +33,9 @@
 #ifndef STMP_TC_GUNROLL
 #define STMP_TC_GUNROLL 2
 #endif
+#ifndef STMP_TC_PREFETCH
+#define STMP_TC_PREFETCH 0
+#endif
 #define STMP_TC_PRAGMA(x) _Pragma(#x)
 #define STMP_TC_UNROLL(n) STMP_TC_PRAGMA(unroll n)
 
@@ -149,11 +152,10 @@ static_assert(kImgZeroRow * kImgRowPitchBytes < 65536, "row offsets must fit 16 
 __device__ __forceinline__ float4 ld4_off(const float* base, uint32_t byte_off) {
   return *reinterpret_cast<const float4*>(reinterpret_cast<const unsigned char*>(base) + byte_off);
 }
+// (u, v) = the task's first group, already loaded (gather_segment fetches it while the previous task is being gathered)
 __device__ __forceinline__ float4 gather_groups(const float* __restrict__ Uj, const img_idx_t* __restrict__ idx4,
-                                                const float4* __restrict__ val4, int g0, int ng) {
+                                                const float4* __restrict__ val4, int g0, int ng, img_idx_t u, float4 v) {
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  img_idx_t u = idx4[g0];
-  float4 v = val4[g0];
   STMP_TC_UNROLL(STMP_TC_GUNROLL)    // 2: +6 % over the rolled loop (A/B on one box: 886 k -> 942 k snapshots/s) -- a task has 2-3 groups on average,
   for (int g = 1; g <= ng; ++g) {    // the loop branch and its convergence barrier were 10 % of the issued instructions
     const img_idx_t un = idx4[g0 + g];     // (one spare group at the end of the arrays)
@@ -178,6 +180,10 @@ __device__ __forceinline__ float4 gather_groups(const float* __restrict__ Uj, co
     v = vn;
   }
   return acc;
+}
+__device__ __forceinline__ float4 gather_groups(const float* __restrict__ Uj, const img_idx_t* __restrict__ idx4,
+                                                const float4* __restrict__ val4, int g0, int ng) {
+  return gather_groups(Uj, idx4, val4, g0, ng, idx4[g0], val4[g0]);
 }
 
 // Step anatomy (all 16 warps; T_k = MMA row tile k = rows [128k, 128k+128)):
@@ -331,6 +337,25 @@ __global__ void __launch_bounds__(512, 1) k_dcrnn_seq_tc(const TcParams p) {
     unsigned char* dh = a_hi + (op ? TC_PANEL_A : 0);
     unsigned char* dl = a_lo + (op ? TC_PANEL_A : 0);
     const int kcol = (op ? 0 : 32) + 4 * j;
+#if STMP_TC_PREFETCH
+    // the next task's descriptor and first edge group are fetched while the current task is gathered: the chain descriptor -> group ->
+    // feature rows (three dependent shared-memory latencies per task) is taken off the critical path
+    uint32_t d = wc > 0 ? s_wt[ws * 4 + quarter] : kImgNoTask;
+    int g0 = d == kImgNoTask ? 0 : (int)(d >> 16);
+    img_idx_t u0 = s_idx[g0];
+    float4 v0 = s_val[g0];
+    for (int i = 0; i < wc; ++i) {
+      const uint32_t dn = i + 1 < wc ? s_wt[(ws + i + 1) * 4 + quarter] : kImgNoTask;
+      const int g0n = dn == kImgNoTask ? 0 : (int)(dn >> 16);
+      const img_idx_t un0 = s_idx[g0n];
+      const float4 vn0 = s_val[g0n];
+      if (d != kImgNoTask) {
+        const float4 acc = gather_groups(Uj, s_idx, s_val, g0, (int)((d >> 9) & 0x7f), u0, v0);
+        store_split4(dh, dl, (int)(d & 0xff), kcol, acc);
+      }
+      d = dn; g0 = g0n; u0 = un0; v0 = vn0;
+    }
+#else
     for (int i = 0; i < wc; ++i) {
       const uint32_t d = s_wt[(ws + i) * 4 + quarter];
       if (d != kImgNoTask) {
@@ -338,6 +363,7 @@ __global__ void __launch_bounds__(512, 1) k_dcrnn_seq_tc(const TcParams p) {
         store_split4(dh, dl, (int)(d & 0xff), kcol, acc);
       }
     }
+#endif
   };
   // One gather round.  tid 0 issues every MMA: the static group (H | X k-steps) of both tiles right away (the block barrier in front of
   // the round ordered those operand stores), tile 0's P_o / P_i groups behind the barrier that closes tile 0's tasks -- they run on the

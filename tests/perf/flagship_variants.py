@@ -11,9 +11,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 LIBDIR = os.path.join(ROOT, "pytorch_geometric_temporal_b200", "lib")
 VARIANTS = {
-    "off16": ["-DSTMP_IMG_OFF16=1"],
-    "gu1": ["-DSTMP_TC_GUNROLL=1"],
-    "gu4": ["-DSTMP_TC_GUNROLL=4"],
+    "pf": ["-DSTMP_TC_PREFETCH=1"],
+    "pf_gu1": ["-DSTMP_TC_PREFETCH=1", "-DSTMP_TC_GUNROLL=1"],
 }
 
 if sys.argv[1] == "build":
